@@ -1,0 +1,98 @@
+/* libobman_b200.so - C ABI of the B200-native obman_train hot path (sm_100a only).
+ *
+ * The reference (hassony2/obman_train) is pure Python: it has no FFI/plugin layer, every device op is
+ * an ATen/cuDNN/cuBLAS call chain.  Each entry point below replaces one such chain and
+ * is what a maintainer would bind from Python (ctypes stub in INTEGRATION.md).  Conventions:
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller (inputs, outputs and
+ *     workspaces); the library allocates nothing and keeps no reference after return;
+ *   - `stream` is the caller's cudaStream_t (as void*); all work is enqueued asynchronously on it;
+ *   - return 0 on success, a negative code on failure (OBMAN_ERR_*), message via obman_get_last_error();
+ *   - tensors are dense row-major fp32 unless stated; point clouds are (B, P, 3) xyz-interleaved,
+ *     geometry in millimetres, like the reference's public layouts.
+ */
+#ifndef OBMAN_B200_H_
+#define OBMAN_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OBMAN_OK 0
+#define OBMAN_ERR_BAD_ARG -1
+#define OBMAN_ERR_CUDA -2
+#define OBMAN_ERR_UNSUPPORTED -3
+#define OBMAN_ERR_DRIVER -4
+
+int obman_version(void);
+const char* obman_get_last_error(void);
+/* 0 when the current device is a Blackwell sm_10x part. */
+int obman_device_ok(void);
+
+/* ---- Pairwise nearest neighbours --------------------------------------------------------------
+ * Replaces batch_pairwise_dist + torch.min (mano_train/networks/branches/contactloss.py:60-79,164-166;
+ * atlasutils.py:20-39) without materialising the (B,N,M) matrix.
+ * x (B,N,3), y (B,M,3).  dirs bit0: minx/idxx (B,N) = nearest y for every x; bit1: miny/idxy (B,M). */
+int obman_nn_fwd(const float* x, const float* y, int B, int N, int M, float* minx, int* idxx,
+                 float* miny, int* idxy, int dirs, void* stream);
+
+/* ChamferLoss.forward(preds, gts) -> (loss_1 (B), loss_2 (B))   atlasutils.py:11-18.
+ * min1/idx1 (B,N): nearest gt of every pred; min2/idx2 (B,M): nearest pred of every gt (saved for bwd). */
+int obman_chamfer_fwd(const float* preds, const float* gts, int B, int N, int M, float* loss1,
+                      float* loss2, float* min1, int* idx1, float* min2, int* idx2, void* stream);
+/* Autograd of the above: gloss1/gloss2 (B) -> gpreds (B,N,3) and, if non-null, ggts (B,M,3). */
+int obman_chamfer_bwd(const float* preds, const float* gts, const int* idx1, const int* idx2,
+                      const float* gloss1, const float* gloss2, int B, int N, int M, float* gpreds,
+                      float* ggts, void* stream);
+
+/* ---- Contact loss -------------------------------------------------------------------------------
+ * batch_mesh_contains_points (mano_train/networks/branches/contactutils.py:62-159): hits (B,P) int32 =
+ * number of triangles of the per-sample mesh (obj_verts (B,N,3), faces (F,3) int32 shared by the batch)
+ * crossed by the fixed-direction ray from points (B,P,3); exterior <=> hits even. */
+int obman_raycast_hits(const float* points, const float* obj_verts, const int* faces, int B, int P,
+                       int N, int F, int* hits, void* stream);
+/* compute_contact_loss value/mask stage (contactloss.py:174-307).  modes: 0 dist_sq, 1 dist,
+ * 2 dist_tanh; zones_mode: 0 all, 1 tips (zone_ids = tip ids, zone_ptr = {0,5}), 2 zones (CSR table).
+ * Outputs: attr_mask/rep_mask (B,P) u8, close (B,P,3), anchor (B,P), partial (B,6) workspace,
+ * out[6] = {missed_loss, penetr_loss, max_penetr, mean_penetr, n_attraction, n_repulsion}. */
+int obman_contact_fwd(const float* hand, const float* obj, const float* mins21, const int* idx21,
+                      const int* hits, const int* zone_ids, const int* zone_ptr, int n_zones,
+                      int zones_mode, int B, int P, int N, float contact_thresh, int contact_mode,
+                      float collision_thresh, int collision_mode, unsigned char* attr_mask,
+                      unsigned char* rep_mask, float* close, float* anchor, float* partial,
+                      float* out, void* stream);
+/* Gradients of missed_loss / penetr_loss; target: 0 all, 1 obj, 2 hand (contact_target). */
+int obman_contact_bwd(const float* hand, const float* close, const float* anchor, const int* idx21,
+                      const unsigned char* attr_mask, const unsigned char* rep_mask,
+                      const float* fwd_out, const float* g_missed, const float* g_penetr, int B,
+                      int P, int N, float contact_thresh, int contact_mode, float collision_thresh,
+                      int collision_mode, int target, float* ghand, float* gobj, void* stream);
+
+/* ---- MANO layer -----------------------------------------------------------------------------------
+ * manopth.manolayer.ManoLayer.forward (external; call site manobranch.py:170-182).  Tables:
+ * v_template (V,3), shapedirs (V,3,10), posedirs (V,3,135), weights (V,16),
+ * j_template (16,3) = J_regressor*v_template, j_shapedirs (16,3,10) = J_regressor*shapedirs,
+ * hands_mean (45), comps (ncomps,45), default_betas (10).  pose (B,3+ncomps), betas (B,10) or NULL,
+ * trans (B,3) or NULL (NULL => centre on joint center_idx, -1 for none).
+ * Workspaces (floats): ws_pose_map B*135, ws_gp B*192, ws_tw B*48, ws_betas B*10.
+ * Outputs: verts (B,V,3) mm, joints (B,21,3) mm. */
+int obman_mano_fwd(const float* v_template, const float* shapedirs, const float* posedirs,
+                   const float* weights, const float* j_template, const float* j_shapedirs,
+                   const float* hands_mean, const float* comps, const float* default_betas, int V,
+                   int ncomps, const float* pose, const float* betas, const float* trans, int B,
+                   int side_left, int root_palm, int center_idx, float* ws_pose_map, float* ws_gp,
+                   float* ws_tw, float* ws_betas, float* verts, float* joints, void* stream);
+/* Backward: gverts (B,V,3) / gjoints (B,21,3) (either may be NULL) -> gpose (B,3+ncomps), gbetas (B,10)
+ * (may be NULL).  Extra workspaces (floats): ws_gv B*V*3, ws_gtw B*48, ws_gacc B*337. */
+int obman_mano_bwd(const float* v_template, const float* shapedirs, const float* posedirs,
+                   const float* weights, const float* j_template, const float* j_shapedirs,
+                   const float* hands_mean, const float* comps, const float* default_betas, int V,
+                   int ncomps, const float* pose, const float* betas, int has_trans, int B,
+                   int side_left, int root_palm, int center_idx, const float* ws_pose_map,
+                   const float* ws_gp, const float* ws_betas, const float* gverts,
+                   const float* gjoints, float* ws_gv, float* ws_gtw, float* ws_gacc, float* gpose,
+                   float* gbetas, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBMAN_B200_H_ */

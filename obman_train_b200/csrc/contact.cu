@@ -1,0 +1,314 @@
+// Contact (attraction / repulsion) loss kernels.
+//
+// Replaces, with three fused kernels and no (B, 778*F, 3) temporaries:
+//   batch_mesh_contains_points   mano_train/networks/branches/contactutils.py:62-159   (ray parity)
+//   compute_contact_loss         mano_train/networks/branches/contactloss.py:149-308   (values, masks)
+//   masked_mean_loss             mano_train/networks/branches/contactloss.py:50-57     (batch-global means)
+// The hand->object nearest-vertex search (contactloss.py:164-166) is the shared kernel in nn_pairs.cu.
+#include "common.cuh"
+
+namespace obman {
+
+// ---- ray / triangle parity --------------------------------------------------------------------
+constexpr int RC_THREADS = 256;
+constexpr int RC_CHUNK = 512;  // triangles per smem stage: 4 float4 each = 32 KB
+
+// Fixed ray direction and tolerances of the reference (contactutils.py:65,78,104).
+#define RC_DX 0.4395064455f
+#define RC_DY 0.617598629942f
+#define RC_DZ 0.652231566745f
+#define RC_TOL 0.0000001f
+#define RC_DET_EPS 0.00000001f
+
+__global__ void __launch_bounds__(RC_THREADS)
+raycast_kernel(const float* __restrict__ pts, const float* __restrict__ obj,
+               const int* __restrict__ faces, int P, int N, int F, int f_per_split,
+               int* __restrict__ hits) {
+  __shared__ float4 sA[RC_CHUNK];  // v0.xyz, invdet
+  __shared__ float4 sB[RC_CHUNK];  // e1.xyz, parallel flag
+  __shared__ float4 sC[RC_CHUNK];  // e2.xyz
+  __shared__ float4 sD[RC_CHUNK];  // pvec.xyz
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * RC_THREADS + threadIdx.x;
+  const int f_begin = blockIdx.z * f_per_split;
+  const int f_end = min(F, f_begin + f_per_split);
+  const float* __restrict__ ob = obj + (size_t)b * N * 3;
+  float px = 0.f, py = 0.f, pz = 0.f;
+  if (p < P) {
+    const float* q = pts + ((size_t)b * P + p) * 3;
+    px = q[0]; py = q[1]; pz = q[2];
+  }
+  int count = 0;
+  for (int f0 = f_begin; f0 < f_end; f0 += RC_CHUNK) {
+    const int n = min(RC_CHUNK, f_end - f0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += RC_THREADS) {
+      const int* fc = faces + (size_t)(f0 + i) * 3;
+      const float* a = ob + 3 * fc[0];
+      const float* bb = ob + 3 * fc[1];
+      const float* c = ob + 3 * fc[2];
+      const float v0x = a[0], v0y = a[1], v0z = a[2];
+      const float e1x = bb[0] - v0x, e1y = bb[1] - v0y, e1z = bb[2] - v0z;
+      const float e2x = c[0] - v0x, e2y = c[1] - v0y, e2z = c[2] - v0z;
+      // pvec = dir x e2
+      const float pvx = RC_DY * e2z - RC_DZ * e2y;
+      const float pvy = RC_DZ * e2x - RC_DX * e2z;
+      const float pvz = RC_DX * e2y - RC_DY * e2x;
+      const float det = e1x * pvx + e1y * pvy + e1z * pvz;
+      const float invdet = 1.0f / (det + RC_DET_EPS);
+      sA[i] = make_float4(v0x, v0y, v0z, invdet);
+      sB[i] = make_float4(e1x, e1y, e1z, fabsf(det) < RC_TOL ? 1.f : 0.f);
+      sC[i] = make_float4(e2x, e2y, e2z, 0.f);
+      sD[i] = make_float4(pvx, pvy, pvz, 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+      const float4 A = sA[i], Bv = sB[i], C = sC[i], D = sD[i];
+      const float tx = px - A.x, ty = py - A.y, tz = pz - A.z;
+      const float u = (tx * D.x + ty * D.y + tz * D.z) * A.w;
+      const float qx = ty * Bv.z - tz * Bv.y;
+      const float qy = tz * Bv.x - tx * Bv.z;
+      const float qz = tx * Bv.y - ty * Bv.x;
+      const float v = (RC_DX * qx + RC_DY * qy + RC_DZ * qz) * A.w;
+      const float t = (C.x * qx + C.y * qy + C.z * qz) * A.w;
+      const bool hit = (u > 0.f) & (u < 1.f) & (v > 0.f) & (u + v < 1.f) & (t >= RC_TOL) &
+                       (Bv.w == 0.f);
+      count += hit ? 1 : 0;
+    }
+  }
+  if (p < P && count) atomicAdd(hits + (size_t)b * P + p, count);
+}
+
+// ---- per-vertex values, masks, per-sample partial sums ------------------------------------------
+enum { MODE_DIST_SQ = 0, MODE_DIST = 1, MODE_DIST_TANH = 2 };
+enum { ZONES_ALL = 0, ZONES_TIPS = 1, ZONES_ZONES = 2 };
+enum { TARGET_ALL = 0, TARGET_OBJ = 1, TARGET_HAND = 2 };
+
+__device__ __forceinline__ float contact_value(int mode, float thresh, float sq, float anchor) {
+  if (mode == MODE_DIST_SQ) return sq;
+  if (mode == MODE_DIST) return anchor;
+  return thresh * tanhf(anchor / thresh);
+}
+// d value / d diff = w * diff
+__device__ __forceinline__ float contact_dweight(int mode, float thresh, float anchor) {
+  if (mode == MODE_DIST_SQ) return 2.f;
+  if (anchor == 0.f) return 0.f;  // torch.norm backward is masked to 0 at the origin
+  if (mode == MODE_DIST) return 1.f / anchor;
+  const float th = tanhf(anchor / thresh);
+  return (1.f - th * th) / anchor;
+}
+
+constexpr int CV_THREADS = 256;
+
+__global__ void __launch_bounds__(CV_THREADS)
+contact_values_kernel(const float* __restrict__ hand, const float* __restrict__ obj,
+                      const float* __restrict__ mins21, const int* __restrict__ idx21,
+                      const int* __restrict__ hits, const int* __restrict__ zone_ids,
+                      const int* __restrict__ zone_ptr, int n_zones, int zones_mode, int P, int N,
+                      float contact_thresh, int contact_mode, float collision_thresh,
+                      int collision_mode, unsigned char* __restrict__ attr_mask,
+                      unsigned char* __restrict__ rep_mask, float* __restrict__ close,
+                      float* __restrict__ anchor_out, float* __restrict__ partial) {
+  extern __shared__ unsigned char s_match[];  // P flags
+  __shared__ float scratch[32];
+  const int b = blockIdx.x;
+  const float* hb = hand + (size_t)b * P * 3;
+  const float* ob = obj + (size_t)b * N * 3;
+  const float* mb = mins21 + (size_t)b * P;
+  const int* ib = idx21 + (size_t)b * P;
+  const int* hc = hits + (size_t)b * P;
+
+  for (int v = threadIdx.x; v < P; v += CV_THREADS) s_match[v] = zones_mode == ZONES_ALL ? 1 : 0;
+  __syncthreads();
+  if (zones_mode == ZONES_TIPS) {
+    for (int i = threadIdx.x; i < zone_ptr[n_zones]; i += CV_THREADS) s_match[zone_ids[i]] = 1;
+  } else if (zones_mode == ZONES_ZONES) {
+    // per zone: the zone vertex with the smallest mins21 (first in list order on ties)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int z = warp; z < n_zones; z += CV_THREADS / 32) {
+      const int beg = zone_ptr[z], end = zone_ptr[z + 1];
+      float bv = 3.0e38f;
+      int bp = 0x7fffffff;
+      for (int i = beg + lane; i < end; i += 32) {
+        float val = mb[zone_ids[i]];
+        if (val < bv) { bv = val; bp = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int op = __shfl_xor_sync(0xffffffffu, bp, o);
+        if (ov < bv || (ov == bv && op < bp)) { bv = ov; bp = op; }
+      }
+      if (lane == 0 && bp != 0x7fffffff) s_match[zone_ids[bp]] = 1;
+    }
+  }
+  __syncthreads();
+
+  float s_av = 0.f, s_ac = 0.f, s_rv = 0.f, s_rc = 0.f, s_pen = 0.f, m_pen = 0.f;
+  for (int v = threadIdx.x; v < P; v += CV_THREADS) {
+    const int j = ib[v];
+    const float cx = ob[3 * j], cy = ob[3 * j + 1], cz = ob[3 * j + 2];
+    const float dx = cx - hb[3 * v], dy = cy - hb[3 * v + 1], dz = cz - hb[3 * v + 2];
+    const float sq = dx * dx + dy * dy + dz * dz;
+    const float anchor = sqrtf(sq);
+    const bool exterior = (hc[v] & 1) == 0;
+    bool below = true;
+    if (contact_mode == MODE_DIST_SQ) below = mb[v] < contact_thresh * contact_thresh;
+    else if (contact_mode == MODE_DIST) below = mb[v] < contact_thresh;  // reference quirk kept
+    const bool attr = below && exterior && s_match[v];
+    const bool rep = !exterior;
+    const size_t o = (size_t)b * P + v;
+    attr_mask[o] = attr;
+    rep_mask[o] = rep;
+    close[3 * o] = cx; close[3 * o + 1] = cy; close[3 * o + 2] = cz;
+    anchor_out[o] = anchor;
+    if (attr) { s_av += contact_value(contact_mode, contact_thresh, sq, anchor); s_ac += 1.f; }
+    if (rep) {
+      s_rv += contact_value(collision_mode, collision_thresh, sq, anchor);
+      s_rc += 1.f;
+      s_pen += anchor;
+      m_pen = fmaxf(m_pen, anchor);
+    }
+  }
+  float r;
+  r = block_sum(s_av, scratch); if (threadIdx.x == 0) partial[b * 6 + 0] = r;
+  r = block_sum(s_ac, scratch); if (threadIdx.x == 0) partial[b * 6 + 1] = r;
+  r = block_sum(s_rv, scratch); if (threadIdx.x == 0) partial[b * 6 + 2] = r;
+  r = block_sum(s_rc, scratch); if (threadIdx.x == 0) partial[b * 6 + 3] = r;
+  r = block_sum(s_pen, scratch); if (threadIdx.x == 0) partial[b * 6 + 4] = r / (float)P;
+  // block max
+  m_pen = warp_max(m_pen);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = m_pen;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int w = 0; w < CV_THREADS / 32; ++w) m = fmaxf(m, scratch[w]);
+    partial[b * 6 + 5] = m;
+  }
+}
+
+// out[0]=missed_loss out[1]=penetr_loss out[2]=max_penetr out[3]=mean_penetr
+// out[4]=#attraction verts out[5]=#repulsion verts    (batch-global, fixed summation order)
+__global__ void __launch_bounds__(256)
+contact_finalize_kernel(const float* __restrict__ partial, int B, float* __restrict__ out) {
+  __shared__ float scratch[32];
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int b = threadIdx.x; b < B; b += blockDim.x)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) acc[k] += partial[b * 6 + k];
+  float tot[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) tot[k] = block_sum(acc[k], scratch);
+  if (threadIdx.x == 0) {
+    out[0] = tot[1] > 0.f ? tot[0] / tot[1] : 0.f;
+    out[1] = tot[3] > 0.f ? tot[2] / tot[3] : 0.f;
+    out[2] = tot[5] / (float)B;
+    out[3] = tot[4] / (float)B;
+    out[4] = tot[1];
+    out[5] = tot[3];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+contact_bwd_kernel(const float* __restrict__ hand, const float* __restrict__ close,
+                   const float* __restrict__ anchor, const int* __restrict__ idx21,
+                   const unsigned char* __restrict__ attr_mask,
+                   const unsigned char* __restrict__ rep_mask, const float* __restrict__ fwd_out,
+                   const float* __restrict__ g_missed, const float* __restrict__ g_penetr, int B,
+                   int P, int N, float contact_thresh, int contact_mode, float collision_thresh,
+                   int collision_mode, int target, float* __restrict__ ghand,
+                   float* __restrict__ gobj) {
+  const size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (size_t)B * P) return;
+  const int b = (int)(o / P);
+  const float n_attr = fwd_out[4], n_rep = fwd_out[5];
+  float w = 0.f;
+  const float a = anchor[o];
+  if (attr_mask[o] && n_attr > 0.f)
+    w += g_missed[0] / n_attr * contact_dweight(contact_mode, contact_thresh, a);
+  if (rep_mask[o] && n_rep > 0.f)
+    w += g_penetr[0] / n_rep * contact_dweight(collision_mode, collision_thresh, a);
+  float gd[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) gd[c] = w * (close[3 * o + c] - hand[3 * o + c]);
+  if (ghand) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ghand[3 * o + c] = target == TARGET_OBJ ? 0.f : -gd[c];
+  }
+  if (gobj && target != TARGET_HAND && w != 0.f) {
+    float* g = gobj + ((size_t)b * N + idx21[o]) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(g + c, gd[c]);
+  }
+}
+
+}  // namespace obman
+
+using namespace obman;
+
+extern "C" int obman_raycast_hits(const float* points, const float* obj_verts, const int* faces,
+                                  int B, int P, int N, int F, int* hits, void* stream) {
+  OBMAN_REQUIRE(B > 0 && P > 0 && N > 0 && F > 0 && B <= 65535, "obman_raycast_hits: bad sizes");
+  OBMAN_REQUIRE(points && obj_verts && faces && hits, "obman_raycast_hits: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(hits, 0, sizeof(int) * (size_t)B * P, st);
+  const int ptiles = (P + RC_THREADS - 1) / RC_THREADS;
+  // split the triangle list across CTAs until the grid covers ~2 waves
+  int chunks = (F + RC_CHUNK - 1) / RC_CHUNK;
+  int splits = 1;
+  while (splits < chunks && (long long)ptiles * B * splits < 2LL * num_sms()) ++splits;
+  int per = ((chunks + splits - 1) / splits) * RC_CHUNK;
+  splits = (F + per - 1) / per;
+  raycast_kernel<<<dim3(ptiles, B, splits), RC_THREADS, 0, st>>>(points, obj_verts, faces, P, N, F,
+                                                                per, hits);
+  return check_launch("raycast_kernel");
+}
+
+extern "C" int obman_contact_fwd(const float* hand, const float* obj, const float* mins21,
+                                 const int* idx21, const int* hits, const int* zone_ids,
+                                 const int* zone_ptr, int n_zones, int zones_mode, int B, int P,
+                                 int N, float contact_thresh, int contact_mode,
+                                 float collision_thresh, int collision_mode,
+                                 unsigned char* attr_mask, unsigned char* rep_mask, float* close,
+                                 float* anchor, float* partial, float* out, void* stream) {
+  OBMAN_REQUIRE(B > 0 && P > 0 && N > 0 && P <= 32768, "obman_contact_fwd: bad sizes");
+  OBMAN_REQUIRE(hand && obj && mins21 && idx21 && hits && attr_mask && rep_mask && close &&
+                    anchor && partial && out, "obman_contact_fwd: null argument");
+  OBMAN_REQUIRE(contact_mode >= 0 && contact_mode <= 2 && collision_mode >= 0 &&
+                    collision_mode <= 2, "obman_contact_fwd: mode not in [dist_sq|dist|dist_tanh]");
+  OBMAN_REQUIRE(zones_mode >= 0 && zones_mode <= 2, "obman_contact_fwd: zones not in [all|tips|zones]");
+  OBMAN_REQUIRE(zones_mode == ZONES_ALL || (zone_ids && zone_ptr && n_zones > 0),
+                "obman_contact_fwd: zone table required for tips/zones");
+  cudaStream_t st = (cudaStream_t)stream;
+  contact_values_kernel<<<B, CV_THREADS, P, st>>>(hand, obj, mins21, idx21, hits, zone_ids,
+                                                  zone_ptr, n_zones, zones_mode, P, N,
+                                                  contact_thresh, contact_mode, collision_thresh,
+                                                  collision_mode, attr_mask, rep_mask, close,
+                                                  anchor, partial);
+  int rc = check_launch("contact_values_kernel");
+  if (rc) return rc;
+  contact_finalize_kernel<<<1, 256, 0, st>>>(partial, B, out);
+  return check_launch("contact_finalize_kernel");
+}
+
+extern "C" int obman_contact_bwd(const float* hand, const float* close, const float* anchor,
+                                 const int* idx21, const unsigned char* attr_mask,
+                                 const unsigned char* rep_mask, const float* fwd_out,
+                                 const float* g_missed, const float* g_penetr, int B, int P, int N,
+                                 float contact_thresh, int contact_mode, float collision_thresh,
+                                 int collision_mode, int target, float* ghand, float* gobj,
+                                 void* stream) {
+  OBMAN_REQUIRE(B > 0 && P > 0 && N > 0, "obman_contact_bwd: bad sizes");
+  OBMAN_REQUIRE(hand && close && anchor && idx21 && attr_mask && rep_mask && fwd_out && g_missed &&
+                    g_penetr, "obman_contact_bwd: null argument");
+  OBMAN_REQUIRE(target >= 0 && target <= 2, "obman_contact_bwd: contact_target not in [all|obj|hand]");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gobj) cudaMemsetAsync(gobj, 0, sizeof(float) * (size_t)B * N * 3, st);
+  size_t total = (size_t)B * P;
+  contact_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+      hand, close, anchor, idx21, attr_mask, rep_mask, fwd_out, g_missed, g_penetr, B, P, N,
+      contact_thresh, contact_mode, collision_thresh, collision_mode, target, ghand, gobj);
+  return check_launch("contact_bwd_kernel");
+}

@@ -92,6 +92,38 @@ int obman_mano_bwd(const float* v_template, const float* shapedirs, const float*
                    const float* gjoints, float* ws_gv, float* ws_gtw, float* ws_gacc, float* gpose,
                    float* gbetas, void* stream);
 
+/* ---- Dense contractions on tcgen05 tensor cores (TF32 inputs, FP32 accumulation in TMEM, TMA feeds) ------
+ * passes = 1: plain TF32; passes = 3: 3xTF32 split (hi*hi + lo*hi + hi*lo), fp32-equivalent accuracy.
+ *
+ * obman_gemm: out[M,N] = epilogue(alpha * A[M,K] * W[N,K]^T); replaces nn.Linear / Conv1d(k=1) calls
+ * (manobranch.py:124-147, atlasbranch.py:44-61, atlasutils.py:65-75).  Row-major, leading dimensions in
+ * elements (lda, ldw multiples of 4; A, W 16-byte aligned).  epilogue: + bias[N] + addend[M,N] (ldo),
+ * ReLU, zero where mask_src[M,N] (ldo) <= 0, then store or atomicAdd (accumulate). */
+int obman_gemm(const float* A, long long lda, const float* W, long long ldw, int M, int N, int K,
+               float* out, long long ldo, const float* bias, const float* addend,
+               const float* mask_src, float alpha, int relu, int accumulate, int passes, void* stream);
+
+/* obman_conv_nhwc: NHWC convolution as implicit GEMM; forward and data-gradient of nn.Conv2d
+ * (mano_train/networks/bases/resnet.py:19-23,38-54,110-152) share it.  x (n_img,h_in,w_in,c_in),
+ * c_in % 4 == 0; w (c_out, w_slots*c_in), tap t uses weight slot tap_wslot[t] (NULL: t) and reads input
+ * pixel (h + tap_dh[t], w + tap_dw[t]) of view tap_phase[t] = ph*2+pw of x[:, ph::in_step, pw::in_step]
+ * (zero outside the view).  out is written at n*o_sN + h*o_sH + w*o_sW + c (elements) for h < h_out,
+ * w < w_out; bias[c_out], addend / mask_src indexed like out (NULL to disable), relu flag. */
+int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, int c_in, int in_step,
+                    const float* w, int c_out, int w_slots, int num_taps, const int* tap_dh,
+                    const int* tap_dw, const int* tap_phase, const int* tap_wslot, float* out,
+                    int h_out, int w_out, long long o_sN, long long o_sH, long long o_sW,
+                    const float* bias, const float* addend, const float* mask_src, int relu,
+                    int passes, void* stream);
+
+/* obman_wgrad_nhwc: dw[co, slot(t)*c_in + ci] = sum_{n,h,w} dy[n,h,w,co] * xview_t[n, h+dh, w+dw, ci];
+ * weight gradient of the convolution above and (h = 1) of obman_gemm.  c_out, c_in multiples of 32.
+ * dw (c_out, w_slots*c_in) is overwritten. */
+int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out, int c_out, const float* x,
+                     int h_in, int w_in, int c_in, int in_step, int num_taps, const int* tap_dh,
+                     const int* tap_dw, const int* tap_phase, const int* tap_wslot, float* dw,
+                     int w_slots, int passes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

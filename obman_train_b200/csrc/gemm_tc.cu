@@ -1,0 +1,562 @@
+// tcgen05 / TMA implicit-GEMM kernel for every dense contraction of the hot path:
+//   * ResNet-18 convolutions, fprop and dgrad   (mano_train/networks/bases/resnet.py:25-54,154-188)
+//   * AtlasNet point-MLP 1x1 convs              (mano_train/networks/branches/atlasutils.py:65-75)
+//   * ManoBranch / AtlasBranch linear layers    (manobranch.py:124-147, atlasbranch.py:44-61)
+//   * weight gradients of all of the above (reduction over pixels: MN-major operands, MODE 1)
+//
+// D[128 x BN] (fp32, TMEM) = sum over taps and 32-wide K blocks of A_tile[128 x 32] * B_tile[BN x 32]^T
+//   A: activations. plain mode: row-major (M, K) matrix, 2-D TMA box {32, 128};
+//      spatial mode: NHWC tensor, 4-D TMA box {32 ch, TW, TH, TN} at (c, w0+dw, h0+dh, n0) - the
+//      3x3 / strided taps are just shifted boxes, image borders come from TMA zero fill.
+//   B: weights (N, K_total) K-major, 2-D TMA box {32, BN}.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2-5 = fp32->(tf32 hi, tf32 lo) splitters during the main loop, then TMEM->register epilogue.
+// Precision: PASSES=1 is plain TF32; PASSES=3 accumulates hi*hi + lo*hi + hi*lo ("3xTF32"), which
+// carries ~22 mantissa bits and is what the parity tests and the headline benchmark use.
+#include "common.cuh"
+#include "sm100.cuh"
+#include "tensormap.cuh"
+
+namespace obman {
+using namespace sm100;
+
+constexpr int BM = 128;
+constexpr int BK = 32;                  // fp32 elements per 128-byte swizzle row
+constexpr int A_TILE_BYTES = BM * BK * 4;
+constexpr int GEMM_THREADS = 192;
+constexpr int MAX_TAPS = 16;
+
+struct alignas(64) GemmMaps {
+  CUtensorMap a[5];   // MODE 0: up to 4 phase views of the activations.  MODE 1: a[0] = dY, a[1..4] = x views
+  CUtensorMap b;      // MODE 0: weights
+};
+
+struct GemmProgram {
+  int spatial;          // 0: A is a (M,K) matrix; 1: A is NHWC with shifted-box taps
+  int num_taps;
+  int kblocks;          // 32-wide K blocks per tap
+  int tap_dh[MAX_TAPS], tap_dw[MAX_TAPS], tap_map[MAX_TAPS], tap_bk[MAX_TAPS];
+  int M, N;             // plain: rows / cols of D.  spatial: N = output channels
+  // spatial output tiling: tile = TN images x TH rows x TW cols (TN*TH*TW == 128)
+  int TN, TH, TW, tiles_h, tiles_w;
+  int n_img, h_out, w_out;
+  int a_stride;         // input coordinate = output coordinate * a_stride + tap offset (phase maps: 1)
+  // wgrad (MODE 1): K runs over blocks of 32 output pixels (kTN x kTH x kTW), split over gridDim.z
+  int kTN, kTH, kTW, kblocks_n, kblocks_h, kblocks_w;
+  int n_tiles;          // column tiles (blockIdx.x = m_tile * n_tiles + n_tile)
+};
+
+struct GemmEpilogue {
+  float* out;
+  const float* bias;      // per output column, nullable
+  const float* addend;    // same indexing as out, nullable
+  const float* mask_src;  // same indexing as out, nullable: out = mask_src > 0 ? v : 0
+  float alpha;            // v = alpha * acc + bias + addend
+  int relu;
+  int accumulate;         // atomicAdd into out instead of store
+  // row -> element offset: plain: row * ld ; spatial: n*sN + h*sH + w*sW  (+ column)
+  long long ld, sN, sH, sW;
+  long long col_base;     // added to the column offset (wgrad: tap slot * c_in)
+};
+
+template <int BN, int PASSES>
+struct GemmCfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = (A_TILE_BYTES + B_TILE_BYTES) * (PASSES == 3 ? 2 : 1);
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int PASSES, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, const GemmEpilogue epi) {
+  using Cfg = GemmCfg<BN, PASSES>;
+  constexpr int S = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;            // [S] TMA bytes landed
+  uint64_t* conv = bars + S;        // [S] hi/lo split done (PASSES==3)
+  uint64_t* empty = bars + 2 * S;   // [S] MMAs reading the stage retired
+  uint64_t* accum = bars + 3 * S;   // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  int n_iters = prog.num_taps * prog.kblocks;
+
+  // tile coordinates
+  int m0 = 0, n_img0 = 0, h0 = 0, w0 = 0;
+  int n0 = blockIdx.y * BN;
+  int pb_begin = 0, wg_tap = 0;
+  if (MODE == 1) {
+    m0 = (blockIdx.x / prog.n_tiles) * BM;
+    n0 = (blockIdx.x % prog.n_tiles) * BN;
+    wg_tap = blockIdx.y;
+    const int total = prog.kblocks_n * prog.kblocks_h * prog.kblocks_w;
+    const int per = (total + gridDim.z - 1) / gridDim.z;
+    pb_begin = blockIdx.z * per;
+    n_iters = min(total, pb_begin + per) - pb_begin;
+    if (n_iters <= 0) return;  // uniform for the whole CTA, before any barrier / TMEM allocation
+  } else if (prog.spatial) {
+    int t = blockIdx.x;
+    const int tw_i = t % prog.tiles_w; t /= prog.tiles_w;
+    const int th_i = t % prog.tiles_h; t /= prog.tiles_h;
+    n_img0 = t * prog.TN;
+    h0 = th_i * prog.TH;
+    w0 = tw_i * prog.TW;
+  } else {
+    m0 = blockIdx.x * BM;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto stage_a = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
+  auto stage_b = [&](int s) { return smem + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };
+  auto stage_alo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + A_TILE_BYTES + Cfg::B_TILE_BYTES; };
+  auto stage_blo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES; };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.b);
+      tma_prefetch_desc(&maps.a[0]);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], A_TILE_BYTES + Cfg::B_TILE_BYTES);
+        if (MODE == 1) {
+          int pb = pb_begin + it;
+          const int bw = pb % prog.kblocks_w; pb /= prog.kblocks_w;
+          const int bh = pb % prog.kblocks_h; pb /= prog.kblocks_h;
+          const int pw = bw * prog.kTW, ph_ = bh * prog.kTH, pn = pb * prog.kTN;
+          tma_load_5d(stage_a(s), &maps.a[0], &full[s], 0, pw, ph_, pn, m0 / 32);
+          tma_load_5d(stage_b(s), &maps.a[1 + prog.tap_map[wg_tap]], &full[s], 0, pw + prog.tap_dw[wg_tap],
+                      ph_ + prog.tap_dh[wg_tap], pn, n0 / 32);
+          continue;
+        }
+        const int tap = it / prog.kblocks;
+        const int kb = it - tap * prog.kblocks;
+        if (prog.spatial) {
+          tma_load_4d(stage_a(s), &maps.a[prog.tap_map[tap]], &full[s], kb * BK,
+                      w0 * prog.a_stride + prog.tap_dw[tap], h0 * prog.a_stride + prog.tap_dh[tap], n_img0);
+        } else {
+          tma_load_2d(stage_a(s), &maps.a[0], &full[s], kb * BK, m0);
+        }
+        tma_load_2d(stage_b(s), &maps.b, &full[s], prog.tap_bk[tap] + kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = umma_idesc_tf32(BM, BN, MODE, MODE);
+    // K-major: 4 k-steps of 32 bytes inside the 128-byte row; MN-major: 4 k-steps of 8 pixel rows (1024 B),
+    // 32-channel groups 4096 B apart (LBO)
+    constexpr uint32_t KSTEP = MODE == 1 ? 1024 : 32;
+    constexpr uint32_t LBO = MODE == 1 ? 4096 : 16;
+    for (int it = 0; it < n_iters; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (it / S) & 1;
+      mbar_wait(PASSES == 3 ? &conv[s] : &full[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_b(s));
+        const uint32_t a_lo = smem_u32(stage_alo(s)), b_lo = smem_u32(stage_blo(s));
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t da = umma_desc(a_hi + k * KSTEP, LBO, 1024);
+          const uint64_t db = umma_desc(b_hi + k * KSTEP, LBO, 1024);
+          if (PASSES == 3) {
+            const uint64_t dal = umma_desc(a_lo + k * KSTEP, LBO, 1024);
+            const uint64_t dbl = umma_desc(b_lo + k * KSTEP, LBO, 1024);
+            umma_tf32(tmem_base, dal, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(tmem_base, da, dbl, idesc, 1u);
+            umma_tf32(tmem_base, da, db, idesc, 1u);
+          } else {
+            umma_tf32(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[s]);
+        if (it == n_iters - 1) umma_commit(accum);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== splitter (main loop) + epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+    const int tid = threadIdx.x - 64;  // 0..127
+    if (PASSES == 3) {
+      constexpr int A_V4 = A_TILE_BYTES / 16, B_V4 = Cfg::B_TILE_BYTES / 16;
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(&full[s], ph);
+        float4* a = reinterpret_cast<float4*>(stage_a(s));
+        float4* alo = reinterpret_cast<float4*>(stage_alo(s));
+        float4* b = reinterpret_cast<float4*>(stage_b(s));
+        float4* blo = reinterpret_cast<float4*>(stage_blo(s));
+#pragma unroll 4
+        for (int i = tid; i < A_V4 + B_V4; i += 128) {
+          float4* src = i < A_V4 ? a + i : b + (i - A_V4);
+          float4* dst = i < A_V4 ? alo + i : blo + (i - A_V4);
+          float4 v = *src, h, l;
+          h.x = to_tf32_rna(v.x); h.y = to_tf32_rna(v.y); h.z = to_tf32_rna(v.z); h.w = to_tf32_rna(v.w);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          *src = h;
+          *dst = l;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&conv[s]);
+      }
+    }
+    // ---- epilogue ----
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row of the tile == TMEM lane
+    bool row_ok;
+    long long row_off;
+    if (MODE == 0 && prog.spatial) {
+      const int tw = r % prog.TW;
+      const int th = (r / prog.TW) % prog.TH;
+      const int tn = r / (prog.TW * prog.TH);
+      const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
+      row_ok = n < prog.n_img && h < prog.h_out && w < prog.w_out;
+      row_off = n * epi.sN + h * epi.sH + w * epi.sW;
+    } else {
+      row_ok = (m0 + r) < prog.M;
+      row_off = (long long)(m0 + r) * epi.ld +
+                (MODE == 1 ? (long long)prog.tap_bk[wg_tap] * prog.N : epi.col_base);
+    }
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
+                          reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0 &&
+                        (row_off & 3) == 0 && !epi.accumulate;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= prog.N) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      const int col0 = n0 + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int col = col0 + j;
+        if (col >= prog.N) break;
+        float x[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[e] = epi.alpha * __uint_as_float(v[j + e]);
+        const bool full4 = (col + 3 < prog.N) && vec_ok && ((col & 3) == 0);
+        if (epi.bias) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (col + e < prog.N) x[e] += __ldg(epi.bias + col + e);
+        }
+        if (full4) {
+          if (epi.addend) {
+            const float4 a4 = *reinterpret_cast<const float4*>(epi.addend + row_off + col);
+            x[0] += a4.x; x[1] += a4.y; x[2] += a4.z; x[3] += a4.w;
+          }
+          if (epi.relu) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+          }
+          if (epi.mask_src) {
+            const float4 m4 = *reinterpret_cast<const float4*>(epi.mask_src + row_off + col);
+            x[0] = m4.x > 0.f ? x[0] : 0.f; x[1] = m4.y > 0.f ? x[1] : 0.f;
+            x[2] = m4.z > 0.f ? x[2] : 0.f; x[3] = m4.w > 0.f ? x[3] : 0.f;
+          }
+          *reinterpret_cast<float4*>(epi.out + row_off + col) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (col + e >= prog.N) break;
+            float y = x[e];
+            if (epi.addend) y += epi.addend[row_off + col + e];
+            if (epi.relu) y = fmaxf(y, 0.f);
+            if (epi.mask_src) y = epi.mask_src[row_off + col + e] > 0.f ? y : 0.f;
+            if (epi.accumulate) atomicAdd(epi.out + row_off + col + e, y);
+            else epi.out[row_off + col + e] = y;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+template <int BN, int PASSES, int MODE>
+static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const GemmEpilogue& epi, dim3 grid,
+                       cudaStream_t st) {
+  using Cfg = GemmCfg<BN, PASSES>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: cudaFuncSetAttribute(%d bytes) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return OBMAN_ERR_CUDA;
+    }
+    attr = true;
+  }
+  gemm_tc_kernel<BN, PASSES, MODE><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
+  return check_launch("gemm_tc_kernel");
+}
+
+template <int MODE>
+static int dispatch_gemm(int BN, int passes, const GemmMaps& maps, const GemmProgram& prog,
+                         const GemmEpilogue& epi, dim3 grid, cudaStream_t st) {
+#define OBMAN_GEMM_CASE(bn)                                                   \
+  if (BN == bn) {                                                             \
+    return passes == 3 ? launch_gemm<bn, 3, MODE>(maps, prog, epi, grid, st)  \
+                       : launch_gemm<bn, 1, MODE>(maps, prog, epi, grid, st); \
+  }
+  OBMAN_GEMM_CASE(64)
+  OBMAN_GEMM_CASE(128)
+  OBMAN_GEMM_CASE(256)
+#undef OBMAN_GEMM_CASE
+  set_error("gemm_tc: unsupported BN=%d", BN);
+  return OBMAN_ERR_UNSUPPORTED;
+}
+
+static int pick_bn(int N, long long m_tiles) {
+  // widest tile that does not waste more than half of its columns; prefer filling the SMs
+  if (N > 128 && m_tiles * ((N + 255) / 256) >= num_sms()) return 256;
+  if (N > 64) return 128;
+  return 64;
+}
+
+}  // namespace obman
+
+using namespace obman;
+
+// out[M,N] = epilogue(alpha * A[M,K] * W[N,K]^T)   (row-major, leading dimensions in elements)
+// epilogue: + bias[N] + addend[M,N] ; relu ; mask by (mask_src > 0) ; store or atomicAdd.
+extern "C" int obman_gemm(const float* A, long long lda, const float* W, long long ldw, int M, int N,
+                          int K, float* out, long long ldo, const float* bias, const float* addend,
+                          const float* mask_src, float alpha, int relu, int accumulate, int passes,
+                          void* stream) {
+  OBMAN_REQUIRE(A && W && out, "obman_gemm: null argument");
+  OBMAN_REQUIRE(M > 0 && N > 0 && K > 0, "obman_gemm: bad sizes M=%d N=%d K=%d", M, N, K);
+  OBMAN_REQUIRE(passes == 1 || passes == 3, "obman_gemm: passes must be 1 (tf32) or 3 (3xtf32)");
+  OBMAN_REQUIRE(lda % 4 == 0 && ldw % 4 == 0, "obman_gemm: lda/ldw must be multiples of 4 floats (TMA 16-byte stride)");
+  OBMAN_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "obman_gemm: A/W must be 16-byte aligned");
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const long long m_tiles = (M + BM - 1) / BM;
+  const int BN = pick_bn(N, m_tiles);
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)lda * 4};
+    uint32_t box[2] = {BK, BM};
+    int rc = make_tensor_map(&maps.a[0], A, 2, dims, strides, box);
+    if (rc) return rc;
+    uint64_t dimsb[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t stridesb[1] = {(uint64_t)ldw * 4};
+    uint32_t boxb[2] = {BK, (uint32_t)BN};
+    rc = make_tensor_map(&maps.b, W, 2, dimsb, stridesb, boxb);
+    if (rc) return rc;
+  }
+  GemmProgram prog;
+  memset(&prog, 0, sizeof(prog));
+  prog.spatial = 0;
+  prog.num_taps = 1;
+  prog.kblocks = (K + BK - 1) / BK;
+  prog.M = M;
+  prog.N = N;
+  GemmEpilogue epi;
+  memset(&epi, 0, sizeof(epi));
+  epi.out = out; epi.bias = bias; epi.addend = addend; epi.mask_src = mask_src;
+  epi.alpha = alpha; epi.relu = relu; epi.accumulate = accumulate; epi.ld = ldo;
+  dim3 grid((unsigned)m_tiles, (unsigned)((N + BN - 1) / BN), 1);
+  return dispatch_gemm<0>(BN, passes, maps, prog, epi, grid, (cudaStream_t)stream);
+}
+
+// NHWC convolution as implicit GEMM (forward and data-gradient share this entry point).
+//   x    : (n_img, h_in, w_in, c_in) NHWC, c_in % 4 == 0
+//   w    : (c_out, w_slots * c_in) K-major; tap t reads weight slot tap_wslot[t] (default t), i.e.
+//          columns [slot*c_in, (slot+1)*c_in)
+//   taps : for tap t the input pixel of output (h, w) is (h*stride_eff + dh[t], w*stride_eff + dw[t])
+//          read through phase view `tap_phase[t]` (ph*2+pw) when in_step == 2, i.e. the input is viewed
+//          as x[:, ph::2, pw::2, :] and stride_eff == 1; with in_step == 1 there is a single view.
+//   out  : written at element offset n*o_sN + h*o_sH + w*o_sW + c   (lets dgrad write strided phases)
+extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, int c_in, int in_step,
+                               const float* w, int c_out, int w_slots, int num_taps, const int* tap_dh,
+                               const int* tap_dw, const int* tap_phase, const int* tap_wslot, float* out,
+                               int h_out, int w_out, long long o_sN, long long o_sH, long long o_sW,
+                               const float* bias, const float* addend, const float* mask_src, int relu,
+                               int passes, void* stream) {
+  OBMAN_REQUIRE(x && w && out && tap_dh && tap_dw, "obman_conv_nhwc: null argument");
+  OBMAN_REQUIRE(n_img > 0 && h_in > 0 && w_in > 0 && c_in > 0 && c_out > 0 && h_out > 0 && w_out > 0,
+                "obman_conv_nhwc: bad sizes");
+  OBMAN_REQUIRE(c_in % 4 == 0, "obman_conv_nhwc: c_in=%d must be a multiple of 4", c_in);
+  OBMAN_REQUIRE(num_taps >= 1 && num_taps <= MAX_TAPS, "obman_conv_nhwc: num_taps=%d out of [1,%d]", num_taps, MAX_TAPS);
+  OBMAN_REQUIRE(in_step == 1 || in_step == 2, "obman_conv_nhwc: in_step must be 1 or 2");
+  OBMAN_REQUIRE(w_slots >= 1, "obman_conv_nhwc: w_slots must be >= 1");
+  OBMAN_REQUIRE(in_step == 1 || (h_in % 2 == 0 && w_in % 2 == 0), "obman_conv_nhwc: phase views need even h_in/w_in");
+  OBMAN_REQUIRE(passes == 1 || passes == 3, "obman_conv_nhwc: passes must be 1 or 3");
+  OBMAN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, "obman_conv_nhwc: x/w must be 16-byte aligned");
+  // output tile shape: TW = largest power of two <= min(w_out, 128) ... keep TN*TH*TW == 128
+  int TW = 1;
+  while (TW * 2 <= w_out && TW * 2 <= 128) TW *= 2;
+  int TH = 1;
+  while (TH * 2 <= h_out && TW * TH * 2 <= 128) TH *= 2;
+  int TN = 128 / (TW * TH);
+  GemmProgram prog;
+  memset(&prog, 0, sizeof(prog));
+  prog.spatial = 1;
+  prog.num_taps = num_taps;
+  prog.kblocks = (c_in + BK - 1) / BK;
+  prog.N = c_out;
+  prog.TN = TN; prog.TH = TH; prog.TW = TW;
+  prog.tiles_h = (h_out + TH - 1) / TH;
+  prog.tiles_w = (w_out + TW - 1) / TW;
+  prog.n_img = n_img; prog.h_out = h_out; prog.w_out = w_out;
+  prog.a_stride = 1;
+  const long long m_tiles = (long long)((n_img + TN - 1) / TN) * prog.tiles_h * prog.tiles_w;
+  const int BN = pick_bn(c_out, m_tiles);
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  bool used[4] = {false, false, false, false};
+  for (int t = 0; t < num_taps; ++t) {
+    const int ph = (in_step == 2 && tap_phase) ? tap_phase[t] : 0;
+    OBMAN_REQUIRE(ph >= 0 && ph < 4, "obman_conv_nhwc: bad tap phase");
+    prog.tap_dh[t] = tap_dh[t];
+    prog.tap_dw[t] = tap_dw[t];
+    prog.tap_map[t] = ph;
+    prog.tap_bk[t] = (tap_wslot ? tap_wslot[t] : t) * c_in;
+    used[ph] = true;
+  }
+  for (int ph = 0; ph < 4; ++ph) {
+    if (!used[ph]) continue;
+    const int py = ph >> 1, px = ph & 1;
+    uint64_t dims[4] = {(uint64_t)c_in, (uint64_t)(w_in / in_step), (uint64_t)(h_in / in_step), (uint64_t)n_img};
+    uint64_t strides[3] = {(uint64_t)c_in * 4 * in_step, (uint64_t)w_in * c_in * 4 * in_step,
+                           (uint64_t)h_in * w_in * c_in * 4};
+    uint32_t box[4] = {BK, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
+    const float* base = x + ((long long)py * w_in + px) * c_in;
+    int rc = make_tensor_map(&maps.a[ph], base, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dimsb[2] = {(uint64_t)w_slots * (uint64_t)c_in, (uint64_t)c_out};
+    uint64_t stridesb[1] = {dimsb[0] * 4};
+    uint32_t boxb[2] = {BK, (uint32_t)BN};
+    int rc = make_tensor_map(&maps.b, w, 2, dimsb, stridesb, boxb);
+    if (rc) return rc;
+  }
+  GemmEpilogue epi;
+  memset(&epi, 0, sizeof(epi));
+  epi.out = out; epi.bias = bias; epi.addend = addend; epi.mask_src = mask_src;
+  epi.alpha = 1.f; epi.relu = relu; epi.accumulate = 0;
+  epi.sN = o_sN; epi.sH = o_sH; epi.sW = o_sW;
+  dim3 grid((unsigned)m_tiles, (unsigned)((c_out + BN - 1) / BN), 1);
+  return dispatch_gemm<0>(BN, passes, maps, prog, epi, grid, (cudaStream_t)stream);
+}
+
+// Weight gradient of the NHWC convolution above (and, with h = 1, of any row-major matrix product):
+//   dw[co, slot(t)*c_in + ci] = sum_{n,h,w} dy[n,h,w,co] * xview_t[n, h + dh[t], w + dw[t], ci]
+// Both operands are read MN-major (channels contiguous, pixels along K) straight from their NHWC
+// layout; the pixel reduction is split over gridDim.z and combined with fp32 atomics.
+// c_out and c_in must be multiples of 32 (pad the channel dimension of the tensors otherwise).
+extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out, int c_out,
+                                const float* x, int h_in, int w_in, int c_in, int in_step, int num_taps,
+                                const int* tap_dh, const int* tap_dw, const int* tap_phase,
+                                const int* tap_wslot, float* dw, int w_slots, int passes, void* stream) {
+  OBMAN_REQUIRE(dy && x && dw && tap_dh && tap_dw, "obman_wgrad_nhwc: null argument");
+  OBMAN_REQUIRE(n_img > 0 && h_out > 0 && w_out > 0 && h_in > 0 && w_in > 0, "obman_wgrad_nhwc: bad sizes");
+  OBMAN_REQUIRE(c_out > 0 && c_in > 0 && c_out % 32 == 0 && c_in % 32 == 0,
+                "obman_wgrad_nhwc: c_out=%d and c_in=%d must be multiples of 32", c_out, c_in);
+  OBMAN_REQUIRE(num_taps >= 1 && num_taps <= MAX_TAPS && w_slots >= 1, "obman_wgrad_nhwc: bad tap count");
+  OBMAN_REQUIRE(in_step == 1 || in_step == 2, "obman_wgrad_nhwc: in_step must be 1 or 2");
+  OBMAN_REQUIRE(in_step == 1 || (h_in % 2 == 0 && w_in % 2 == 0), "obman_wgrad_nhwc: phase views need even h_in/w_in");
+  OBMAN_REQUIRE(passes == 1 || passes == 3, "obman_wgrad_nhwc: passes must be 1 or 3");
+  OBMAN_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0, "obman_wgrad_nhwc: dy/x must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  int kTW = 1;
+  while (kTW * 2 <= w_out && kTW * 2 <= 32) kTW *= 2;
+  int kTH = 1;
+  while (kTH * 2 <= h_out && kTW * kTH * 2 <= 32) kTH *= 2;
+  const int kTN = 32 / (kTW * kTH);
+  GemmProgram prog;
+  memset(&prog, 0, sizeof(prog));
+  prog.num_taps = num_taps;
+  prog.kblocks = 1;
+  prog.M = c_out;
+  prog.N = c_in;
+  prog.kTN = kTN; prog.kTH = kTH; prog.kTW = kTW;
+  prog.kblocks_n = (n_img + kTN - 1) / kTN;
+  prog.kblocks_h = (h_out + kTH - 1) / kTH;
+  prog.kblocks_w = (w_out + kTW - 1) / kTW;
+  const int m_tiles = (c_out + BM - 1) / BM;
+  const int BN = c_in > 128 ? 256 : (c_in > 64 ? 128 : 64);
+  prog.n_tiles = (c_in + BN - 1) / BN;
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  {
+    uint64_t dims[5] = {32, (uint64_t)w_out, (uint64_t)h_out, (uint64_t)n_img, (uint64_t)(c_out / 32)};
+    uint64_t strides[4] = {(uint64_t)c_out * 4, (uint64_t)w_out * c_out * 4, (uint64_t)h_out * w_out * c_out * 4, 128};
+    uint32_t box[5] = {32, (uint32_t)kTW, (uint32_t)kTH, (uint32_t)kTN, 4};
+    int rc = make_tensor_map(&maps.a[0], dy, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  bool used[4] = {false, false, false, false};
+  for (int t = 0; t < num_taps; ++t) {
+    const int ph = (in_step == 2 && tap_phase) ? tap_phase[t] : 0;
+    OBMAN_REQUIRE(ph >= 0 && ph < 4, "obman_wgrad_nhwc: bad tap phase");
+    prog.tap_dh[t] = tap_dh[t];
+    prog.tap_dw[t] = tap_dw[t];
+    prog.tap_map[t] = ph;
+    prog.tap_bk[t] = (tap_wslot ? tap_wslot[t] : t);
+    used[ph] = true;
+  }
+  for (int ph = 0; ph < 4; ++ph) {
+    if (!used[ph]) continue;
+    const int py = ph >> 1, px = ph & 1;
+    uint64_t dims[5] = {32, (uint64_t)(w_in / in_step), (uint64_t)(h_in / in_step), (uint64_t)n_img, (uint64_t)(c_in / 32)};
+    uint64_t strides[4] = {(uint64_t)c_in * 4 * in_step, (uint64_t)w_in * c_in * 4 * in_step,
+                           (uint64_t)h_in * w_in * c_in * 4, 128};
+    uint32_t box[5] = {32, (uint32_t)kTW, (uint32_t)kTH, (uint32_t)kTN, (uint32_t)(BN / 32)};
+    const float* base = x + ((long long)py * w_in + px) * c_in;
+    int rc = make_tensor_map(&maps.a[1 + ph], base, 5, dims, strides, box);
+    if (rc) return rc;
+  }
+  const long long total_blocks = (long long)prog.kblocks_n * prog.kblocks_h * prog.kblocks_w;
+  const long long tiles = (long long)m_tiles * prog.n_tiles * num_taps;
+  long long splits = (2LL * num_sms() + tiles - 1) / tiles;
+  if (splits > total_blocks / 8) splits = total_blocks / 8;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  const long long ld = (long long)w_slots * c_in;
+  if (splits > 1) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)c_out * ld, st);
+  // one launch per tap would need a per-launch col_base; instead gridDim.y = taps and the kernel derives the
+  // slot from tap_bk, so encode col_base = slot * c_in through a per-tap table
+  int rc = OBMAN_OK;
+  GemmEpilogue epi;
+  memset(&epi, 0, sizeof(epi));
+  epi.out = dw;
+  epi.alpha = 1.f;
+  epi.accumulate = splits > 1;
+  epi.ld = ld;
+  epi.col_base = -1;  // marker: column base comes from prog.tap_bk[tap] * N
+  dim3 grid((unsigned)(m_tiles * prog.n_tiles), (unsigned)num_taps, (unsigned)splits);
+  rc = dispatch_gemm<1>(BN, passes, maps, prog, epi, grid, st);
+  return rc;
+}

@@ -1,0 +1,124 @@
+"""Low-level Python entry points of the tcgen05 dense kernels (obman_gemm / obman_conv_nhwc /
+obman_wgrad_nhwc) and the tap tables that express fprop / dgrad / wgrad of a strided, padded
+convolution as shifted-box implicit GEMMs.  Activations are NHWC, weights are (C_out, KH*KW*C_in).
+"""
+import ctypes
+
+import torch
+
+from ._lib import call, ptr, stream_ptr
+
+PASSES = {"tf32": 1, "tf32x3": 3}
+_precision = {"fwd": "tf32x3", "bwd": "tf32x3"}
+
+
+def set_precision(fwd="tf32x3", bwd="tf32x3"):
+    """'tf32x3' (3xTF32 split, fp32-equivalent; default) or 'tf32' (single pass) per direction."""
+    assert fwd in PASSES and bwd in PASSES
+    _precision["fwd"] = fwd
+    _precision["bwd"] = bwd
+
+
+def get_precision():
+    return dict(_precision)
+
+
+def _ints(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def _chk(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise RuntimeError("{}: expected a contiguous CUDA float32 tensor".format(name))
+    return t
+
+
+def gemm(a, w, out=None, bias=None, addend=None, mask_src=None, alpha=1.0, relu=False,
+         accumulate=False, passes=3, n=None, k=None):
+    """out[M,N] = epilogue(alpha * a[M,:K] @ w[:N,:K]^T).  ``a`` / ``w`` may have padded leading
+    dimensions (row stride multiple of 4 floats); ``n`` / ``k`` give the logical sizes."""
+    _chk(a, "a"); _chk(w, "w")
+    M = a.shape[0]
+    K = k if k is not None else a.shape[1]
+    N = n if n is not None else w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    call("obman_gemm", ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, ptr(out), out.stride(0),
+         ptr(bias), ptr(addend), ptr(mask_src), float(alpha), int(relu), int(accumulate), int(passes),
+         stream_ptr())
+    return out
+
+
+# ---- tap tables -------------------------------------------------------------------------------------
+def fprop_taps(ksize, stride, pad):
+    """Taps of y[h,w] = sum_{kh,kw} x[h*stride + kh - pad, w*stride + kw - pad] * W[kh,kw] in the
+    phase-view coordinates of obman_conv_nhwc: returns (dh, dw, phase, wslot, in_step)."""
+    dh, dw, phase, slot = [], [], [], []
+    for kh in range(ksize):
+        for kw in range(ksize):
+            oh, ow = kh - pad, kw - pad
+            if stride == 1:
+                dh.append(oh); dw.append(ow); phase.append(0)
+            else:
+                ph, pw = oh % 2, ow % 2
+                dh.append((oh - ph) // 2); dw.append((ow - pw) // 2); phase.append(ph * 2 + pw)
+            slot.append(kh * ksize + kw)
+    return dh, dw, phase, slot, stride
+
+
+def dgrad_taps(ksize, stride, pad, out_phase=(0, 0)):
+    """Taps of dx[h,w] = sum dy[(h + pad - kh)/stride, (w + pad - kw)/stride] * W[kh,kw] for the output
+    pixels h = stride*i + out_phase[0], w = stride*j + out_phase[1]: (dh, dw, wslot) on the dy grid."""
+    dh, dw, slot = [], [], []
+    for kh in range(ksize):
+        for kw in range(ksize):
+            th, tw = out_phase[0] + pad - kh, out_phase[1] + pad - kw
+            if th % stride or tw % stride:
+                continue
+            dh.append(th // stride); dw.append(tw // stride); slot.append(kh * ksize + kw)
+    return dh, dw, slot
+
+
+def conv_nhwc(x, w, c_out, taps, in_step, out, h_out, w_out, out_strides=None, out_offset=0,
+              bias=None, addend=None, mask_src=None, relu=False, passes=3, w_slots=None):
+    """Raw obman_conv_nhwc call.  x (N,H,W,C) contiguous; w (c_out, slots*C); taps = (dh, dw, phase, slot).
+    ``out`` is any tensor whose storage receives element (n,h,w,c) at out_offset + n*sN + h*sH + w*sW + c."""
+    _chk(x, "x"); _chk(w, "w")
+    n_img, h_in, w_in, c_in = x.shape
+    dh, dw, phase, slot = taps
+    if w_slots is None:
+        w_slots = w.shape[1] // c_in
+    if out_strides is None:
+        out_strides = (h_out * w_out * c_out, w_out * c_out, c_out)
+    esz = 4
+
+    def off(t):
+        return None if t is None else t.data_ptr() + out_offset * esz
+
+    call("obman_conv_nhwc", ptr(x), n_img, h_in, w_in, c_in, int(in_step), ptr(w), int(c_out),
+         int(w_slots), len(dh), _ints(dh), _ints(dw), _ints(phase) if phase is not None else None,
+         _ints(slot), off(out), int(h_out), int(w_out), int(out_strides[0]), int(out_strides[1]),
+         int(out_strides[2]), ptr(bias), off(addend), off(mask_src), int(relu), int(passes),
+         stream_ptr())
+    return out
+
+
+def wgrad_nhwc(dy, x, taps, in_step, dw_out, w_slots, passes=3):
+    """dw_out (c_out, w_slots*c_in) = sum over pixels dy (N,Ho,Wo,c_out) x shifted x (N,H,W,c_in)."""
+    _chk(dy, "dy"); _chk(x, "x"); _chk(dw_out, "dw")
+    n_img, h_out, w_out, c_out = dy.shape
+    _, h_in, w_in, c_in = x.shape
+    dh, dw, phase, slot = taps
+    call("obman_wgrad_nhwc", ptr(dy), n_img, h_out, w_out, c_out, ptr(x), h_in, w_in, c_in,
+         int(in_step), len(dh), _ints(dh), _ints(dw), _ints(phase) if phase is not None else None,
+         _ints(slot), ptr(dw_out), int(w_slots), int(passes), stream_ptr())
+    return dw_out
+
+
+def wgrad_matrix(dy, x, dw_out=None, passes=3):
+    """dw[N,K] = dy[M,N]^T @ x[M,K]; N and K (the padded row lengths) multiples of 32."""
+    M, N = dy.shape
+    K = x.shape[1]
+    if dw_out is None:
+        dw_out = torch.empty((N, K), device=dy.device, dtype=torch.float32)
+    return wgrad_nhwc(dy.view(1, 1, M, N), x.view(1, 1, M, K), ([0], [0], None, [0]), 1, dw_out, 1, passes)

@@ -124,6 +124,37 @@ int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out, int c_out
                      const int* tap_dw, const int* tap_phase, const int* tap_wslot, float* dw,
                      int w_slots, int passes, void* stream);
 
+/* ---- Encoder helpers (bandwidth-bound; mano_train/networks/bases/resnet.py:154-188) -----------------------
+ * obman_stem_pack: x (B,3,H,W) NCHW -> out (B,H/2,W/2,32) NHWC space-to-depth (channel (ph*2+pw)*3+c,
+ * 20 zero channels) so that the 7x7/2 stem runs as a 4x4/1 obman_conv_nhwc. */
+int obman_stem_pack(const float* x, int B, int H, int W, float* out, void* stream);
+/* BatchNorm(eval) folding + weight re-layout, once per step.  w (O,I,KH,KW); gamma/beta/mean/var (O) or NULL
+ * (no BN: beta, if given, is a plain bias).  wf (O, KH*KW*Ip) fprop operand, wft (I, KH*KW*O) dgrad operand
+ * (NULL to skip), shift/scale/rstd (O).  stem=1: (O,3,7,7) filter -> (O, 16*32) space-to-depth layout. */
+int obman_fold_conv(const float* w, const float* gamma, const float* beta, const float* mean,
+                    const float* var, float eps, int O, int I, int KH, int KW, int Ip, int stem,
+                    float* wf, float* wft, float* shift, float* scale, float* rstd, void* stream);
+/* MaxPool2d(3, stride 2, pad 1), NHWC (resnet.py:107): idx (B,H/2,W/2,C) u8 = arg-max window slot. */
+int obman_maxpool_fwd(const float* x, int B, int H, int W, int C, float* out, unsigned char* idx,
+                      void* stream);
+int obman_maxpool_bwd(const float* gout, const unsigned char* idx, int B, int H, int W, int C,
+                      float* gx, void* stream);
+/* x.mean(3).mean(2) (resnet.py:179) on (B,P,C); backward fused with the ReLU mask of x. */
+int obman_meanpool_fwd(const float* x, int B, int P, int C, float* out, void* stream);
+int obman_meanpool_bwd(const float* gout, const float* x, int B, int P, int C, float* gx,
+                       void* stream);
+/* out[c] = sum_r x[r*ld + c]  (bias / BatchNorm-beta gradients). */
+int obman_colsum(const float* x, long long rows, int C, long long ld, float* out, void* stream);
+/* Raw weight gradient dwraw (O, KH*KW*Ip) -> gw (O,I,KH,KW) = scale*dwraw and, with BatchNorm,
+ * ggamma = rstd*(sum_k w*dwraw - mean*gbeta_sum), gbeta = gbeta_sum. */
+int obman_bn_wgrad_finish(const float* dwraw, const float* w, const float* scale, const float* rstd,
+                          const float* mean, const float* gbeta_sum, int O, int I, int KH, int KW,
+                          int Ip, int stem, float* gw, float* ggamma, float* gbeta, void* stream);
+/* Fused torch.optim.Adam step (traineval.py:113-116) on flat fp32 buffers; g is multiplied by grad_scale. */
+int obman_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,341 @@
+// Bandwidth-bound helpers around the tensor-core convolutions of the ResNet-18 encoder
+// (mano_train/networks/bases/resnet.py:154-188) and the parameter update:
+//   stem_pack        NCHW image -> space-to-depth NHWC (2x2 blocks, 12 real + 20 zero channels) so that the
+//                    7x7/2 stem becomes a 4x4/1 shifted-box convolution on the same TMA path as every other conv
+//   fold_conv        BatchNorm(eval) folding + OIHW -> (O, KH*KW*I) / (I, KH*KW*O) re-layout, once per step
+//   maxpool 3x3/2    forward (with arg-max) and backward
+//   meanpool         spatial mean forward; backward fused with the ReLU mask of the last block
+//   colsum           per-channel sums of a (rows, C) tensor (BatchNorm beta / bias gradients)
+//   bn_wgrad_finish  raw weight gradient -> gradients of conv weight (OIHW), gamma, beta
+//   adam             fused Adam step on a flat parameter buffer (torch.optim.Adam semantics, traineval.py:113-116)
+#include "common.cuh"
+
+namespace obman {
+
+// x (B,3,H,W) NCHW  ->  out (B, H/2, W/2, 32): channel (ph*2+pw)*3 + c = x[b, c, 2i+ph, 2j+pw], channels 12..31 = 0
+__global__ void __launch_bounds__(256)
+stem_pack_kernel(const float* __restrict__ x, int B, int H, int W, float* __restrict__ out) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)B * Ho * Wo * 8;  // one float4 (4 channels) per thread
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int q = (int)(t & 7);
+  size_t p = t >> 3;
+  const int j = (int)(p % Wo); p /= Wo;
+  const int i = (int)(p % Ho);
+  const int b = (int)(p / Ho);
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (q < 3) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ch = q * 4 + e;  // 0..11
+      const int ph = ch / 6, pw = (ch / 3) & 1, c = ch % 3;
+      v[e] = __ldg(x + (((size_t)b * 3 + c) * H + (2 * i + ph)) * W + (2 * j + pw));
+    }
+  }
+  reinterpret_cast<float4*>(out)[t] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// Folded weights for one convolution.  w (O,I,KH,KW); scale s[o] = gamma*rsqrt(var+eps) (or 1 without BN).
+//   wf [o][(kh*KW+kw)*Ip + i] = s[o]*w[o,i,kh,kw]        (fprop B operand; Ip = padded input channels)
+//   wft[i][(kh*KW+kw)*O  + o] = s[o]*w[o,i,kh,kw]        (dgrad B operand), i < I only
+//   shift[o] = beta - mean*s ; scale[o] = s ; rstd[o]
+// stem == 1: w is the (64,3,7,7) stem filter, written in the 4x4 x 32-channel space-to-depth layout.
+__global__ void __launch_bounds__(256)
+fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, const float* __restrict__ mean,
+                 const float* __restrict__ var, float eps, int O, int I, int KH, int KW, int Ip,
+                 int stem, float* __restrict__ wf, float* __restrict__ wft, float* __restrict__ shift,
+                 float* __restrict__ scale, float* __restrict__ rstd_out) {
+  const int o = blockIdx.x;
+  float s = 1.f, rs = 1.f;
+  if (gamma) {
+    rs = rsqrtf(var[o] + eps);
+    s = gamma[o] * rs;
+  }
+  if (threadIdx.x == 0) {
+    scale[o] = s;
+    rstd_out[o] = rs;
+    shift[o] = gamma ? beta[o] - mean[o] * s : (beta ? beta[o] : 0.f);
+  }
+  if (stem) {
+    // taps (a,b) in [-2,1]^2 -> slot (a+2)*4 + (b+2); channel (ph*2+pw)*3 + c <-> kh = 2a+ph+3, kw = 2b+pw+3
+    for (int k = threadIdx.x; k < 16 * 32; k += blockDim.x) {
+      const int slot = k >> 5, ch = k & 31;
+      float v = 0.f;
+      if (ch < 12) {
+        const int a = (slot >> 2) - 2, b = (slot & 3) - 2;
+        const int ph = ch / 6, pw = (ch / 3) & 1, c = ch % 3;
+        const int kh = 2 * a + ph + 3, kw = 2 * b + pw + 3;
+        if (kh >= 0 && kh < 7 && kw >= 0 && kw < 7) v = s * w[((o * 3 + c) * 7 + kh) * 7 + kw];
+      }
+      wf[(size_t)o * 512 + k] = v;
+    }
+    return;
+  }
+  const int taps = KH * KW;
+  for (int k = threadIdx.x; k < taps * Ip; k += blockDim.x) {
+    const int t = k / Ip, i = k - t * Ip;
+    float v = 0.f;
+    if (i < I) {
+      v = s * w[((size_t)o * I + i) * taps + t];
+      if (wft) wft[(size_t)i * taps * O + (size_t)t * O + o] = v;
+    }
+    wf[(size_t)o * taps * Ip + k] = v;
+  }
+}
+
+// 3x3 stride-2 pad-1 max pooling, NHWC; idx = winning window position 0..8
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, float* __restrict__ out,
+                   unsigned char* __restrict__ idx) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const size_t total = (size_t)B * Ho * Wo * C4;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c4 = (int)(t % C4);
+  size_t p = t / C4;
+  const int j = (int)(p % Wo); p /= Wo;
+  const int i = (int)(p % Ho);
+  const int b = (int)(p / Ho);
+  float best[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+  int bi[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int h = 2 * i + dy - 1;
+    if (h < 0 || h >= H) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int w = 2 * j + dx - 1;
+      if (w < 0 || w >= W) continue;
+      const float4 v = *reinterpret_cast<const float4*>(x + (((size_t)b * H + h) * W + w) * C + c4 * 4);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (vv[e] > best[e]) { best[e] = vv[e]; bi[e] = dy * 3 + dx; }
+    }
+  }
+  reinterpret_cast<float4*>(out)[t] = make_float4(best[0], best[1], best[2], best[3]);
+  reinterpret_cast<uchar4*>(idx)[t] = make_uchar4(bi[0], bi[1], bi[2], bi[3]);
+}
+
+// gx[b,h,w,c] = sum over the (<= 4) windows that contain (h,w) and whose arg-max is (h,w)
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const float* __restrict__ gout, const unsigned char* __restrict__ idx, int B, int H,
+                   int W, int C, float* __restrict__ gx) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const size_t total = (size_t)B * H * W * C4;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c4 = (int)(t % C4);
+  size_t p = t / C4;
+  const int w = (int)(p % W); p /= W;
+  const int h = (int)(p % H);
+  const int b = (int)(p / H);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = (h + 1) / 2 - 1; i <= (h + 1) / 2; ++i) {
+    if (i < 0 || i >= Ho) continue;
+    const int dy = h - (2 * i - 1);
+    if (dy < 0 || dy > 2) continue;
+    for (int j = (w + 1) / 2 - 1; j <= (w + 1) / 2; ++j) {
+      if (j < 0 || j >= Wo) continue;
+      const int dx = w - (2 * j - 1);
+      if (dx < 0 || dx > 2) continue;
+      const size_t o = (((size_t)b * Ho + i) * Wo + j) * C4 + c4;
+      const uchar4 k = reinterpret_cast<const uchar4*>(idx)[o];
+      const float4 g = reinterpret_cast<const float4*>(gout)[o];
+      const int me = dy * 3 + dx;
+      if (k.x == me) acc[0] += g.x;
+      if (k.y == me) acc[1] += g.y;
+      if (k.z == me) acc[2] += g.z;
+      if (k.w == me) acc[3] += g.w;
+    }
+  }
+  reinterpret_cast<float4*>(gx)[t] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// out[b,c] = mean over P pixels of x[b,p,c]
+__global__ void __launch_bounds__(256)
+meanpool_fwd_kernel(const float* __restrict__ x, int B, int P, int C, float* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * C) return;
+  const int b = t / C, c = t % C;
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += x[((size_t)b * P + p) * C + c];
+  out[t] = s / (float)P;
+}
+
+// gx[b,p,c] = x[b,p,c] > 0 ? gout[b,c] / P : 0     (mean backward fused with the ReLU mask of x)
+__global__ void __launch_bounds__(256)
+meanpool_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x, int B, int P, int C,
+                    float* __restrict__ gx) {
+  const size_t total = (size_t)B * P * C;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  const int b = (int)(t / ((size_t)P * C));
+  gx[t] = x[t] > 0.f ? gout[(size_t)b * C + c] / (float)P : 0.f;
+}
+
+// out[c] (+)= sum_r x[r, c] ; x has row stride ld. grid (col tiles of 32, row chunks); out zero-initialised.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ x, long long rows, int C, long long ld, long long rows_per_block,
+              float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  if (c < C)
+    for (long long r = r0 + ry; r < r1; r += 8) s += x[r * ld + c];
+  red[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += red[k][threadIdx.x & 31];
+    atomicAdd(out + c, tot);
+  }
+}
+
+// dwraw [O][(kh*KW+kw)*Ip + i] -> gw (O,I,KH,KW) = s[o]*dwraw ; ggamma[o] = rstd*(sum_k w*dwraw - mean*gbeta) ; gbeta = colsum
+// stem == 1: dwraw is in the 16-slot x 32-channel space-to-depth layout of the 7x7 stem.
+__global__ void __launch_bounds__(256)
+bn_wgrad_finish_kernel(const float* __restrict__ dwraw, const float* __restrict__ w,
+                       const float* __restrict__ scale, const float* __restrict__ rstd,
+                       const float* __restrict__ mean, const float* __restrict__ gbeta_sum, int O, int I,
+                       int KH, int KW, int Ip, int stem, float* __restrict__ gw,
+                       float* __restrict__ ggamma, float* __restrict__ gbeta) {
+  __shared__ float scratch[32];
+  const int o = blockIdx.x;
+  const float s = scale[o];
+  const int taps = KH * KW;
+  float dot = 0.f;
+  for (int k = threadIdx.x; k < I * taps; k += blockDim.x) {
+    const int i = k / taps, t = k - i * taps;  // OIHW order of this output channel
+    float raw;
+    if (stem) {
+      const int kh = t / 7, kw = t % 7;
+      const int a = (kh - 3) >> 1, ph = (kh - 3) & 1, b = (kw - 3) >> 1, pw = (kw - 3) & 1;
+      raw = dwraw[(size_t)o * 512 + ((a + 2) * 4 + (b + 2)) * 32 + (ph * 2 + pw) * 3 + i];
+    } else {
+      raw = dwraw[(size_t)o * taps * Ip + (size_t)t * Ip + i];
+    }
+    const float wv = w[(size_t)o * I * taps + k];
+    dot = fmaf(wv, raw, dot);
+    gw[(size_t)o * I * taps + k] = s * raw;
+  }
+  dot = block_sum(dot, scratch);
+  if (threadIdx.x == 0 && ggamma) {
+    const float gb = gbeta_sum[o];
+    ggamma[o] = rstd[o] * (dot - mean[o] * gb);
+    gbeta[o] = gb;
+  }
+}
+
+// torch.optim.Adam (no amsgrad, no weight decay unless wd != 0), bias-corrected, on flat buffers.
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+            float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps, float wd,
+            float bc1, float bc2_sqrt, float gscale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float grad = g[i] * gscale;
+  const float pv = p[i];
+  if (wd != 0.f) grad = fmaf(wd, pv, grad);
+  const float mm = beta1 * m[i] + (1.f - beta1) * grad;
+  const float vv = beta2 * v[i] + (1.f - beta2) * grad * grad;
+  m[i] = mm;
+  v[i] = vv;
+  const float denom = sqrtf(vv) / bc2_sqrt + eps;
+  p[i] = pv - (lr / bc1) * (mm / denom);
+}
+
+}  // namespace obman
+
+using namespace obman;
+
+extern "C" int obman_stem_pack(const float* x, int B, int H, int W, float* out, void* stream) {
+  OBMAN_REQUIRE(x && out && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "obman_stem_pack: bad arguments");
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * 8;
+  stem_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, out);
+  return check_launch("stem_pack_kernel");
+}
+
+extern "C" int obman_fold_conv(const float* w, const float* gamma, const float* beta, const float* mean,
+                               const float* var, float eps, int O, int I, int KH, int KW, int Ip, int stem,
+                               float* wf, float* wft, float* shift, float* scale, float* rstd,
+                               void* stream) {
+  OBMAN_REQUIRE(w && wf && shift && scale && rstd && O > 0 && I > 0 && KH > 0 && KW > 0 && Ip >= I,
+                "obman_fold_conv: bad arguments");
+  OBMAN_REQUIRE(!stem || (I == 3 && KH == 7 && KW == 7), "obman_fold_conv: stem layout needs a (O,3,7,7) filter");
+  fold_conv_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(w, gamma, beta, mean, var, eps, O, I, KH, KW, Ip, stem,
+                                                        wf, wft, shift, scale, rstd);
+  return check_launch("fold_conv_kernel");
+}
+
+extern "C" int obman_maxpool_fwd(const float* x, int B, int H, int W, int C, float* out,
+                                 unsigned char* idx, void* stream) {
+  OBMAN_REQUIRE(x && out && idx && B > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "obman_maxpool_fwd: bad arguments");
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 4);
+  maxpool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, out, idx);
+  return check_launch("maxpool_fwd_kernel");
+}
+
+extern "C" int obman_maxpool_bwd(const float* gout, const unsigned char* idx, int B, int H, int W, int C,
+                                 float* gx, void* stream) {
+  OBMAN_REQUIRE(gout && idx && gx && B > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "obman_maxpool_bwd: bad arguments");
+  const size_t total = (size_t)B * H * W * (C / 4);
+  maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gout, idx, B, H, W, C, gx);
+  return check_launch("maxpool_bwd_kernel");
+}
+
+extern "C" int obman_meanpool_fwd(const float* x, int B, int P, int C, float* out, void* stream) {
+  OBMAN_REQUIRE(x && out && B > 0 && P > 0 && C > 0, "obman_meanpool_fwd: bad arguments");
+  meanpool_fwd_kernel<<<(B * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(x, B, P, C, out);
+  return check_launch("meanpool_fwd_kernel");
+}
+
+extern "C" int obman_meanpool_bwd(const float* gout, const float* x, int B, int P, int C, float* gx,
+                                  void* stream) {
+  OBMAN_REQUIRE(gout && x && gx && B > 0 && P > 0 && C > 0, "obman_meanpool_bwd: bad arguments");
+  const size_t total = (size_t)B * P * C;
+  meanpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gout, x, B, P, C, gx);
+  return check_launch("meanpool_bwd_kernel");
+}
+
+extern "C" int obman_colsum(const float* x, long long rows, int C, long long ld, float* out, void* stream) {
+  OBMAN_REQUIRE(x && out && rows > 0 && C > 0 && ld >= C, "obman_colsum: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(out, 0, sizeof(float) * C, st);
+  const int ctiles = (C + 31) / 32;
+  long long chunks = (4LL * num_sms() + ctiles - 1) / ctiles;
+  if (chunks > (rows + 63) / 64) chunks = (rows + 63) / 64;
+  if (chunks < 1) chunks = 1;
+  const long long per = (rows + chunks - 1) / chunks;
+  colsum_kernel<<<dim3(ctiles, (unsigned)((rows + per - 1) / per)), 256, 0, st>>>(x, rows, C, ld, per, out);
+  return check_launch("colsum_kernel");
+}
+
+extern "C" int obman_bn_wgrad_finish(const float* dwraw, const float* w, const float* scale,
+                                     const float* rstd, const float* mean, const float* gbeta_sum, int O,
+                                     int I, int KH, int KW, int Ip, int stem, float* gw, float* ggamma,
+                                     float* gbeta, void* stream) {
+  OBMAN_REQUIRE(dwraw && w && scale && gw && O > 0 && I > 0 && Ip >= I, "obman_bn_wgrad_finish: bad arguments");
+  OBMAN_REQUIRE(!ggamma || (rstd && mean && gbeta_sum && gbeta), "obman_bn_wgrad_finish: BatchNorm outputs need rstd/mean/gbeta_sum");
+  bn_wgrad_finish_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(dwraw, w, scale, rstd, mean, gbeta_sum, O, I, KH,
+                                                              KW, Ip, stem, gw, ggamma, gbeta);
+  return check_launch("bn_wgrad_finish_kernel");
+}
+
+extern "C" int obman_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int step,
+                               float grad_scale, void* stream) {
+  OBMAN_REQUIRE(p && g && m && v && n > 0 && step >= 1, "obman_adam_step: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+  return check_launch("adam_kernel");
+}

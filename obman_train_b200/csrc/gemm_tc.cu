@@ -13,6 +13,8 @@
 // warps 2-5 = fp32->(tf32 hi, tf32 lo) splitters during the main loop, then TMEM->register epilogue.
 // Precision: PASSES=1 is plain TF32; PASSES=3 accumulates hi*hi + lo*hi + hi*lo ("3xTF32"), which
 // carries ~22 mantissa bits and is what the parity tests and the headline benchmark use.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "sm100.cuh"
 #include "tensormap.cuh"
@@ -44,6 +46,7 @@ struct GemmProgram {
   // wgrad (MODE 1): K runs over blocks of 32 output pixels (kTN x kTH x kTW), split over gridDim.z
   int kTN, kTH, kTW, kblocks_n, kblocks_h, kblocks_w;
   int n_tiles;          // column tiles (blockIdx.x = m_tile * n_tiles + n_tile)
+  unsigned mn_lbo, mn_sbo, mn_layout;  // MN-major smem descriptor fields (bytes, bytes, layout type)
 };
 
 struct GemmEpilogue {
@@ -167,10 +170,13 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = umma_idesc_tf32(BM, BN, MODE, MODE);
-    // K-major: 4 k-steps of 32 bytes inside the 128-byte row; MN-major: 4 k-steps of 8 pixel rows (1024 B),
-    // 32-channel groups 4096 B apart (LBO)
+    // K-major: 4 k-steps of 32 bytes inside the 128-byte row (SW128, 8-row groups 1024 B apart).
+    // MN-major (TF32 => SW128 with 32-byte atoms): 4 k-steps of 8 pixel rows (1024 B), 4-row K atoms 512 B
+    // apart (SBO), 32-channel groups 4096 B apart (LBO)
     constexpr uint32_t KSTEP = MODE == 1 ? 1024 : 32;
-    constexpr uint32_t LBO = MODE == 1 ? 4096 : 16;
+    const uint32_t LBO = MODE == 1 ? prog.mn_lbo : 16;
+    const uint32_t SBO = MODE == 1 ? prog.mn_sbo : 1024;
+    const uint32_t LT = MODE == 1 ? prog.mn_layout : 2;
     for (int it = 0; it < n_iters; ++it) {
       const int s = it % S;
       const uint32_t ph = (it / S) & 1;
@@ -181,11 +187,11 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         const uint32_t a_lo = smem_u32(stage_alo(s)), b_lo = smem_u32(stage_blo(s));
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t da = umma_desc(a_hi + k * KSTEP, LBO, 1024);
-          const uint64_t db = umma_desc(b_hi + k * KSTEP, LBO, 1024);
+          const uint64_t da = umma_desc(a_hi + k * KSTEP, LBO, SBO, LT);
+          const uint64_t db = umma_desc(b_hi + k * KSTEP, LBO, SBO, LT);
           if (PASSES == 3) {
-            const uint64_t dal = umma_desc(a_lo + k * KSTEP, LBO, 1024);
-            const uint64_t dbl = umma_desc(b_lo + k * KSTEP, LBO, 1024);
+            const uint64_t dal = umma_desc(a_lo + k * KSTEP, LBO, SBO, LT);
+            const uint64_t dbl = umma_desc(b_lo + k * KSTEP, LBO, SBO, LT);
             umma_tf32(tmem_base, dal, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
             umma_tf32(tmem_base, da, dbl, idesc, 1u);
             umma_tf32(tmem_base, da, db, idesc, 1u);
@@ -502,6 +508,14 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
   prog.M = c_out;
   prog.N = c_in;
   prog.kTN = kTN; prog.kTH = kTH; prog.kTW = kTW;
+  prog.mn_lbo = 4096; prog.mn_sbo = 512; prog.mn_layout = 1;
+  CUtensorMapSwizzle mn_swizzle = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  if (const char* dbg = getenv("OBMAN_WGRAD_DESC")) {  // bring-up override: "lbo,sbo,layout,tma_swizzle"
+    unsigned a = 0, b = 0, c = 0, d = 0;
+    if (sscanf(dbg, "%u,%u,%u,%u", &a, &b, &c, &d) == 4) {
+      prog.mn_lbo = a; prog.mn_sbo = b; prog.mn_layout = c; mn_swizzle = (CUtensorMapSwizzle)d;
+    }
+  }
   prog.kblocks_n = (n_img + kTN - 1) / kTN;
   prog.kblocks_h = (h_out + kTH - 1) / kTH;
   prog.kblocks_w = (w_out + kTW - 1) / kTW;
@@ -514,7 +528,7 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
     uint64_t dims[5] = {32, (uint64_t)w_out, (uint64_t)h_out, (uint64_t)n_img, (uint64_t)(c_out / 32)};
     uint64_t strides[4] = {(uint64_t)c_out * 4, (uint64_t)w_out * c_out * 4, (uint64_t)h_out * w_out * c_out * 4, 128};
     uint32_t box[5] = {32, (uint32_t)kTW, (uint32_t)kTH, (uint32_t)kTN, 4};
-    int rc = make_tensor_map(&maps.a[0], dy, 5, dims, strides, box);
+    int rc = make_tensor_map(&maps.a[0], dy, 5, dims, strides, box, mn_swizzle);
     if (rc) return rc;
   }
   bool used[4] = {false, false, false, false};
@@ -535,7 +549,7 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
                            (uint64_t)h_in * w_in * c_in * 4, 128};
     uint32_t box[5] = {32, (uint32_t)kTW, (uint32_t)kTH, (uint32_t)kTN, (uint32_t)(BN / 32)};
     const float* base = x + ((long long)py * w_in + px) * c_in;
-    int rc = make_tensor_map(&maps.a[1 + ph], base, 5, dims, strides, box);
+    int rc = make_tensor_map(&maps.a[1 + ph], base, 5, dims, strides, box, mn_swizzle);
     if (rc) return rc;
   }
   const long long total_blocks = (long long)prog.kblocks_n * prog.kblocks_h * prog.kblocks_w;

@@ -140,13 +140,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // K-major  : rows of 128 B (32 tf32 along K), 8-row groups 1024 B apart (SBO); LBO unused.
 // MN-major : rows of 128 B (32 elements along M/N), 8 K-rows per 1024-B atom (SBO between K atoms),
 //            LBO = byte distance between consecutive 32-element M/N groups.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//            TF32 MN-major operands must use layout type 1 (SWIZZLE_128B_BASE32B: 32-byte chunks XOR-ed with
+//            the row index mod 4, matching TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 4 K-rows per 512-B atom.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;  // version
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;  // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 // Instruction descriptor: TF32 x TF32 -> FP32, M x N tile, operand majors (0 = K-major, 1 = MN-major).

@@ -33,7 +33,8 @@ inline EncodeTiledFn encode_tiled_fn() {
 // fp32 tensor, 128-byte swizzle, zero fill outside the tensor. dims[0] is the contiguous dimension;
 // strides_bytes[i] is the byte stride of dims[i+1] (multiple of 16); box[0] must be 32 (128 bytes).
 inline int make_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                           const uint64_t* strides_bytes, const uint32_t* box) {
+                           const uint64_t* strides_bytes, const uint32_t* box,
+                           CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return OBMAN_ERR_DRIVER;
   cuuint64_t gdim[5];
@@ -47,7 +48,7 @@ inline int make_tensor_map(CUtensorMap* map, const void* base, int rank, const u
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
-                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",

@@ -1,0 +1,202 @@
+"""ResNet-18 image encoder as ONE hand-scheduled autograd node over the tcgen05 convolution kernels.
+
+Forward and backward of mano_train/networks/bases/resnet.py:154-188 (conv7x7/2 -> BN -> ReLU -> maxpool ->
+4x2 BasicBlocks -> spatial mean) with BatchNorm in eval mode (the README recipe trains with
+--freeze_batchnorm, i.e. fixed running statistics and trainable gamma/beta):
+
+* activations are NHWC; BN scale is folded into the weights once per step, BN shift / residual add /
+  ReLU run in the convolution epilogue, so no elementwise pass ever touches HBM;
+* the backward pass fuses the ReLU mask and the residual-branch add into the dgrad epilogues and derives
+  d(gamma), d(beta) from the raw weight gradient (sum_k W*dWraw), so no pre-BN tensor is saved.
+"""
+import torch
+
+from . import dense
+from ._lib import call, ptr, stream_ptr
+
+BN_EPS = 1e-5
+
+# (name, out_ch, in_ch, ksize, stride) of the 20 conv+BN units in state-dict order
+def resnet18_units():
+    units = [("conv1", "bn1", 64, 3, 7, 2)]
+    inp = 64
+    for li, (planes, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2)), start=1):
+        for bi in range(2):
+            s = stride if bi == 0 else 1
+            p = "layer{}.{}.".format(li, bi)
+            units.append((p + "conv1", p + "bn1", planes, inp, 3, s))
+            units.append((p + "conv2", p + "bn2", planes, planes, 3, 1))
+            if bi == 0 and (s != 1 or inp != planes):
+                units.append((p + "downsample.0", p + "downsample.1", planes, inp, 1, s))
+            inp = planes
+    return units
+
+
+def _empty(*shape):
+    return torch.empty(shape, device="cuda", dtype=torch.float32)
+
+
+class _Unit(object):
+    """Per-step folded weights of one conv+BN unit."""
+
+    def __init__(self, w, gamma, beta, mean, var, ksize, stride, stem=False, need_dgrad=True):
+        self.w, self.gamma, self.mean = w, gamma, mean
+        self.O, self.I = w.shape[0], w.shape[1]
+        self.k, self.stride, self.stem = ksize, stride, stem
+        self.Ip = 32 if stem else self.I
+        self.slots = 16 if stem else ksize * ksize
+        self.wf = _empty(self.O, self.slots * self.Ip)
+        self.wft = _empty(self.I, self.slots * self.O) if (need_dgrad and not stem) else None
+        self.shift, self.scale, self.rstd = _empty(self.O), _empty(self.O), _empty(self.O)
+        call("obman_fold_conv", ptr(w), ptr(gamma), ptr(beta), ptr(mean), ptr(var), BN_EPS, self.O, self.I,
+             ksize, ksize, self.Ip, int(stem), ptr(self.wf), ptr(self.wft), ptr(self.shift),
+             ptr(self.scale), ptr(self.rstd), stream_ptr())
+        if stem:
+            dh = [a for a in range(-2, 2) for _ in range(4)]
+            dw = [b for _ in range(4) for b in range(-2, 2)]
+            self.taps = (dh, dw, [0] * 16, list(range(16)))
+            self.in_step = 1
+        else:
+            dh, dw, phase, slot, step = dense.fprop_taps(ksize, stride, ksize // 2)
+            self.taps = (dh, dw, phase, slot)
+            self.in_step = step
+
+    def fprop(self, x, h_out, w_out, addend=None, relu=True, passes=3):
+        out = _empty(x.shape[0], h_out, w_out, self.O)
+        dense.conv_nhwc(x, self.wf, self.O, self.taps, self.in_step, out, h_out, w_out, bias=self.shift,
+                        addend=addend, relu=relu, passes=passes, w_slots=self.slots)
+        return out
+
+    def dgrad(self, g, h_in, w_in, addend=None, mask_src=None, passes=3):
+        """g (B,Ho,Wo,O) -> gx (B,h_in,w_in,I) = conv^T(g) [+ addend] [masked by mask_src > 0]."""
+        B = g.shape[0]
+        s, k = self.stride, self.k
+        gx = _empty(B, h_in, w_in, self.I)
+        for ph in range(s):
+            for pw in range(s):
+                dh, dw, slot = dense.dgrad_taps(k, s, k // 2, (ph, pw))
+                off = (ph * w_in + pw) * self.I
+                strides = (h_in * w_in * self.I, s * w_in * self.I, s * self.I)
+                if not dh:  # this output phase receives no contribution from the convolution
+                    view = gx[:, ph::s, pw::s]
+                    if addend is not None:
+                        src = addend[:, ph::s, pw::s]
+                        view.copy_(src if mask_src is None else src * (mask_src[:, ph::s, pw::s] > 0))
+                    else:
+                        view.zero_()
+                    continue
+                dense.conv_nhwc(g, self.wft, self.I, (dh, dw, None, slot), 1, gx, h_in // s, w_in // s,
+                                out_strides=strides, out_offset=off, addend=addend, mask_src=mask_src,
+                                passes=passes, w_slots=k * k)
+        return gx
+
+    def wgrad(self, g, x, passes=3):
+        dwraw = _empty(self.O, self.slots * self.Ip)
+        dense.wgrad_nhwc(g, x, self.taps, self.in_step, dwraw, self.slots, passes=passes)
+        return dwraw
+
+    def finish(self, dwraw, gbeta_sum):
+        gw = torch.empty_like(self.w)
+        ggamma = torch.empty_like(self.gamma)
+        gbeta = torch.empty_like(self.gamma)
+        call("obman_bn_wgrad_finish", ptr(dwraw), ptr(self.w), ptr(self.scale), ptr(self.rstd),
+             ptr(self.mean), ptr(gbeta_sum), self.O, self.I, self.k, self.k, self.Ip, int(self.stem),
+             ptr(gw), ptr(ggamma), ptr(gbeta), stream_ptr())
+        return gw, ggamma, gbeta
+
+
+def colsum(x2d_rows, C, t):
+    out = _empty(C)
+    call("obman_colsum", ptr(t), int(x2d_rows), int(C), int(C), ptr(out), stream_ptr())
+    return out
+
+
+class _EncoderFn(torch.autograd.Function):
+    """features (B,512) = resnet18(images (B,3,H,W)); params = 5 tensors per unit (w, gamma, beta, mean, var)."""
+
+    @staticmethod
+    def forward(ctx, images, *params):
+        if not (images.is_cuda and images.dtype == torch.float32):
+            raise RuntimeError("encoder: expected CUDA float32 images (no CPU path)")
+        images = images.contiguous()
+        B, _, H, W = images.shape
+        if H % 32 or W % 32:
+            raise RuntimeError("encoder: image height/width must be multiples of 32")
+        pf = dense.PASSES[dense.get_precision()["fwd"]]
+        specs = resnet18_units()
+        units = []
+        for i, (_, _, O, I, k, s) in enumerate(specs):
+            w, gamma, beta, mean, var = [p.detach().contiguous() for p in params[5 * i:5 * i + 5]]
+            units.append(_Unit(w, gamma, beta, mean, var, k, s, stem=(i == 0)))
+        st = stream_ptr()
+        xs = _empty(B, H // 2, W // 2, 32)
+        call("obman_stem_pack", ptr(images), B, H, W, ptr(xs), st)
+        c1 = units[0].fprop(xs, H // 2, W // 2, relu=True, passes=pf)
+        hp, wp = H // 4, W // 4
+        p = _empty(B, hp, wp, 64)
+        pidx = torch.empty((B, hp, wp, 64), device="cuda", dtype=torch.uint8)
+        call("obman_maxpool_fwd", ptr(c1), B, H // 2, W // 2, 64, ptr(p), ptr(pidx), st)
+        x, h, w_ = p, hp, wp
+        blocks = []
+        ui = 1
+        for li in range(4):
+            for bi in range(2):
+                u1, u2 = units[ui], units[ui + 1]
+                ud = None
+                nxt = ui + 2
+                if nxt < len(specs) and "downsample" in specs[nxt][0] and specs[nxt][0].startswith("layer{}.{}.".format(li + 1, bi)):
+                    ud = units[nxt]
+                    nxt += 1
+                ho, wo = h // u1.stride, w_ // u1.stride
+                a = u1.fprop(x, ho, wo, relu=True, passes=pf)
+                r = ud.fprop(x, ho, wo, relu=False, passes=pf) if ud is not None else x
+                out = u2.fprop(a, ho, wo, addend=r, relu=True, passes=pf)
+                blocks.append((u1, u2, ud, x, a, out, h, w_))
+                x, h, w_ = out, ho, wo
+                ui = nxt
+        feats = _empty(B, 512)
+        call("obman_meanpool_fwd", ptr(x), B, h * w_, 512, ptr(feats), st)
+        ctx.units, ctx.blocks = units, blocks
+        ctx.saved = (xs, pidx, p, H, W)
+        return feats
+
+    @staticmethod
+    def backward(ctx, gfeat):
+        units, blocks = ctx.units, ctx.blocks
+        xs, pidx, p, H, W = ctx.saved
+        pb = dense.PASSES[dense.get_precision()["bwd"]]
+        st = stream_ptr()
+        gfeat = gfeat.contiguous()
+        B = gfeat.shape[0]
+        last = blocks[-1][5]
+        hl, wl = last.shape[1], last.shape[2]
+        g2 = torch.empty_like(last)
+        call("obman_meanpool_bwd", ptr(gfeat), ptr(last), B, hl * wl, 512, ptr(g2), st)
+        grads = {}
+        for (u1, u2, ud, x, a, out, h, w_) in reversed(blocks):
+            ho, wo = out.shape[1], out.shape[2]
+            rows = B * ho * wo
+            gb2 = colsum(rows, u2.O, g2)
+            grads[id(u2)] = u2.finish(u2.wgrad(g2, a, pb), gb2)
+            g1 = u2.dgrad(g2, ho, wo, mask_src=a, passes=pb)
+            grads[id(u1)] = u1.finish(u1.wgrad(g1, x, pb), colsum(rows, u1.O, g1))
+            if ud is not None:
+                grads[id(ud)] = ud.finish(ud.wgrad(g2, x, pb), gb2)
+                gres = ud.dgrad(g2, h, w_, passes=pb)
+            else:
+                gres = g2
+            g2 = u1.dgrad(g1, h, w_, addend=gres, mask_src=x, passes=pb)
+        # g2 is now the gradient w.r.t. the max-pool output (already masked by p > 0)
+        gc1 = _empty(B, H // 2, W // 2, 64)
+        call("obman_maxpool_bwd", ptr(g2), ptr(pidx), B, H // 2, W // 2, 64, ptr(gc1), st)
+        u0 = units[0]
+        grads[id(u0)] = u0.finish(u0.wgrad(gc1, xs, pb), colsum(B * (H // 2) * (W // 2), 64, gc1))
+        outs = [None]
+        for u in units:
+            gw, gg, gbt = grads[id(u)]
+            outs.extend([gw, gg, gbt, None, None])
+        return tuple(outs)
+
+
+def resnet18_features(images, params):
+    return _EncoderFn.apply(images, *params)

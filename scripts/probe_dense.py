@@ -159,6 +159,16 @@ CASES = {
 }
 
 
+def _variant(v):
+    os.environ["OBMAN_WGRAD_DESC"] = v
+    return case_wgrad_matrix(4096, 128, 256, 1)
+
+
+for _v in ("4096,512,1,4", "512,4096,1,4", "4096,1024,1,4", "4096,512,1,3", "4096,1024,2,3", "1024,4096,2,3",
+           "4096,512,2,4", "4096,256,1,4"):
+    CASES["wgradv_" + _v.replace(",", "_")] = (lambda v=_v: _variant(v))
+
+
 def main():
     if len(sys.argv) > 1:
         name = sys.argv[1]
@@ -170,7 +180,11 @@ def main():
         return
     results = {}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    for name in CASES:
+    names = [n for n in CASES if (len(sys.argv) <= 1)]
+    only = os.environ.get("PROBE_ONLY")
+    if only:
+        names = [n for n in CASES if only in n]
+    for name in names:
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True,
                                text=True, timeout=180)

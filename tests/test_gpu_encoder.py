@@ -1,0 +1,66 @@
+"""ResNet-18 encoder (fused tcgen05 path) vs the fp64 CPU oracle: features and every parameter gradient."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets
+
+pytestmark = pytest.mark.gpu
+
+
+def _randomise_bn(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data = 0.5 + torch.rand(m.weight.shape, generator=g)
+            m.bias.data = torch.randn(m.bias.shape, generator=g) * 0.1
+            m.running_mean.data = torch.randn(m.running_mean.shape, generator=g) * 0.1
+            m.running_var.data = 0.5 + torch.rand(m.running_var.shape, generator=g)
+
+
+@pytest.mark.parametrize("B,H,precision,tol", [(2, 64, "tf32x3", 1e-4), (3, 96, "tf32x3", 1e-4), (2, 64, "tf32", 2e-2)])
+def test_resnet18_fwd_bwd_vs_oracle(B, H, precision, tol):
+    from obman_train_b200 import dense
+    from obman_train_b200.networks.bases.resnet import resnet18
+    torch.manual_seed(0)
+    model = resnet18()
+    _randomise_bn(model, 1)
+    model.eval()
+    state64 = {"base_net." + k: v.detach().double().clone() for k, v in model.state_dict().items()}
+    for v in state64.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    g = torch.Generator().manual_seed(2)
+    images = torch.rand(B, 3, H, H, generator=g) - 0.5
+    wts = torch.randn(B, 512, generator=g)
+    ref = nets.resnet18_features(state64, images.double(), "base_net", False)
+    (ref * wts.double()).sum().backward()
+
+    model = model.cuda()
+    dense.set_precision(precision, precision)
+    try:
+        feats, extra = model(images.cuda())
+        assert extra == {}
+        (feats * wts.cuda()).sum().backward()
+    finally:
+        dense.set_precision("tf32x3", "tf32x3")
+    scale = ref.abs().max().item()
+    err = (feats.detach().cpu().double() - ref.detach()).abs().max().item()
+    assert err < tol * scale, (err, scale)
+    worst = 0.0
+    for name, p in model.named_parameters():
+        if name.startswith("fc."):
+            assert p.grad is None
+            continue
+        gref = state64["base_net." + name].grad
+        rel = (p.grad.cpu().double() - gref).abs().max().item() / (gref.abs().max().item() + 1e-30)
+        worst = max(worst, rel)
+        assert rel < 10 * tol, (name, rel)
+    print("features rel err %.2e, worst grad rel err %.2e" % (err / scale, worst))
+
+
+def test_resnet18_train_mode_bn_is_rejected():
+    from obman_train_b200.networks.bases.resnet import resnet18
+    model = resnet18().cuda().train()
+    with pytest.raises(NotImplementedError):
+        model(torch.zeros(1, 3, 64, 64, device="cuda"))

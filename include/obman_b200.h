@@ -129,9 +129,10 @@ int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out, int c_out
  * 20 zero channels) so that the 7x7/2 stem runs as a 4x4/1 obman_conv_nhwc. */
 int obman_stem_pack(const float* x, int B, int H, int W, float* out, void* stream);
 /* BatchNorm(eval) folding + weight re-layout, once per step.  w (O,I,KH,KW); gamma/beta/mean/var (O) or NULL
- * (no BN: beta, if given, is a plain bias).  wf (O, KH*KW*Ip) fprop operand, wft (I, KH*KW*O) dgrad operand
+ * (no BN), cbias (O) conv bias or NULL: shift = beta + (cbias - mean)*scale (no BN: shift = cbias).
+ * wf (O, KH*KW*Ip) fprop operand, wft (I, KH*KW*O) dgrad operand
  * (NULL to skip), shift/scale/rstd (O).  stem=1: (O,3,7,7) filter -> (O, 16*32) space-to-depth layout. */
-int obman_fold_conv(const float* w, const float* gamma, const float* beta, const float* mean,
+int obman_fold_conv(const float* w, const float* cbias, const float* gamma, const float* beta, const float* mean,
                     const float* var, float eps, int O, int I, int KH, int KW, int Ip, int stem,
                     float* wf, float* wft, float* shift, float* scale, float* rstd, void* stream);
 /* MaxPool2d(3, stride 2, pad 1), NHWC (resnet.py:107): idx (B,H/2,W/2,C) u8 = arg-max window slot. */
@@ -145,11 +146,20 @@ int obman_meanpool_bwd(const float* gout, const float* x, int B, int P, int C, f
                        void* stream);
 /* out[c] = sum_r x[r*ld + c]  (bias / BatchNorm-beta gradients). */
 int obman_colsum(const float* x, long long rows, int C, long long ld, float* out, void* stream);
-/* Raw weight gradient dwraw (O, KH*KW*Ip) -> gw (O,I,KH,KW) = scale*dwraw and, with BatchNorm,
- * ggamma = rstd*(sum_k w*dwraw - mean*gbeta_sum), gbeta = gbeta_sum. */
-int obman_bn_wgrad_finish(const float* dwraw, const float* w, const float* scale, const float* rstd,
-                          const float* mean, const float* gbeta_sum, int O, int I, int KH, int KW,
-                          int Ip, int stem, float* gw, float* ggamma, float* gbeta, void* stream);
+/* Raw weight gradient dwraw (O rows of stride dw_ld, KH*KW*Ip used) -> gw (O,I,KH,KW) = scale*dwraw and
+ * (NULL to skip) ggamma = rstd*(sum_k w*dwraw + (cbias - mean)*gbeta_sum), gbeta = gbeta_sum,
+ * gcbias = scale*gbeta_sum. */
+int obman_bn_wgrad_finish(const float* dwraw, long long dw_ld, const float* w, const float* cbias,
+                          const float* scale, const float* rstd, const float* mean,
+                          const float* gbeta_sum, int O, int I, int KH, int KW, int Ip, int stem,
+                          float* gw, float* ggamma, float* gbeta, float* gcbias, void* stream);
+/* AtlasNet decoder layer 1 after the conv1 split (atlasbranch.py:117-131 + atlasutils.py:65-67):
+ * out[b,n,c] = relu(G[b*g_bstride + n*C + c] + F[b*C + c]) (c < C), 0 (C <= c < ld). */
+int obman_pointmlp_l1_fwd(const float* G, long long g_bstride, const float* F, int B, int N, int C,
+                          int ld, float* out, void* stream);
+/* g (B,N, ld) -> gF[b,c] = sum_n g, gG[n,c] = sum_b g (gG may be NULL). */
+int obman_pointmlp_l1_bwd(const float* g, int B, int N, int C, int ld, float* gF, float* gG,
+                          void* stream);
 /* Fused torch.optim.Adam step (traineval.py:113-116) on flat fp32 buffers; g is multiplied by grad_scale. */
 int obman_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int step, float grad_scale,

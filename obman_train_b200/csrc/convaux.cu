@@ -39,10 +39,11 @@ stem_pack_kernel(const float* __restrict__ x, int B, int H, int W, float* __rest
 // Folded weights for one convolution.  w (O,I,KH,KW); scale s[o] = gamma*rsqrt(var+eps) (or 1 without BN).
 //   wf [o][(kh*KW+kw)*Ip + i] = s[o]*w[o,i,kh,kw]        (fprop B operand; Ip = padded input channels)
 //   wft[i][(kh*KW+kw)*O  + o] = s[o]*w[o,i,kh,kw]        (dgrad B operand), i < I only
-//   shift[o] = beta - mean*s ; scale[o] = s ; rstd[o]
+//   shift[o] = beta + (conv_bias - mean)*s ; scale[o] = s ; rstd[o]
 // stem == 1: w is the (64,3,7,7) stem filter, written in the 4x4 x 32-channel space-to-depth layout.
 __global__ void __launch_bounds__(256)
-fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
+                 const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ mean,
                  const float* __restrict__ var, float eps, int O, int I, int KH, int KW, int Ip,
                  int stem, float* __restrict__ wf, float* __restrict__ wft, float* __restrict__ shift,
@@ -56,7 +57,8 @@ fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
   if (threadIdx.x == 0) {
     scale[o] = s;
     rstd_out[o] = rs;
-    shift[o] = gamma ? beta[o] - mean[o] * s : (beta ? beta[o] : 0.f);
+    const float cb = cbias ? cbias[o] : 0.f;
+    shift[o] = gamma ? beta[o] + (cb - mean[o]) * s : cb;
   }
   if (stem) {
     // taps (a,b) in [-2,1]^2 -> slot (a+2)*4 + (b+2); channel (ph*2+pw)*3 + c <-> kh = 2a+ph+3, kw = 2b+pw+3
@@ -202,11 +204,12 @@ colsum_kernel(const float* __restrict__ x, long long rows, int C, long long ld, 
 // dwraw [O][(kh*KW+kw)*Ip + i] -> gw (O,I,KH,KW) = s[o]*dwraw ; ggamma[o] = rstd*(sum_k w*dwraw - mean*gbeta) ; gbeta = colsum
 // stem == 1: dwraw is in the 16-slot x 32-channel space-to-depth layout of the 7x7 stem.
 __global__ void __launch_bounds__(256)
-bn_wgrad_finish_kernel(const float* __restrict__ dwraw, const float* __restrict__ w,
+bn_wgrad_finish_kernel(const float* __restrict__ dwraw, long long dw_ld, const float* __restrict__ w,
+                       const float* __restrict__ cbias,
                        const float* __restrict__ scale, const float* __restrict__ rstd,
                        const float* __restrict__ mean, const float* __restrict__ gbeta_sum, int O, int I,
                        int KH, int KW, int Ip, int stem, float* __restrict__ gw,
-                       float* __restrict__ ggamma, float* __restrict__ gbeta) {
+                       float* __restrict__ ggamma, float* __restrict__ gbeta, float* __restrict__ gcbias) {
   __shared__ float scratch[32];
   const int o = blockIdx.x;
   const float s = scale[o];
@@ -218,19 +221,23 @@ bn_wgrad_finish_kernel(const float* __restrict__ dwraw, const float* __restrict_
     if (stem) {
       const int kh = t / 7, kw = t % 7;
       const int a = (kh - 3) >> 1, ph = (kh - 3) & 1, b = (kw - 3) >> 1, pw = (kw - 3) & 1;
-      raw = dwraw[(size_t)o * 512 + ((a + 2) * 4 + (b + 2)) * 32 + (ph * 2 + pw) * 3 + i];
+      raw = dwraw[(size_t)o * dw_ld + ((a + 2) * 4 + (b + 2)) * 32 + (ph * 2 + pw) * 3 + i];
     } else {
-      raw = dwraw[(size_t)o * taps * Ip + (size_t)t * Ip + i];
+      raw = dwraw[(size_t)o * dw_ld + (size_t)t * Ip + i];
     }
     const float wv = w[(size_t)o * I * taps + k];
     dot = fmaf(wv, raw, dot);
     gw[(size_t)o * I * taps + k] = s * raw;
   }
   dot = block_sum(dot, scratch);
-  if (threadIdx.x == 0 && ggamma) {
-    const float gb = gbeta_sum[o];
-    ggamma[o] = rstd[o] * (dot - mean[o] * gb);
-    gbeta[o] = gb;
+  if (threadIdx.x == 0) {
+    const float gb = gbeta_sum ? gbeta_sum[o] : 0.f;
+    if (ggamma) {
+      const float cb = cbias ? cbias[o] : 0.f;
+      ggamma[o] = rstd[o] * (dot + (cb - mean[o]) * gb);
+      gbeta[o] = gb;
+    }
+    if (gcbias) gcbias[o] = s * gb;
   }
 }
 
@@ -252,9 +259,85 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   p[i] = pv - (lr / bc1) * (mm / denom);
 }
 
+// AtlasNet decoder, first layer after the algebraic split of conv1 (atlasutils.py:65-67 on the input of
+// atlasbranch.py:117-131): h1[b,n,c] = relu(G[n,c] + F[b,c]) for c < C, 0 for C <= c < ld.
+// G = grid * (s*W[:, :3])^T is batch-independent (or per-sample when g_bstride != 0), F = feat * (s*W[:, 3:])^T + shift.
+__global__ void __launch_bounds__(256)
+pointmlp_l1_fwd_kernel(const float* __restrict__ G, long long g_bstride, const float* __restrict__ F, int B,
+                       int N, int C, int ld, float* __restrict__ out) {
+  const int ld4 = ld / 4;
+  const size_t total = (size_t)B * N * ld4;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % ld4) * 4;
+  const size_t row = t / ld4;
+  const int n = (int)(row % N);
+  const int b = (int)(row / N);
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int cc = c + e;
+    v[e] = cc < C ? fmaxf(G[(size_t)b * g_bstride + (size_t)n * C + cc] + F[(size_t)b * C + cc], 0.f) : 0.f;
+  }
+  reinterpret_cast<float4*>(out)[t] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// gF[b,c] = sum_n g[b,n,c]   (g has row stride ld); grid (ceil(C/32), B)
+__global__ void __launch_bounds__(256)
+pointmlp_l1_bwd_f_kernel(const float* __restrict__ g, int N, int C, int ld, float* __restrict__ gF) {
+  __shared__ float red[8][33];
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  float s = 0.f;
+  if (c < C)
+    for (int n = ry; n < N; n += 8) s += g[((size_t)b * N + n) * ld + c];
+  red[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot += red[k][threadIdx.x & 31];
+    gF[(size_t)b * C + c] = tot;
+  }
+}
+
+// gG[n,c] = sum_b g[b,n,c]
+__global__ void __launch_bounds__(256)
+pointmlp_l1_bwd_g_kernel(const float* __restrict__ g, int B, int N, int C, int ld, float* __restrict__ gG) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)N * C) return;
+  const int c = (int)(t % C);
+  const int n = (int)(t / C);
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += g[((size_t)b * N + n) * ld + c];
+  gG[t] = s;
+}
+
 }  // namespace obman
 
 using namespace obman;
+
+extern "C" int obman_pointmlp_l1_fwd(const float* G, long long g_bstride, const float* F, int B, int N, int C,
+                                     int ld, float* out, void* stream) {
+  OBMAN_REQUIRE(G && F && out && B > 0 && N > 0 && C > 0 && ld >= C && ld % 4 == 0, "obman_pointmlp_l1_fwd: bad arguments");
+  const size_t total = (size_t)B * N * (ld / 4);
+  pointmlp_l1_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(G, g_bstride, F, B, N, C,
+                                                                                         ld, out);
+  return check_launch("pointmlp_l1_fwd_kernel");
+}
+
+extern "C" int obman_pointmlp_l1_bwd(const float* g, int B, int N, int C, int ld, float* gF, float* gG,
+                                     void* stream) {
+  OBMAN_REQUIRE(g && gF && B > 0 && N > 0 && C > 0 && ld >= C && B <= 65535, "obman_pointmlp_l1_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  pointmlp_l1_bwd_f_kernel<<<dim3((C + 31) / 32, B), 256, 0, st>>>(g, N, C, ld, gF);
+  int rc = check_launch("pointmlp_l1_bwd_f_kernel");
+  if (rc || !gG) return rc;
+  const size_t total = (size_t)N * C;
+  pointmlp_l1_bwd_g_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, B, N, C, ld, gG);
+  return check_launch("pointmlp_l1_bwd_g_kernel");
+}
 
 extern "C" int obman_stem_pack(const float* x, int B, int H, int W, float* out, void* stream) {
   OBMAN_REQUIRE(x && out && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "obman_stem_pack: bad arguments");
@@ -263,14 +346,14 @@ extern "C" int obman_stem_pack(const float* x, int B, int H, int W, float* out, 
   return check_launch("stem_pack_kernel");
 }
 
-extern "C" int obman_fold_conv(const float* w, const float* gamma, const float* beta, const float* mean,
+extern "C" int obman_fold_conv(const float* w, const float* cbias, const float* gamma, const float* beta, const float* mean,
                                const float* var, float eps, int O, int I, int KH, int KW, int Ip, int stem,
                                float* wf, float* wft, float* shift, float* scale, float* rstd,
                                void* stream) {
   OBMAN_REQUIRE(w && wf && shift && scale && rstd && O > 0 && I > 0 && KH > 0 && KW > 0 && Ip >= I,
                 "obman_fold_conv: bad arguments");
   OBMAN_REQUIRE(!stem || (I == 3 && KH == 7 && KW == 7), "obman_fold_conv: stem layout needs a (O,3,7,7) filter");
-  fold_conv_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(w, gamma, beta, mean, var, eps, O, I, KH, KW, Ip, stem,
+  fold_conv_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(w, cbias, gamma, beta, mean, var, eps, O, I, KH, KW, Ip, stem,
                                                         wf, wft, shift, scale, rstd);
   return check_launch("fold_conv_kernel");
 }
@@ -318,14 +401,16 @@ extern "C" int obman_colsum(const float* x, long long rows, int C, long long ld,
   return check_launch("colsum_kernel");
 }
 
-extern "C" int obman_bn_wgrad_finish(const float* dwraw, const float* w, const float* scale,
+extern "C" int obman_bn_wgrad_finish(const float* dwraw, long long dw_ld, const float* w, const float* cbias,
+                                     const float* scale,
                                      const float* rstd, const float* mean, const float* gbeta_sum, int O,
                                      int I, int KH, int KW, int Ip, int stem, float* gw, float* ggamma,
-                                     float* gbeta, void* stream) {
+                                     float* gbeta, float* gcbias, void* stream) {
   OBMAN_REQUIRE(dwraw && w && scale && gw && O > 0 && I > 0 && Ip >= I, "obman_bn_wgrad_finish: bad arguments");
   OBMAN_REQUIRE(!ggamma || (rstd && mean && gbeta_sum && gbeta), "obman_bn_wgrad_finish: BatchNorm outputs need rstd/mean/gbeta_sum");
-  bn_wgrad_finish_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(dwraw, w, scale, rstd, mean, gbeta_sum, O, I, KH,
-                                                              KW, Ip, stem, gw, ggamma, gbeta);
+  OBMAN_REQUIRE(!gcbias || gbeta_sum, "obman_bn_wgrad_finish: conv-bias gradient needs gbeta_sum");
+  bn_wgrad_finish_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(dwraw, dw_ld, w, cbias, scale, rstd, mean, gbeta_sum,
+                                                              O, I, KH, KW, Ip, stem, gw, ggamma, gbeta, gcbias);
   return check_launch("bn_wgrad_finish_kernel");
 }
 

@@ -48,7 +48,7 @@ class _Unit(object):
         self.wf = _empty(self.O, self.slots * self.Ip)
         self.wft = _empty(self.I, self.slots * self.O) if (need_dgrad and not stem) else None
         self.shift, self.scale, self.rstd = _empty(self.O), _empty(self.O), _empty(self.O)
-        call("obman_fold_conv", ptr(w), ptr(gamma), ptr(beta), ptr(mean), ptr(var), BN_EPS, self.O, self.I,
+        call("obman_fold_conv", ptr(w), None, ptr(gamma), ptr(beta), ptr(mean), ptr(var), BN_EPS, self.O, self.I,
              ksize, ksize, self.Ip, int(stem), ptr(self.wf), ptr(self.wft), ptr(self.shift),
              ptr(self.scale), ptr(self.rstd), stream_ptr())
         if stem:
@@ -99,9 +99,9 @@ class _Unit(object):
         gw = torch.empty_like(self.w)
         ggamma = torch.empty_like(self.gamma)
         gbeta = torch.empty_like(self.gamma)
-        call("obman_bn_wgrad_finish", ptr(dwraw), ptr(self.w), ptr(self.scale), ptr(self.rstd),
-             ptr(self.mean), ptr(gbeta_sum), self.O, self.I, self.k, self.k, self.Ip, int(self.stem),
-             ptr(gw), ptr(ggamma), ptr(gbeta), stream_ptr())
+        call("obman_bn_wgrad_finish", ptr(dwraw), dwraw.stride(0), ptr(self.w), None, ptr(self.scale),
+             ptr(self.rstd), ptr(self.mean), ptr(gbeta_sum), self.O, self.I, self.k, self.k, self.Ip,
+             int(self.stem), ptr(gw), ptr(ggamma), ptr(gbeta), None, stream_ptr())
         return gw, ggamma, gbeta
 
 

@@ -1,0 +1,202 @@
+"""Linear layers and the AtlasNet point decoder as autograd nodes over the tcgen05 GEMM kernels.
+
+``linear``        nn.Linear (+ReLU) of ManoBranch / AtlasBranch heads (manobranch.py:57-67,82-85,124-147;
+                  atlasbranch.py:44-61).
+``point_decoder`` PointGenCon (atlasutils.py:42-75) on the AtlasBranch input cat(grid, feature)
+                  (atlasbranch.py:117-131), BatchNorm1d in eval mode, with conv1 split algebraically:
+                  conv1(x)[b,:,n] = W[:, :3] grid[n] + (W[:, 3:] feat_b + bias), which removes the
+                  (B,515,N) concatenated tensor and 61 % of the decoder MACs.
+"""
+import torch
+
+from . import dense
+from ._lib import call, ptr, stream_ptr
+
+BN_EPS = 1e-5
+
+
+def _r32(n):
+    return (n + 31) // 32 * 32
+
+
+def _zeros(*shape):
+    return torch.zeros(shape, device="cuda", dtype=torch.float32)
+
+
+def _empty(*shape):
+    return torch.empty(shape, device="cuda", dtype=torch.float32)
+
+
+def _pad_cols(t, width):
+    """Copy (M,N) into a zero-padded (M,width) buffer (no copy when already that wide and contiguous)."""
+    if t.shape[1] == width and t.is_contiguous():
+        return t
+    out = _zeros(t.shape[0], width)
+    out[:, :t.shape[1]] = t
+    return out
+
+
+def colsum(t, C=None):
+    C = t.shape[1] if C is None else C
+    out = _empty(C)
+    call("obman_colsum", ptr(t), t.shape[0], C, t.stride(0), ptr(out), stream_ptr())
+    return out
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        x = x.contiguous()
+        w = weight.detach().contiguous()
+        if x.shape[1] % 4:
+            raise RuntimeError("linear: in_features must be a multiple of 4 for the TMA path")
+        pf = dense.PASSES[dense.get_precision()["fwd"]]
+        y = dense.gemm(x, w, bias=None if bias is None else bias.detach().contiguous(), relu=relu, passes=pf)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, y = ctx.saved_tensors
+        pb = dense.PASSES[dense.get_precision()["bwd"]]
+        N, K = w.shape
+        if ctx.relu:
+            g = g * (y > 0)
+        gp = _pad_cols(g.contiguous(), _r32(N))
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wt = _zeros(K, _r32(N))
+            wt[:, :N] = w.t()
+            gx = dense.gemm(gp, wt, passes=pb, n=K, k=N)
+        if ctx.needs_input_grad[1]:
+            xk = _pad_cols(x, _r32(K))
+            gw = dense.wgrad_matrix(gp, xk, passes=pb)[:N, :K].contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = colsum(gp, N)
+        return gx, gw, gb, None
+
+
+def linear(x, weight, bias=None, relu=False):
+    return _LinearFn.apply(x, weight, bias, relu)
+
+
+class _Layer(object):
+    """Folded 1x1-conv (+BN eval) layer of the point decoder: y = relu?(x Wf^T + shift)."""
+
+    def __init__(self, w, cbias, bn):
+        self.w = w.detach().reshape(w.shape[0], w.shape[1]).contiguous()
+        self.cbias = cbias.detach().contiguous()
+        self.O, self.I = self.w.shape
+        self.bn = None if bn is None else [t.detach().contiguous() for t in bn]
+        gamma, beta, mean, var = self.bn if self.bn is not None else (None, None, None, None)
+        self.ld = (self.I + 3) // 4 * 4
+        self.wf = _empty(self.O, self.ld)
+        self.wft = _zeros(self.I, _r32(self.O))   # (I, O padded): dgrad operand
+        wft_tmp = _empty(self.I, self.O)
+        self.shift, self.scale, self.rstd = _empty(self.O), _empty(self.O), _empty(self.O)
+        call("obman_fold_conv", ptr(self.w), ptr(self.cbias), ptr(gamma), ptr(beta), ptr(mean), ptr(var),
+             BN_EPS, self.O, self.I, 1, 1, self.ld, 0, ptr(self.wf), ptr(wft_tmp), ptr(self.shift),
+             ptr(self.scale), ptr(self.rstd), stream_ptr())
+        self.wft[:, :self.O] = wft_tmp
+
+    def finish(self, dwraw, gsum):
+        """dwraw (>=O rows, row stride ld_raw, first I columns valid) -> (gw, gcbias, ggamma, gbeta)."""
+        gw = _empty(self.O, self.I)
+        gcb = _empty(self.O)
+        gg = gbt = None
+        mean = None
+        if self.bn is not None:
+            gg, gbt = _empty(self.O), _empty(self.O)
+            mean = self.bn[2]
+        call("obman_bn_wgrad_finish", ptr(dwraw), dwraw.stride(0), ptr(self.w), ptr(self.cbias),
+             ptr(self.scale), ptr(self.rstd), ptr(mean), ptr(gsum), self.O, self.I, 1, 1, dwraw.stride(0), 0,
+             ptr(gw), ptr(gg), ptr(gbt), ptr(gcb), stream_ptr())
+        return gw, gcb, gg, gbt
+
+
+class _PointDecoderFn(torch.autograd.Function):
+    """verts (B,N,3) = out_factor * PointGenCon(cat(grid, feat repeated)), BatchNorm in eval mode.
+
+    args: feat (B,F), grid (N,3) shared or (B,N,3) per sample, out_factor, then
+    conv1.w, conv1.b, conv2.w, conv2.b, conv3.w, conv3.b, conv4.w, conv4.b,
+    bn1 (g,b,m,v), bn2 (g,b,m,v), bn3 (g,b,m,v)."""
+
+    @staticmethod
+    def forward(ctx, feat, grid, out_factor, *p):
+        pf = dense.PASSES[dense.get_precision()["fwd"]]
+        st = stream_ptr()
+        feat = feat.contiguous()
+        grid = grid.detach().contiguous()
+        B, Fdim = feat.shape
+        N = grid.shape[-2]
+        per_sample = grid.dim() == 3
+        l1 = _Layer(p[0], p[1], p[8:12])
+        l2 = _Layer(p[2], p[3], p[12:16])
+        l3 = _Layer(p[4], p[5], p[16:20])
+        l4 = _Layer(p[6], p[7], None)
+        C1, C2, C3 = l1.O, l2.O, l3.O
+        # layer 1: grid part (K = 3, batch independent) + feature part (B x F GEMM) -> relu(G + F)
+        wg = l1.wf[:, :3]                                    # (C1,3) folded
+        wfeat = l1.wf[:, 3:3 + Fdim].contiguous()            # (C1,F) folded
+        G = (grid.unsqueeze(-2) * wg).sum(-1).contiguous()   # (N,C1) or (B,N,C1)
+        Fb = dense.gemm(feat, wfeat, bias=l1.shift, passes=pf)        # (B,C1)
+        ld1, ld2 = _r32(C1), _r32(C2)
+        h1 = _empty(B * N, ld1)
+        call("obman_pointmlp_l1_fwd", ptr(G), N * C1 if per_sample else 0, ptr(Fb), B, N, C1, ld1, ptr(h1), st)
+        h2 = _zeros(B * N, ld2)
+        dense.gemm(h1, l2.wf, out=h2, bias=l2.shift, relu=True, passes=pf, n=C2, k=C1)
+        h3 = dense.gemm(h2, l3.wf, bias=l3.shift, relu=True, passes=pf, n=C3, k=C2)
+        y = dense.gemm(h3, l4.wf, bias=l4.shift * out_factor, alpha=out_factor, passes=pf, n=3, k=C3)
+        ctx.layers = (l1, l2, l3, l4)
+        ctx.param_shapes = [tuple(t.shape) for t in p]
+        ctx.saved = (feat, grid, wfeat, h1, h2, h3, B, N, per_sample, out_factor)
+        return y.view(B, N, 3)
+
+    @staticmethod
+    def backward(ctx, gy):
+        pb = dense.PASSES[dense.get_precision()["bwd"]]
+        st = stream_ptr()
+        l1, l2, l3, l4 = ctx.layers
+        feat, grid, wfeat, h1, h2, h3, B, N, per_sample, out_factor = ctx.saved
+        C1, C2, C3 = l1.O, l2.O, l3.O
+        M = B * N
+        g4 = _zeros(M, 32)
+        g4[:, :3] = gy.reshape(M, 3) * out_factor
+        gw4, gb4, _, _ = l4.finish(dense.wgrad_matrix(g4, h3, passes=pb), colsum(g4, 3))
+        g3 = dense.gemm(g4, l4.wft, mask_src=h3, passes=pb, n=C3, k=3)                       # (M,C3)
+        gw3, gb3, gg3, gbt3 = l3.finish(dense.wgrad_matrix(g3, h2, passes=pb), colsum(g3, C3))
+        g2 = _zeros(M, h2.shape[1])
+        dense.gemm(g3, l3.wft, out=g2, mask_src=h2, passes=pb, n=C2, k=C3)
+        gw2, gb2, gg2, gbt2 = l2.finish(dense.wgrad_matrix(g2, h1, passes=pb), colsum(g2, C2))
+        g1 = _zeros(M, h1.shape[1])
+        dense.gemm(g2, l2.wft, out=g1, mask_src=h1, passes=pb, n=C1, k=C2)
+        gF = _zeros(B, _r32(C1))
+        gFc = _empty(B, C1)
+        gG = None if per_sample else _empty(N, C1)
+        call("obman_pointmlp_l1_bwd", ptr(g1), B, N, C1, g1.shape[1], ptr(gFc), ptr(gG), st)
+        gF[:, :C1] = gFc
+        # raw weight gradient of conv1 = [grid part | feature part]
+        if per_sample:
+            gwg = torch.einsum("mc,mk->ck", g1[:, :C1], grid.reshape(M, 3))
+        else:
+            gwg = torch.einsum("nc,nk->ck", gG, grid)
+        Fdim = feat.shape[1]
+        gwf = dense.wgrad_matrix(gF, _pad_cols(feat, _r32(Fdim)), passes=pb)[:C1, :Fdim]
+        dw1 = torch.cat([gwg, gwf], dim=1).contiguous()                                      # (C1, 3+F)
+        gw1, gb1, gg1, gbt1 = l1.finish(dw1, colsum(gF, C1))
+        gfeat = None
+        if ctx.needs_input_grad[0]:
+            wft = _zeros(Fdim, _r32(C1))
+            wft[:, :C1] = wfeat.t()
+            gfeat = dense.gemm(gF, wft, passes=pb, n=Fdim, k=C1)
+        p = ctx.param_shapes
+        return (gfeat, None, None,
+                gw1.view(p[0]), gb1, gw2.view(p[2]), gb2, gw3.view(p[4]), gb3, gw4.view(p[6]), gb4,
+                gg1, gbt1, None, None, gg2, gbt2, None, None, gg3, gbt3, None, None)
+
+
+def point_decoder(feat, grid, out_factor, conv_params, bn_params):
+    """conv_params: [w1,b1,w2,b2,w3,b3,w4,b4]; bn_params: [g1,b1,m1,v1, g2,..., g3,...]."""
+    return _PointDecoderFn.apply(feat, grid, out_factor, *(list(conv_params) + list(bn_params)))

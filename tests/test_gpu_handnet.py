@@ -1,0 +1,91 @@
+"""End-to-end parity of the drop-in HandNet (all stages in libobman_b200.so) against the fp64 CPU oracle:
+total loss, every logged loss, vertex coordinates and all parameter gradients."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import icosphere, nets
+from obman_train_b200.assets import load_contacts
+from tests.util import FULL_CFG, enum_sample, make_sample, randomise_bn
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_tables(layer):
+    return {k: v.detach().cpu().double() for k, v in layer.named_buffers() if k != "th_faces"}
+
+
+def _run(cfg, B, H, seed, n_gt=600, sides=None):
+    from obman_train_b200.networks.handnet import HandNet
+    torch.manual_seed(seed)
+    model = HandNet(**cfg)
+    randomise_bn(model, seed + 1)
+    model.eval()
+    sample = make_sample(B, H, seed + 2, n_gt=n_gt, sides=sides)
+    state = {k: v.detach().double().clone() for k, v in model.state_dict().items()}
+    for k, v in state.items():
+        if v.is_floating_point() and "running_" not in k and "th_" not in k:
+            v.requires_grad_(True)
+    tables = {"right": _oracle_tables(model.mano_branch.mano_layer_right),
+              "left": _oracle_tables(model.mano_branch.mano_layer_left)}
+    grid = model.atlas_branch.test_verts.double()
+    faces = model.atlas_branch.test_faces
+    _, zones = load_contacts()
+    s64 = {k: (v.double() if torch.is_tensor(v) else v) for k, v in sample.items()}
+    ototal, oresults, olosses = nets.handnet_forward(state, cfg, s64, tables, grid, faces, zones)
+    ototal.backward()
+    model = model.cuda()
+    total, results, losses = model.forward(enum_sample(sample))
+    total.backward()
+    return model, state, (total, results, losses), (ototal, oresults, olosses)
+
+
+def _check(model, state, got, ref, rtol=1e-4, grad_rtol=2e-3):
+    total, results, losses = got
+    ototal, oresults, olosses = ref
+    assert abs(total.item() - ototal.item()) < rtol * abs(ototal.item()), (total.item(), ototal.item())
+    for key, oval in olosses.items():
+        if oval is None or key in ("total_loss", "mano_total_loss", "contact_loss"):
+            continue
+        assert abs(float(losses[key]) - float(oval)) <= rtol * abs(float(oval)) + 1e-6, (key, float(losses[key]), float(oval))
+    for key in ("verts", "joints", "objpoints3d"):
+        if key in oresults:
+            o = oresults[key].detach().numpy()
+            g = results[key].detach().cpu().numpy()
+            assert np.abs(g - o).max() < rtol * np.abs(o).max(), key
+    assert float(losses["mano_total_loss"]) == float(total)  # aliasing quirk, SURVEY.md Appendix A.1
+    worst = ("", 0.0)
+    for name, p in model.named_parameters():
+        og = state[name].grad
+        if p.grad is None:
+            assert og is None or og.abs().max() == 0, name
+            continue
+        rel = (p.grad.cpu().double() - og).abs().max().item() / (og.abs().max().item() + 1e-12)
+        if rel > worst[1]:
+            worst = (name, rel)
+    assert worst[1] < grad_rtol, worst
+    print("total %.6f (oracle %.6f); worst grad rel err %.2e at %s" % (total.item(), ototal.item(), worst[1], worst[0]))
+
+
+def test_handnet_full_stack_matches_oracle():
+    _check(*_run(FULL_CFG, B=3, H=64, seed=0))
+
+
+def test_handnet_shared_encoder_ico3_no_contact():
+    cfg = dict(FULL_CFG)
+    cfg.update(atlas_separate_encoder=False, atlas_ico_divisions=3, contact_lambda=0, collision_lambda=0,
+               atlas_lambda_regul_edges=0)
+    _check(*_run(cfg, B=2, H=64, seed=10, sides=["right", "right"]))
+
+
+def test_handnet_no_loss_inference_hand_only():
+    from obman_train_b200.networks.handnet import HandNet
+    from obman_train_b200.queries import TransQueries, BaseQueries
+    torch.manual_seed(1)
+    model = HandNet(**FULL_CFG).eval().cuda()
+    sample = {TransQueries.images: torch.rand(1, 3, 256, 256) - 0.5, BaseQueries.sides: ["left"], "root": "wrist",
+              TransQueries.joints3d: torch.ones(1, 21, 3)}
+    total, results, losses = model.forward(sample, no_loss=True)
+    assert total is None and losses["total_loss"] is None
+    assert results["verts"].shape == (1, 778, 3) and results["joints"].shape == (1, 21, 3)
+    assert torch.isfinite(results["verts"]).all()

@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the obman_train hot path on B200 (driver contract).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+
+One "step" = one training step (HandNet forward + backward + Adam) on a synthetic batch of
+BASELINE.json configs[1]: per-GPU batch 64, 256x256 images, ResNet-18 (shared encoder) + ManoLayer(778 v)
++ AtlasNet (1 patch, ico-3 = 642 points) + Chamfer (M = 600 GT points) + Mano/Atlas losses; weak scaling
+(per-GPU batch fixed).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(resnet_version=18, mano_root="synthetic", mano_comps=30, mano_use_shape=True, mano_use_pca=True,
+           mano_neurons=[1024, 256], mano_center_idx=0, mano_lambda_verts=0.167, mano_lambda_joints3d=0.167,
+           mano_lambda_shape=0.167, mano_lambda_pose_reg=0.167, atlas_lambda=0.167, atlas_final_lambda=0.167,
+           atlas_mesh=True, atlas_predict_trans=True, atlas_predict_scale=True, atlas_trans_weight=0.167,
+           atlas_scale_weight=0.167, atlas_separate_encoder=False, atlas_ico_divisions=3, atlas_points_nb=600)
+PER_GPU_BATCH = 64
+IMG = 256
+N_GT = 600
+
+
+def synthetic_sample(B, seed):
+    """images U(0,1)-0.5; verts/joints N(0,40^2); object points N(0,40^2)+30 (mm)."""
+    g = torch.Generator().manual_seed(seed)
+    return {
+        "images": torch.rand(B, 3, IMG, IMG, generator=g) - 0.5,
+        "sides": ["right" if i % 2 == 0 else "left" for i in range(B)],
+        "root": "wrist",
+        "joints3d": torch.randn(B, 21, 3, generator=g) * 40,
+        "verts3d": torch.randn(B, 778, 3, generator=g) * 40,
+        "objpoints3d": torch.randn(B, N_GT, 3, generator=g) * 40 + 30,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md): nvidia-smi polled during the timed region
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port; the reference itself cannot travel to the GPU box)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(batch, steps, warmup):
+    """Train step (fwd + bwd + Adam) of the reference algorithm on the host cores: oracle/nets.py, pinned
+    against the reference's own files by tests/test_oracle_vs_reference.py.  Returns seconds per step."""
+    from oracle import nets
+    from obman_train_b200.networks.handnet import HandNet
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = HandNet(**CFG).eval()
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    leaves = []
+    for k, v in state.items():
+        if v.is_floating_point() and "running_" not in k and "th_" not in k and ".fc." not in k:
+            v.requires_grad_(True)
+            leaves.append(v)
+    opt = torch.optim.Adam(leaves, lr=1e-4)
+    tables = {s: {k: v.detach() for k, v in getattr(model.mano_branch, "mano_layer_" + s).named_buffers()
+                  if k != "th_faces"} for s in ("right", "left")}
+    grid, faces = model.atlas_branch.test_verts, model.atlas_branch.test_faces
+    sample = synthetic_sample(batch, 0)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        total, _, _ = nets.handnet_forward(state, CFG, sample, tables, grid, faces, None)
+        total.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 8
+    sec, threads = cpu_reference_steps(batch, max(1, min(args.steps, 5)), 1)
+    val = batch / sec
+    line = {
+        "impl": "reference", "metric": "train-step images/sec", "value": val, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": "batch %d of the same workload, fwd+bwd+Adam, oracle/nets.py on torch CPU" % batch},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE.json configs[1]: train step fwd+bwd+Adam, ResNet-18 + ManoLayer(778v) + "
+                        "AtlasNet(642 pts) + Chamfer(600 GT) + Mano/Atlas losses, 256x256",
+            "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * n_gpus,
+            "parallelism": "dp%d" % n_gpus, "precision": "3xTF32 tensor-core passes (fp32-equivalent) fwd+bwd",
+            "l2_policy": "activations per step (~3 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from obman_train_b200 import _lib, dense
+    from obman_train_b200.networks.handnet import HandNet
+    from obman_train_b200.trainer import FlatAdamTrainer
+    from obman_train_b200.queries import TransQueries, BaseQueries
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    if lib.obman_device_ok() != 0:
+        raise RuntimeError(lib.obman_get_last_error().decode())
+    dense.set_precision(args.precision, args.precision)
+
+    torch.manual_seed(0)  # identical replicas on every rank
+    model = HandNet(**CFG).eval().cuda()
+    trainer = FlatAdamTrainer(model, lr=1e-4, world_size=world)
+    B = PER_GPU_BATCH
+    host = synthetic_sample(B, 1000 + rank)
+    pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
+
+    def to_device(src):
+        return {TransQueries.images: src["images"].cuda(non_blocking=True), BaseQueries.sides: src["sides"],
+                "root": src["root"], TransQueries.joints3d: src["joints3d"].cuda(non_blocking=True),
+                TransQueries.verts3d: src["verts3d"].cuda(non_blocking=True),
+                TransQueries.objpoints3d: src["objpoints3d"].cuda(non_blocking=True)}
+
+    resident = to_device(pinned)
+    h2d = sum(v.numel() * 4 for v in host.values() if torch.is_tensor(v))
+
+    def timed(n_steps, fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return ms.item()
+
+    def step_resident():
+        trainer.step(resident)
+
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step_e2e():
+        loss = trainer.step(to_device(pinned))
+        loss_host.copy_(loss.detach(), non_blocking=False)  # the user's read of the step result
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    kern0 = _lib.kernel_count
+    ms = timed(args.steps, step_resident)
+    kernels = _lib.kernel_count - kern0
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(args.steps, step_e2e)
+
+    # roofline of the dominant kernel (gemm_tc_kernel): per-launch CUDA events + algorithmic FLOPs
+    dense.profile_begin()
+    nprof = min(args.steps, 3)
+    for _ in range(nprof):
+        step_resident()
+    dense.profile_end.steps = nprof
+    prof = dense.profile_end()
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured" if peaks else "fallback"
+    tf32_peak = bf16 / 2.0
+    value = B * world * args.steps / (ms / 1e3)
+    e2e = B * world * args.steps / (ms_e2e / 1e3)
+    line = {
+        "metric": "train-step images/sec", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32x3" if args.precision == "tf32x3" else "tf32", "data": "synthetic",
+        "config": workload_config(world), "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(kernels),
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (all conv/GEMM launches of a step)",
+                     "achieved": prof["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": prof["tflops"] / tf32_peak,
+                     "peak_source": "%s bf16_tflops_sustained / 2 (TF32 rate)" % peak_src,
+                     "tensor_pipe_tflops_incl_3x_passes": prof["tflops"] * (3 if args.precision == "tf32x3" else 1),
+                     "gemm_ms_per_step": prof["ms_per_step"], "gemm_launches_per_step": prof["launches_per_step"],
+                     "share_of_step": prof["ms_per_step"] / (ms / args.steps), "traffic": None},
+    }
+    if not args.no_cpu_baseline:
+        sec, threads = cpu_reference_steps(8, 2, 1)
+        line["cpu_baseline"] = {"value": 8 / sec, "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": "batch 8 of the same workload (fwd+bwd+Adam), 2 timed steps, oracle/nets.py"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,15 +63,19 @@ def load():
     return lib
 
 
-launch_count = 0  # kernels-launching C calls issued (bench.py reads this for its gpu_launches claim)
+launch_count = 0  # kernel-launching C calls issued
+kernel_count = 0  # kernels those calls launched (bench.py reads this for its gpu_launches claim)
+KERNELS_PER_CALL = {"obman_chamfer_fwd": 2, "obman_contact_fwd": 2, "obman_mano_fwd": 3, "obman_mano_bwd": 3,
+                    "obman_pointmlp_l1_bwd": 2}
 
 
 def call(name, *args):
     """Call an int-returning entry point; raise RuntimeError(obman_get_last_error()) on failure."""
-    global launch_count
+    global launch_count, kernel_count
     lib = load()
     rc = getattr(lib, name)(*args)
     launch_count += 1
+    kernel_count += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         msg = lib.obman_get_last_error()
         raise RuntimeError("{} failed (rc={}): {}".format(name, rc, msg.decode() if msg else "?"))

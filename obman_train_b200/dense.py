@@ -23,6 +23,37 @@ def get_precision():
     return dict(_precision)
 
 
+# ---- optional per-launch profiling (bench.py roofline): CUDA events on the launching stream ------------------
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """Returns algorithmic TFLOP/s of all tensor-core launches since profile_begin (sum flops / sum time)."""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    ms = sum(e0.elapsed_time(e1) for _, e0, e1 in rec)
+    flops = sum(f for f, _, _ in rec)
+    steps = max(1, getattr(profile_end, "steps", 1))
+    return {"tflops": flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, "ms_total": ms, "launches": len(rec),
+            "ms_per_step": ms / steps, "launches_per_step": len(rec) / steps, "flops": flops}
+
+
+def _tc_call(flops, name, *args):
+    if _prof is None:
+        return call(name, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(name, *args)
+    e1.record()
+    _prof.append((float(flops), e0, e1))
+
+
 def _ints(vals):
     return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
 
@@ -43,7 +74,7 @@ def gemm(a, w, out=None, bias=None, addend=None, mask_src=None, alpha=1.0, relu=
     N = n if n is not None else w.shape[0]
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32)
-    call("obman_gemm", ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, ptr(out), out.stride(0),
+    _tc_call(2.0 * M * N * K, "obman_gemm", ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, ptr(out), out.stride(0),
          ptr(bias), ptr(addend), ptr(mask_src), float(alpha), int(relu), int(accumulate), int(passes),
          stream_ptr())
     return out
@@ -80,7 +111,7 @@ def dgrad_taps(ksize, stride, pad, out_phase=(0, 0)):
 
 
 def conv_nhwc(x, w, c_out, taps, in_step, out, h_out, w_out, out_strides=None, out_offset=0,
-              bias=None, addend=None, mask_src=None, relu=False, passes=3, w_slots=None):
+              bias=None, addend=None, mask_src=None, relu=False, passes=3, w_slots=None, algo_k=None):
     """Raw obman_conv_nhwc call.  x (N,H,W,C) contiguous; w (c_out, slots*C); taps = (dh, dw, phase, slot).
     ``out`` is any tensor whose storage receives element (n,h,w,c) at out_offset + n*sN + h*sH + w*sW + c."""
     _chk(x, "x"); _chk(w, "w")
@@ -95,7 +126,9 @@ def conv_nhwc(x, w, c_out, taps, in_step, out, h_out, w_out, out_strides=None, o
     def off(t):
         return None if t is None else t.data_ptr() + out_offset * esz
 
-    call("obman_conv_nhwc", ptr(x), n_img, h_in, w_in, c_in, int(in_step), ptr(w), int(c_out),
+    k_eff = algo_k if algo_k is not None else len(dh) * c_in
+    _tc_call(2.0 * n_img * h_out * w_out * c_out * k_eff,
+             "obman_conv_nhwc", ptr(x), n_img, h_in, w_in, c_in, int(in_step), ptr(w), int(c_out),
          int(w_slots), len(dh), _ints(dh), _ints(dw), _ints(phase) if phase is not None else None,
          _ints(slot), off(out), int(h_out), int(w_out), int(out_strides[0]), int(out_strides[1]),
          int(out_strides[2]), ptr(bias), off(addend), off(mask_src), int(relu), int(passes),
@@ -103,13 +136,15 @@ def conv_nhwc(x, w, c_out, taps, in_step, out, h_out, w_out, out_strides=None, o
     return out
 
 
-def wgrad_nhwc(dy, x, taps, in_step, dw_out, w_slots, passes=3):
+def wgrad_nhwc(dy, x, taps, in_step, dw_out, w_slots, passes=3, algo_k=None):
     """dw_out (c_out, w_slots*c_in) = sum over pixels dy (N,Ho,Wo,c_out) x shifted x (N,H,W,c_in)."""
     _chk(dy, "dy"); _chk(x, "x"); _chk(dw_out, "dw")
     n_img, h_out, w_out, c_out = dy.shape
     _, h_in, w_in, c_in = x.shape
     dh, dw, phase, slot = taps
-    call("obman_wgrad_nhwc", ptr(dy), n_img, h_out, w_out, c_out, ptr(x), h_in, w_in, c_in,
+    k_eff = algo_k if algo_k is not None else len(dh) * c_in
+    _tc_call(2.0 * n_img * h_out * w_out * c_out * k_eff,
+             "obman_wgrad_nhwc", ptr(dy), n_img, h_out, w_out, c_out, ptr(x), h_in, w_in, c_in,
          int(in_step), len(dh), _ints(dh), _ints(dw), _ints(phase) if phase is not None else None,
          _ints(slot), ptr(dw_out), int(w_slots), int(passes), stream_ptr())
     return dw_out

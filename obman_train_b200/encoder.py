@@ -64,7 +64,8 @@ class _Unit(object):
     def fprop(self, x, h_out, w_out, addend=None, relu=True, passes=3):
         out = _empty(x.shape[0], h_out, w_out, self.O)
         dense.conv_nhwc(x, self.wf, self.O, self.taps, self.in_step, out, h_out, w_out, bias=self.shift,
-                        addend=addend, relu=relu, passes=passes, w_slots=self.slots)
+                        addend=addend, relu=relu, passes=passes, w_slots=self.slots,
+                        algo_k=147 if self.stem else None)
         return out
 
     def dgrad(self, g, h_in, w_in, addend=None, mask_src=None, passes=3):
@@ -92,7 +93,8 @@ class _Unit(object):
 
     def wgrad(self, g, x, passes=3):
         dwraw = _empty(self.O, self.slots * self.Ip)
-        dense.wgrad_nhwc(g, x, self.taps, self.in_step, dwraw, self.slots, passes=passes)
+        dense.wgrad_nhwc(g, x, self.taps, self.in_step, dwraw, self.slots, passes=passes,
+                         algo_k=147 if self.stem else None)
         return dwraw
 
     def finish(self, dwraw, gbeta_sum):

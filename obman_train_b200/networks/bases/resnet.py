@@ -93,13 +93,15 @@ class ResNet(nn.Module):
 
 
 def resnet18(pretrained=False, **kwargs):
-    """ResNet-18; ``pretrained=True`` needs the torchvision ImageNet checkpoint, which cannot be fetched
-    offline: a warning is emitted and the random initialisation is kept."""
+    """ResNet-18; ``pretrained=True`` loads the torchvision ImageNet checkpoint from the local torch-hub cache
+    (``resnet18-5c106cde.pth``) when it is there.  No download is attempted (no network on the B200 boxes):
+    if the file is absent a warning is emitted and the random initialisation is kept."""
     model = ResNet(BasicBlock, [2, 2, 2, 2], **kwargs)
     if pretrained:
-        try:
-            import torch.utils.model_zoo as model_zoo
-            model.load_state_dict(model_zoo.load_url("https://download.pytorch.org/models/resnet18-5c106cde.pth"))
-        except Exception as exc:  # noqa: BLE001
-            warnings.warn("ImageNet weights unavailable ({}); keeping random init".format(type(exc).__name__))
+        import os
+        path = os.path.join(torch.hub.get_dir(), "checkpoints", "resnet18-5c106cde.pth")
+        if os.path.exists(path):
+            model.load_state_dict(torch.load(path, map_location="cpu"))
+        else:
+            warnings.warn("ImageNet weights not found at {}; keeping random init".format(path))
     return model

@@ -27,21 +27,25 @@ class FlatAdamTrainer(object):
         params = [(n, p) for n, p in model.named_parameters()
                   if p.requires_grad and ".fc." not in "." + n + "."]
         self.names = [n for n, _ in params]
-        total = sum(p.numel() for _, p in params)
+        # every parameter starts on a 256-byte boundary (TMA operands must be 16-byte aligned)
+        align = 64
+        offsets, total = [], 0
+        for _, p in params:
+            offsets.append(total)
+            total += (p.numel() + align - 1) // align * align
         dev = params[0][1].device
-        self.flat_p = torch.empty(total, device=dev, dtype=torch.float32)
+        self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
-        off = 0
-        for _, p in params:
+        for (_, p), off in zip(params, offsets):
             n = p.numel()
             self.flat_p[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + n].view_as(p)
             p.grad = self.flat_g[off:off + n].view_as(p)
-            off += n
         self.params = [p for _, p in params]
         self.numel = total
+        self.param_numel = sum(p.numel() for _, p in params)
         self.step_count = 0
 
     def zero_grad(self):

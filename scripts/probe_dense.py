@@ -146,6 +146,14 @@ CASES = {
     "conv3x3_s2_32_64_128_p3": lambda: case_conv(2, 32, 64, 128, 3, 2, 3),
     "conv1x1_s2_32_64_128_p3": lambda: case_conv(2, 32, 64, 128, 1, 2, 3),
     "conv3x3_s1_20_36_40_p3": lambda: case_conv(2, 20, 36, 40, 3, 1, 3),
+    "small_conv3x3_s1_4_512_512_p3": lambda: case_conv(4, 4, 512, 512, 3, 1, 3),
+    "small_conv3x3_s1_2_512_512_p3": lambda: case_conv(2, 2, 512, 512, 3, 1, 3, True),
+    "small_dgrad3x3_s1_4_512_512_p3": lambda: case_dgrad(4, 4, 512, 512, 3, 1, 3),
+    "small_dgrad3x3_s1_2_512_512_p3": lambda: case_dgrad(2, 2, 512, 512, 3, 1, 3),
+    "small_dgrad3x3_s2_4_256_512_p3": lambda: case_dgrad(2, 4, 256, 512, 3, 2, 3),
+    "small_wgrad3x3_s1_4_512_512_p3": lambda: case_wgrad(4, 4, 512, 512, 3, 1, 3),
+    "small_wgrad3x3_s1_2_512_512_p3": lambda: case_wgrad(2, 2, 512, 512, 3, 1, 3),
+    "small_wgrad3x3_s2_4_256_512_p3": lambda: case_wgrad(2, 4, 256, 512, 3, 2, 3),
     "dgrad3x3_s1_16_64_64_p3": lambda: case_dgrad(2, 16, 64, 64, 3, 1, 3),
     "dgrad3x3_s2_32_64_128_p3": lambda: case_dgrad(2, 32, 64, 128, 3, 2, 3),
     "dgrad1x1_s2_32_64_128_p3": lambda: case_dgrad(2, 32, 64, 128, 1, 2, 3),

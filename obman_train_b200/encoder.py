@@ -15,6 +15,7 @@ from . import dense
 from ._lib import call, ptr, stream_ptr
 
 BN_EPS = 1e-5
+DEBUG = None  # set to a dict to capture intermediate gradients (diagnostics only)
 
 # (name, out_ch, in_ch, ksize, stride) of the 20 conv+BN units in state-dict order
 def resnet18_units():
@@ -175,12 +176,16 @@ class _EncoderFn(torch.autograd.Function):
         g2 = torch.empty_like(last)
         call("obman_meanpool_bwd", ptr(gfeat), ptr(last), B, hl * wl, 512, ptr(g2), st)
         grads = {}
-        for (u1, u2, ud, x, a, out, h, w_) in reversed(blocks):
+        for bidx, (u1, u2, ud, x, a, out, h, w_) in reversed(list(enumerate(blocks))):
             ho, wo = out.shape[1], out.shape[2]
+            if DEBUG is not None:
+                DEBUG["g_out_%d" % bidx] = g2.clone()
             rows = B * ho * wo
             gb2 = colsum(rows, u2.O, g2)
             grads[id(u2)] = u2.finish(u2.wgrad(g2, a, pb), gb2)
             g1 = u2.dgrad(g2, ho, wo, mask_src=a, passes=pb)
+            if DEBUG is not None:
+                DEBUG["g_a_%d" % bidx] = g1.clone()
             grads[id(u1)] = u1.finish(u1.wgrad(g1, x, pb), colsum(rows, u1.O, g1))
             if ud is not None:
                 grads[id(ud)] = ud.finish(ud.wgrad(g2, x, pb), gb2)
@@ -191,6 +196,9 @@ class _EncoderFn(torch.autograd.Function):
         # g2 is now the gradient w.r.t. the max-pool output (already masked by p > 0)
         gc1 = _empty(B, H // 2, W // 2, 64)
         call("obman_maxpool_bwd", ptr(g2), ptr(pidx), B, H // 2, W // 2, 64, ptr(gc1), st)
+        if DEBUG is not None:
+            DEBUG["g_p"] = g2.clone()
+            DEBUG["g_c1"] = gc1.clone()
         u0 = units[0]
         grads[id(u0)] = u0.finish(u0.wgrad(gc1, xs, pb), colsum(B * (H // 2) * (W // 2), 64, gc1))
         outs = [None]

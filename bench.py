@@ -101,7 +101,9 @@ def cpu_reference_steps(batch, steps, warmup):
     against the reference's own files by tests/test_oracle_vs_reference.py.  Returns seconds per step."""
     from oracle import nets
     from obman_train_b200.networks.handnet import HandNet
-    threads = os.cpu_count() or 1
+    # all host cores up to 32 threads: beyond that torch's CPU conv/bmm kernels slow down on this workload
+    # (measured on the 128-core GPU box: 128 threads gave 0.26 img/s where 8 threads give ~19 img/s)
+    threads = min(os.cpu_count() or 1, int(os.environ.get("OBMAN_BENCH_CPU_THREADS", "32")))
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     model = HandNet(**CFG).eval()
@@ -132,8 +134,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 8
-    sec, threads = cpu_reference_steps(batch, max(1, min(args.steps, 5)), 1)
+    batch = int(os.environ.get("OBMAN_BENCH_CPU_BATCH", "8"))
+    sec, threads = cpu_reference_steps(batch, max(1, min(args.steps, 5)), min(1, args.warmup))
     val = batch / sec
     line = {
         "impl": "reference", "metric": "train-step images/sec", "value": val, "unit": "images/s",

@@ -135,6 +135,8 @@ class _EncoderFn(torch.autograd.Function):
         xs = _empty(B, H // 2, W // 2, 32)
         call("obman_stem_pack", ptr(images), B, H, W, ptr(xs), st)
         c1 = units[0].fprop(xs, H // 2, W // 2, relu=True, passes=pf)
+        if DEBUG is not None:
+            DEBUG["act_c1"] = c1
         hp, wp = H // 4, W // 4
         p = _empty(B, hp, wp, 64)
         pidx = torch.empty((B, hp, wp, 64), device="cuda", dtype=torch.uint8)
@@ -155,6 +157,9 @@ class _EncoderFn(torch.autograd.Function):
                 r = ud.fprop(x, ho, wo, relu=False, passes=pf) if ud is not None else x
                 out = u2.fprop(a, ho, wo, addend=r, relu=True, passes=pf)
                 blocks.append((u1, u2, ud, x, a, out, h, w_))
+                if DEBUG is not None:
+                    DEBUG["act_a%d" % (len(blocks) - 1)] = a
+                    DEBUG["act_out%d" % (len(blocks) - 1)] = out
                 x, h, w_ = out, ho, wo
                 ui = nxt
         feats = _empty(B, 512)

@@ -59,9 +59,18 @@ class FlatAdamTrainer(object):
         self.reduce_and_update()
         return loss
 
-    def reduce_and_update(self):
+    def all_reduce_grads(self):
+        """The only data-path collective of the step: one sum all-reduce of the flat gradient buffer."""
         if self.world_size > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+
+    def reduce_and_update(self):
+        self.all_reduce_grads()
+        self.adam_update()
+
+    def adam_update(self):
+        if not self.flat_p.is_cuda:
+            raise RuntimeError("FlatAdamTrainer.adam_update: the fused Adam kernel needs CUDA buffers (no CPU path)")
         self.step_count += 1
         call("obman_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.exp_avg), ptr(self.exp_avg_sq),
              self.numel, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),

@@ -27,18 +27,42 @@ def _bn(x, state, prefix, training):
     return F.batch_norm(x, rm, rv, w, b, False, 0.0, BN_EPS)
 
 
-def resnet18_features(state, images, prefix="base_net", bn_training=False):
-    """(B,3,H,W) -> (B,512); conv7x7/2, BN, ReLU, maxpool3/2, 4x2 BasicBlocks, spatial mean."""
+class _ReluWithMask(torch.autograd.Function):
+    """relu(z) whose backward uses an externally supplied branch mask.  Test-only: lets a gradient check
+    follow the ReLU branches the implementation under test actually took (a pre-activation within rounding
+    of zero may legitimately fall on the other side), so that the comparison measures arithmetic, not flips."""
+
+    @staticmethod
+    def forward(ctx, z, mask):
+        ctx.save_for_backward(mask)
+        return z.clamp(min=0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return g * mask.to(g.dtype), None
+
+
+def _relu(z, masks, name):
+    if masks is None:
+        return F.relu(z)
+    return _ReluWithMask.apply(z, masks[name])
+
+
+def resnet18_features(state, images, prefix="base_net", bn_training=False, relu_masks=None):
+    """(B,3,H,W) -> (B,512); conv7x7/2, BN, ReLU, maxpool3/2, 4x2 BasicBlocks, spatial mean.
+    ``relu_masks`` (tests only): {"c1", "a0".."a7", "out0".."out7"} -> bool NCHW branch masks."""
     p = prefix + "."
     x = F.conv2d(images, state[p + "conv1.weight"], None, stride=2, padding=3)
-    x = F.relu(_bn(x, state, p + "bn1", bn_training))
+    x = _relu(_bn(x, state, p + "bn1", bn_training), relu_masks, "c1")
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    b = 0
     for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
         for bi in range(2):
             q = "{}layer{}.{}.".format(p, li, bi)
             s = stride if bi == 0 else 1
             out = F.conv2d(x, state[q + "conv1.weight"], None, stride=s, padding=1)
-            out = F.relu(_bn(out, state, q + "bn1", bn_training))
+            out = _relu(_bn(out, state, q + "bn1", bn_training), relu_masks, "a%d" % b)
             out = F.conv2d(out, state[q + "conv2.weight"], None, stride=1, padding=1)
             out = _bn(out, state, q + "bn2", bn_training)
             if (q + "downsample.0.weight") in state:
@@ -46,7 +70,8 @@ def resnet18_features(state, images, prefix="base_net", bn_training=False):
                 res = _bn(res, state, q + "downsample.1", bn_training)
             else:
                 res = x
-            x = F.relu(out + res)
+            x = _relu(out + res, relu_masks, "out%d" % b)
+            b += 1
     return x.mean(3).mean(2)
 
 

@@ -18,35 +18,43 @@ def _randomise_bn(model, seed):
             m.running_var.data = 0.5 + torch.rand(m.running_var.shape, generator=g)
 
 
-@pytest.mark.parametrize("B,H,precision,tol,grad_tol", [(2, 64, "tf32x3", 1e-4, 5e-2), (3, 96, "tf32x3", 1e-4, 1e-3),
-                                                        (4, 128, "tf32x3", 1e-4, 1e-3), (2, 64, "tf32", 2e-2, 0.5)])
+@pytest.mark.parametrize("B,H,precision,tol,grad_tol", [(2, 64, "tf32x3", 1e-4, 1e-3), (3, 96, "tf32x3", 1e-4, 1e-3),
+                                                        (4, 128, "tf32x3", 1e-4, 1e-3), (2, 64, "tf32", 2e-2, 5e-2)])
 def test_resnet18_fwd_bwd_vs_oracle(B, H, precision, tol, grad_tol):
-    from obman_train_b200 import dense
+    """Features vs the plain fp64 oracle; gradients vs the fp64 oracle evaluated on the ReLU branches the CUDA
+    forward took (oracle.nets._ReluWithMask): a pre-activation within the forward error (~5e-5 with 3xTF32)
+    of zero may fall on the other side than in fp64, and one such flip moves whole gradient fields by percents
+    (measured: scripts/diag_encoder2.py), which says nothing about the arithmetic under test."""
+    from obman_train_b200 import dense, encoder
     from obman_train_b200.networks.bases.resnet import resnet18
     torch.manual_seed(0)
     model = resnet18()
     _randomise_bn(model, 1)
     model.eval()
     state64 = {"base_net." + k: v.detach().double().clone() for k, v in model.state_dict().items()}
-    for v in state64.values():
-        pass
     for k, v in state64.items():
         if v.is_floating_point() and "running_" not in k:
             v.requires_grad_(True)
     g = torch.Generator().manual_seed(2)
     images = torch.rand(B, 3, H, H, generator=g) - 0.5
     wts = torch.randn(B, 512, generator=g)
-    ref = nets.resnet18_features(state64, images.double(), "base_net", False)
-    (ref * wts.double()).sum().backward()
 
     model = model.cuda()
     dense.set_precision(precision, precision)
+    encoder.DEBUG = {}
     try:
         feats, extra = model(images.cuda())
         assert extra == {}
         (feats * wts.cuda()).sum().backward()
+        masks = {k[4:]: (v.permute(0, 3, 1, 2) > 0).cpu() for k, v in encoder.DEBUG.items() if k.startswith("act_")}
     finally:
         dense.set_precision("tf32x3", "tf32x3")
+        encoder.DEBUG = None
+    ref_plain = nets.resnet18_features({k: v.detach() for k, v in state64.items()}, images.double(), "base_net", False)
+    ref = nets.resnet18_features(state64, images.double(), "base_net", False, relu_masks=masks)
+    (ref * wts.double()).sum().backward()
+    assert (ref_plain - ref.detach()).abs().max() < 1e-3 * ref_plain.abs().max()
+    ref = ref_plain
     scale = ref.abs().max().item()
     err = (feats.detach().cpu().double() - ref.detach()).abs().max().item()
     assert err < tol * scale, (err, scale)

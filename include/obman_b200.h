@@ -98,10 +98,14 @@ int obman_mano_bwd(const float* v_template, const float* shapedirs, const float*
  * obman_gemm: out[M,N] = epilogue(alpha * A[M,K] * W[N,K]^T); replaces nn.Linear / Conv1d(k=1) calls
  * (manobranch.py:124-147, atlasbranch.py:44-61, atlasutils.py:65-75).  Row-major, leading dimensions in
  * elements (lda, ldw multiples of 4; A, W 16-byte aligned).  epilogue: + bias[N] + addend[M,N] (ldo),
- * ReLU, zero where mask_src[M,N] (ldo) <= 0, then store or atomicAdd (accumulate). */
-int obman_gemm(const float* A, long long lda, const float* W, long long ldw, int M, int N, int K,
-               float* out, long long ldo, const float* bias, const float* addend,
+ * ReLU, zero where mask_src[M,N] (ldo) <= 0, then store or atomicAdd (accumulate).  W_lo (NULL or the
+ * residual of pre-split weights, W then being the tf32-rounded part) selects the A-in-TMEM kernel. */
+int obman_gemm(const float* A, long long lda, const float* W, const float* W_lo, long long ldw, int M,
+               int N, int K, float* out, long long ldo, const float* bias, const float* addend,
                const float* mask_src, float alpha, int relu, int accumulate, int passes, void* stream);
+/* hi = tf32-rounded w, lo = w - hi (n floats): weights pre-split for the 3xTF32 path whose A operand is
+ * staged in tensor memory (pass them as W / W_lo, w / w_lo). */
+int obman_split_tf32(const float* w, long long n, float* hi, float* lo, void* stream);
 
 /* obman_conv_nhwc: NHWC convolution as implicit GEMM; forward and data-gradient of nn.Conv2d
  * (mano_train/networks/bases/resnet.py:19-23,38-54,110-152) share it.  x (n_img,h_in,w_in,c_in),
@@ -110,19 +114,18 @@ int obman_gemm(const float* A, long long lda, const float* W, long long ldw, int
  * (zero outside the view).  out is written at n*o_sN + h*o_sH + w*o_sW + c (elements) for h < h_out,
  * w < w_out; bias[c_out], addend / mask_src indexed like out (NULL to disable), relu flag. */
 int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, int c_in, int in_step,
-                    const float* w, int c_out, int w_slots, int num_taps, const int* tap_dh,
-                    const int* tap_dw, const int* tap_phase, const int* tap_wslot, float* out,
-                    int h_out, int w_out, long long o_sN, long long o_sH, long long o_sW,
+                    const float* w, const float* w_lo, int c_out, int w_slots, int num_taps,
+                    const int* tap_dh, const int* tap_dw, const int* tap_phase, const int* tap_wslot,
+                    float* out, int h_out, int w_out, long long o_sN, long long o_sH, long long o_sW,
                     const float* bias, const float* addend, const float* mask_src, int relu,
                     int passes, void* stream);
 
-/* obman_wgrad_nhwc: dw[co, slot(t)*c_in + ci] = sum_{n,h,w} dy[n,h,w,co] * xview_t[n, h+dh, w+dw, ci];
- * weight gradient of the convolution above and (h = 1) of obman_gemm.  c_out, c_in multiples of 32.
- * dw (c_out, w_slots*c_in) is overwritten. */
+/* obman_wgrad_nhwc: dw[co, t*c_in + ci] = sum_{n,h,w} dy[n,h,w,co] * xview_t[n, h+dh[t], w+dw[t], ci];
+ * weight gradient of the convolution above and (h = 1) of obman_gemm, as ONE GEMM with the taps stacked
+ * along N.  c_out, c_in multiples of 32.  dw (c_out, num_taps*c_in) is overwritten. */
 int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out, int c_out, const float* x,
                      int h_in, int w_in, int c_in, int in_step, int num_taps, const int* tap_dh,
-                     const int* tap_dw, const int* tap_phase, const int* tap_wslot, float* dw,
-                     int w_slots, int passes, void* stream);
+                     const int* tap_dw, const int* tap_phase, float* dw, int passes, void* stream);
 
 /* ---- Encoder helpers (bandwidth-bound; mano_train/networks/bases/resnet.py:154-188) -----------------------
  * obman_stem_pack: x (B,3,H,W) NCHW -> out (B,H/2,W/2,32) NHWC space-to-depth (channel (ph*2+pw)*3+c,
@@ -130,11 +133,13 @@ int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out, int c_out
 int obman_stem_pack(const float* x, int B, int H, int W, float* out, void* stream);
 /* BatchNorm(eval) folding + weight re-layout, once per step.  w (O,I,KH,KW); gamma/beta/mean/var (O) or NULL
  * (no BN), cbias (O) conv bias or NULL: shift = beta + (cbias - mean)*scale (no BN: shift = cbias).
+ * wf_lo / wft_lo (NULL or): pre-split mode, wf/wft = tf32-rounded value, *_lo = residual.
  * wf (O, KH*KW*Ip) fprop operand, wft (I, KH*KW*O) dgrad operand
  * (NULL to skip), shift/scale/rstd (O).  stem=1: (O,3,7,7) filter -> (O, 16*32) space-to-depth layout. */
 int obman_fold_conv(const float* w, const float* cbias, const float* gamma, const float* beta, const float* mean,
                     const float* var, float eps, int O, int I, int KH, int KW, int Ip, int stem,
-                    float* wf, float* wft, float* shift, float* scale, float* rstd, void* stream);
+                    float* wf, float* wf_lo, float* wft, float* wft_lo, float* shift, float* scale,
+                    float* rstd, void* stream);
 /* MaxPool2d(3, stride 2, pad 1), NHWC (resnet.py:107): idx (B,H/2,W/2,C) u8 = arg-max window slot. */
 int obman_maxpool_fwd(const float* x, int B, int H, int W, int C, float* out, unsigned char* idx,
                       void* stream);

@@ -12,6 +12,12 @@
 
 namespace obman {
 
+__device__ __forceinline__ float to_tf32_rna_dev(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // x (B,3,H,W) NCHW  ->  out (B, H/2, W/2, 32): channel (ph*2+pw)*3 + c = x[b, c, 2i+ph, 2j+pw], channels 12..31 = 0
 __global__ void __launch_bounds__(256)
 stem_pack_kernel(const float* __restrict__ x, int B, int H, int W, float* __restrict__ out) {
@@ -37,6 +43,8 @@ stem_pack_kernel(const float* __restrict__ x, int B, int H, int W, float* __rest
 }
 
 // Folded weights for one convolution.  w (O,I,KH,KW); scale s[o] = gamma*rsqrt(var+eps) (or 1 without BN).
+// When wf_lo / wft_lo are given, wf / wft hold the tf32-rounded value and the *_lo arrays the residual
+// (pre-split operands of the 3xTF32 A-in-TMEM GEMM path).
 //   wf [o][(kh*KW+kw)*Ip + i] = s[o]*w[o,i,kh,kw]        (fprop B operand; Ip = padded input channels)
 //   wft[i][(kh*KW+kw)*O  + o] = s[o]*w[o,i,kh,kw]        (dgrad B operand), i < I only
 //   shift[o] = beta + (conv_bias - mean)*s ; scale[o] = s ; rstd[o]
@@ -46,8 +54,9 @@ fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
                  const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ mean,
                  const float* __restrict__ var, float eps, int O, int I, int KH, int KW, int Ip,
-                 int stem, float* __restrict__ wf, float* __restrict__ wft, float* __restrict__ shift,
-                 float* __restrict__ scale, float* __restrict__ rstd_out) {
+                 int stem, float* __restrict__ wf, float* __restrict__ wf_lo, float* __restrict__ wft,
+                 float* __restrict__ wft_lo, float* __restrict__ shift, float* __restrict__ scale,
+                 float* __restrict__ rstd_out) {
   const int o = blockIdx.x;
   float s = 1.f, rs = 1.f;
   if (gamma) {
@@ -71,7 +80,9 @@ fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
         const int kh = 2 * a + ph + 3, kw = 2 * b + pw + 3;
         if (kh >= 0 && kh < 7 && kw >= 0 && kw < 7) v = s * w[((o * 3 + c) * 7 + kh) * 7 + kw];
       }
-      wf[(size_t)o * 512 + k] = v;
+      const float h = to_tf32_rna_dev(v);
+      wf[(size_t)o * 512 + k] = wf_lo ? h : v;
+      if (wf_lo) wf_lo[(size_t)o * 512 + k] = v - h;
     }
     return;
   }
@@ -79,11 +90,15 @@ fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
   for (int k = threadIdx.x; k < taps * Ip; k += blockDim.x) {
     const int t = k / Ip, i = k - t * Ip;
     float v = 0.f;
-    if (i < I) {
-      v = s * w[((size_t)o * I + i) * taps + t];
-      if (wft) wft[(size_t)i * taps * O + (size_t)t * O + o] = v;
+    if (i < I) v = s * w[((size_t)o * I + i) * taps + t];
+    const float h = to_tf32_rna_dev(v);
+    if (i < I && wft) {
+      const size_t ot = (size_t)i * taps * O + (size_t)t * O + o;
+      wft[ot] = wft_lo ? h : v;
+      if (wft_lo) wft_lo[ot] = v - h;
     }
-    wf[(size_t)o * taps * Ip + k] = v;
+    wf[(size_t)o * taps * Ip + k] = wf_lo ? h : v;
+    if (wf_lo) wf_lo[(size_t)o * taps * Ip + k] = v - h;
   }
 }
 
@@ -348,13 +363,14 @@ extern "C" int obman_stem_pack(const float* x, int B, int H, int W, float* out, 
 
 extern "C" int obman_fold_conv(const float* w, const float* cbias, const float* gamma, const float* beta, const float* mean,
                                const float* var, float eps, int O, int I, int KH, int KW, int Ip, int stem,
-                               float* wf, float* wft, float* shift, float* scale, float* rstd,
-                               void* stream) {
+                               float* wf, float* wf_lo, float* wft, float* wft_lo, float* shift, float* scale,
+                               float* rstd, void* stream) {
   OBMAN_REQUIRE(w && wf && shift && scale && rstd && O > 0 && I > 0 && KH > 0 && KW > 0 && Ip >= I,
                 "obman_fold_conv: bad arguments");
   OBMAN_REQUIRE(!stem || (I == 3 && KH == 7 && KW == 7), "obman_fold_conv: stem layout needs a (O,3,7,7) filter");
+  OBMAN_REQUIRE(!wft_lo || wft, "obman_fold_conv: wft_lo without wft");
   fold_conv_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(w, cbias, gamma, beta, mean, var, eps, O, I, KH, KW, Ip, stem,
-                                                        wf, wft, shift, scale, rstd);
+                                                        wf, wf_lo, wft, wft_lo, shift, scale, rstd);
   return check_launch("fold_conv_kernel");
 }
 

@@ -5,14 +5,21 @@
 //   * weight gradients of all of the above (reduction over pixels: MN-major operands, MODE 1)
 //
 // D[128 x BN] (fp32, TMEM) = sum over taps and 32-wide K blocks of A_tile[128 x 32] * B_tile[BN x 32]^T
-//   A: activations. plain mode: row-major (M, K) matrix, 2-D TMA box {32, 128};
-//      spatial mode: NHWC tensor, 4-D TMA box {32 ch, TW, TH, TN} at (c, w0+dw, h0+dh, n0) - the
-//      3x3 / strided taps are just shifted boxes, image borders come from TMA zero fill.
-//   B: weights (N, K_total) K-major, 2-D TMA box {32, BN}.
+//   MODE 0 (K-major)
+//     A: activations. plain: row-major (M, K) matrix, 2-D TMA box {32, 128}; spatial: NHWC tensor, 4-D TMA
+//        box {32 ch, TW, TH, TN} at (c, w0+dw, h0+dh, n0) - 3x3 / strided / transposed taps are shifted boxes,
+//        image borders come from TMA zero fill.
+//     B: weights (N, K_total) K-major, 2-D TMA box {32, BN}.
+//   MODE 1 (MN-major, weight gradients): K runs over blocks of 32 output pixels; A = dY channels, B = the
+//     taps of the (shifted) input stacked along N ("virtual im2col": column group g = (tap, 32-channel group),
+//     one 5-D TMA box per group), so dY is read once per 256 output columns instead of once per tap.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2-5 = fp32->(tf32 hi, tf32 lo) splitters during the main loop, then TMEM->register epilogue.
-// Precision: PASSES=1 is plain TF32; PASSES=3 accumulates hi*hi + lo*hi + hi*lo ("3xTF32"), which
-// carries ~22 mantissa bits and is what the parity tests and the headline benchmark use.
+// warps 2-5 = fp32 -> (tf32 hi, tf32 lo) splitters during the main loop, then TMEM -> register epilogue.
+// Precision: PASSES=1 is plain TF32; PASSES=3 accumulates lo*hi + hi*lo + hi*hi ("3xTF32", ~fp32 accuracy).
+//   TS=1 (MODE 0, PASSES 3, weights pre-split into hi/lo in global memory): the splitters write the A tile's
+//   hi/lo halves straight into TENSOR MEMORY and the MMAs take A from TMEM (tcgen05.mma [d],[a_tmem],b_desc),
+//   which removes the A re-reads and the splitter's shared-memory writes - the kernel was shared-memory
+//   bandwidth bound with all four operand tiles in shared memory (profiles/ncu_full_r1_gemm_summary.txt).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -30,7 +37,8 @@ constexpr int MAX_TAPS = 16;
 
 struct alignas(64) GemmMaps {
   CUtensorMap a[5];   // MODE 0: up to 4 phase views of the activations.  MODE 1: a[0] = dY, a[1..4] = x views
-  CUtensorMap b;      // MODE 0: weights
+  CUtensorMap b;      // MODE 0: weights (hi part when TS)
+  CUtensorMap b_lo;   // MODE 0, TS: weights lo part
 };
 
 struct GemmProgram {
@@ -38,14 +46,15 @@ struct GemmProgram {
   int num_taps;
   int kblocks;          // 32-wide K blocks per tap
   int tap_dh[MAX_TAPS], tap_dw[MAX_TAPS], tap_map[MAX_TAPS], tap_bk[MAX_TAPS];
-  int M, N;             // plain: rows / cols of D.  spatial: N = output channels
+  int M, N;             // rows / cols of D that exist
   // spatial output tiling: tile = TN images x TH rows x TW cols (TN*TH*TW == 128)
   int TN, TH, TW, tiles_h, tiles_w;
   int n_img, h_out, w_out;
-  int a_stride;         // input coordinate = output coordinate * a_stride + tap offset (phase maps: 1)
   // wgrad (MODE 1): K runs over blocks of 32 output pixels (kTN x kTH x kTW), split over gridDim.z
   int kTN, kTH, kTW, kblocks_n, kblocks_h, kblocks_w;
   int n_tiles;          // column tiles (blockIdx.x = m_tile * n_tiles + n_tile)
+  int cg_in;            // 32-channel groups per tap of the input (c_in / 32)
+  int total_groups;     // num_taps * cg_in
   unsigned mn_lbo, mn_sbo, mn_layout;  // MN-major smem descriptor fields (bytes, bytes, layout type)
 };
 
@@ -59,23 +68,29 @@ struct GemmEpilogue {
   int accumulate;         // atomicAdd into out instead of store
   // row -> element offset: plain: row * ld ; spatial: n*sN + h*sH + w*sW  (+ column)
   long long ld, sN, sH, sW;
-  long long col_base;     // added to the column offset (wgrad: tap slot * c_in)
 };
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, int TS>
 struct GemmCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = (A_TILE_BYTES + B_TILE_BYTES) * (PASSES == 3 ? 2 : 1);
+  static constexpr int STAGE_BYTES =
+      TS ? (A_TILE_BYTES + 2 * B_TILE_BYTES) : (A_TILE_BYTES + B_TILE_BYTES) * (PASSES == 3 ? 2 : 1);
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int STAGES_SMEM = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  // TS: every stage also owns 64 TMEM columns (A hi | A lo); 512 columns in total
+  static constexpr int STAGES_TMEM = (512 - BN) / 64;
+  static constexpr int STAGES = TS ? (STAGES_SMEM < STAGES_TMEM ? STAGES_SMEM : STAGES_TMEM) : STAGES_SMEM;
+  static constexpr int TMEM_NEED = TS ? BN + STAGES * 64 : BN;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int PASSES, int MODE>
+template <int BN, int PASSES, int MODE, int TS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, const GemmEpilogue epi) {
-  using Cfg = GemmCfg<BN, PASSES>;
+  using Cfg = GemmCfg<BN, PASSES, TS>;
   constexpr int S = Cfg::STAGES;
+  constexpr int B_TILE_BYTES = Cfg::B_TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
@@ -92,11 +107,10 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   // tile coordinates
   int m0 = 0, n_img0 = 0, h0 = 0, w0 = 0;
   int n0 = blockIdx.y * BN;
-  int pb_begin = 0, wg_tap = 0;
+  int pb_begin = 0;
   if (MODE == 1) {
     m0 = (blockIdx.x / prog.n_tiles) * BM;
     n0 = (blockIdx.x % prog.n_tiles) * BN;
-    wg_tap = blockIdx.y;
     const int total = prog.kblocks_n * prog.kblocks_h * prog.kblocks_w;
     const int per = (total + gridDim.z - 1) / gridDim.z;
     pb_begin = blockIdx.z * per;
@@ -123,7 +137,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -131,10 +145,19 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // stage layout.  SS: A | B | A_lo | B_lo.   TS: A_raw | B_hi | B_lo.
   auto stage_a = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
   auto stage_b = [&](int s) { return smem + s * Cfg::STAGE_BYTES + A_TILE_BYTES; };
-  auto stage_alo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + A_TILE_BYTES + Cfg::B_TILE_BYTES; };
-  auto stage_blo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES; };
+  auto stage_alo = [&](int s) { return smem + s * Cfg::STAGE_BYTES + A_TILE_BYTES + B_TILE_BYTES; };
+  auto stage_blo = [&](int s) {
+    return smem + s * Cfg::STAGE_BYTES + (TS ? A_TILE_BYTES + B_TILE_BYTES : 2 * A_TILE_BYTES + B_TILE_BYTES);
+  };
+  // TS: TMEM columns of stage s: [BN + 64 s, +32) = A hi, next 32 = A lo
+  auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(BN + 64 * s); };
+
+  // MODE 1: number of 32-column groups of this tile that exist
+  int valid_groups = BN / 32;
+  if (MODE == 1) valid_groups = min(BN / 32, prog.total_groups - n0 / 32);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -145,26 +168,32 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full[s], A_TILE_BYTES + Cfg::B_TILE_BYTES);
         if (MODE == 1) {
+          mbar_arrive_expect_tx(&full[s], A_TILE_BYTES + 4096 * valid_groups);
           int pb = pb_begin + it;
           const int bw = pb % prog.kblocks_w; pb /= prog.kblocks_w;
           const int bh = pb % prog.kblocks_h; pb /= prog.kblocks_h;
           const int pw = bw * prog.kTW, ph_ = bh * prog.kTH, pn = pb * prog.kTN;
           tma_load_5d(stage_a(s), &maps.a[0], &full[s], 0, pw, ph_, pn, m0 / 32);
-          tma_load_5d(stage_b(s), &maps.a[1 + prog.tap_map[wg_tap]], &full[s], 0, pw + prog.tap_dw[wg_tap],
-                      ph_ + prog.tap_dh[wg_tap], pn, n0 / 32);
+          for (int j = 0; j < valid_groups; ++j) {
+            const int g = n0 / 32 + j;
+            const int tap = g / prog.cg_in, cg = g - tap * prog.cg_in;
+            tma_load_5d(stage_b(s) + j * 4096, &maps.a[1 + prog.tap_map[tap]], &full[s], 0, pw + prog.tap_dw[tap],
+                        ph_ + prog.tap_dh[tap], pn, cg);
+          }
           continue;
         }
+        mbar_arrive_expect_tx(&full[s], A_TILE_BYTES + B_TILE_BYTES * (TS ? 2 : 1));
         const int tap = it / prog.kblocks;
         const int kb = it - tap * prog.kblocks;
         if (prog.spatial) {
-          tma_load_4d(stage_a(s), &maps.a[prog.tap_map[tap]], &full[s], kb * BK,
-                      w0 * prog.a_stride + prog.tap_dw[tap], h0 * prog.a_stride + prog.tap_dh[tap], n_img0);
+          tma_load_4d(stage_a(s), &maps.a[prog.tap_map[tap]], &full[s], kb * BK, w0 + prog.tap_dw[tap],
+                      h0 + prog.tap_dh[tap], n_img0);
         } else {
           tma_load_2d(stage_a(s), &maps.a[0], &full[s], kb * BK, m0);
         }
         tma_load_2d(stage_b(s), &maps.b, &full[s], prog.tap_bk[tap] + kb * BK, n0);
+        if (TS) tma_load_2d(stage_blo(s), &maps.b_lo, &full[s], prog.tap_bk[tap] + kb * BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -180,23 +209,32 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
     for (int it = 0; it < n_iters; ++it) {
       const int s = it % S;
       const uint32_t ph = (it / S) & 1;
-      mbar_wait(PASSES == 3 ? &conv[s] : &full[s], ph);
+      mbar_wait(&full[s], ph);
+      if (PASSES == 3) mbar_wait(&conv[s], ph);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_b(s));
         const uint32_t a_lo = smem_u32(stage_alo(s)), b_lo = smem_u32(stage_blo(s));
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t da = umma_desc(a_hi + k * KSTEP, LBO, SBO, LT);
           const uint64_t db = umma_desc(b_hi + k * KSTEP, LBO, SBO, LT);
-          if (PASSES == 3) {
+          const uint32_t acc0 = (it > 0 || k > 0) ? 1u : 0u;
+          if (TS) {
+            const uint64_t dbl = umma_desc(b_lo + k * KSTEP, LBO, SBO, LT);
+            const uint32_t ta_hi = tmem_a(s) + k * 8, ta_lo = tmem_a(s) + 32 + k * 8;
+            umma_tf32_ts(tmem_base, ta_lo, db, idesc, acc0);
+            umma_tf32_ts(tmem_base, ta_hi, dbl, idesc, 1u);
+            umma_tf32_ts(tmem_base, ta_hi, db, idesc, 1u);
+          } else if (PASSES == 3) {
+            const uint64_t da = umma_desc(a_hi + k * KSTEP, LBO, SBO, LT);
             const uint64_t dal = umma_desc(a_lo + k * KSTEP, LBO, SBO, LT);
             const uint64_t dbl = umma_desc(b_lo + k * KSTEP, LBO, SBO, LT);
-            umma_tf32(tmem_base, dal, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(tmem_base, dal, db, idesc, acc0);
             umma_tf32(tmem_base, da, dbl, idesc, 1u);
             umma_tf32(tmem_base, da, db, idesc, 1u);
           } else {
-            umma_tf32(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            const uint64_t da = umma_desc(a_hi + k * KSTEP, LBO, SBO, LT);
+            umma_tf32(tmem_base, da, db, idesc, acc0);
           }
         }
         umma_commit(&empty[s]);
@@ -207,8 +245,36 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   } else {
     // ===== splitter (main loop) + epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
     const int tid = threadIdx.x - 64;  // 0..127
-    if (PASSES == 3) {
-      constexpr int A_V4 = A_TILE_BYTES / 16, B_V4 = Cfg::B_TILE_BYTES / 16;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;       // row of the tile == TMEM lane
+    if (TS) {
+      // A row r (32 fp32 along K, 8 swizzled 16-byte chunks) -> hi / lo -> tensor memory
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(&full[s], ph);
+        const uint8_t* row = stage_a(s) + r * 128;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
+          const float h0f = to_tf32_rna(v.x), h1f = to_tf32_rna(v.y), h2f = to_tf32_rna(v.z), h3f = to_tf32_rna(v.w);
+          hi[4 * j + 0] = __float_as_uint(h0f); lo[4 * j + 0] = __float_as_uint(v.x - h0f);
+          hi[4 * j + 1] = __float_as_uint(h1f); lo[4 * j + 1] = __float_as_uint(v.y - h1f);
+          hi[4 * j + 2] = __float_as_uint(h2f); lo[4 * j + 2] = __float_as_uint(v.z - h2f);
+          hi[4 * j + 3] = __float_as_uint(h3f); lo[4 * j + 3] = __float_as_uint(v.w - h3f);
+        }
+        const uint32_t dst = lane_base + (uint32_t)(BN + 64 * s);
+        tmem_st_32x32(dst, hi);
+        tmem_st_32x32(dst + 32, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&conv[s]);
+      }
+    } else if (PASSES == 3) {
+      constexpr int A_V4 = A_TILE_BYTES / 16;
+      const int b_v4 = (MODE == 1 ? valid_groups * 4096 : B_TILE_BYTES) / 16;
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
@@ -218,7 +284,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         float4* b = reinterpret_cast<float4*>(stage_b(s));
         float4* blo = reinterpret_cast<float4*>(stage_blo(s));
 #pragma unroll 4
-        for (int i = tid; i < A_V4 + B_V4; i += 128) {
+        for (int i = tid; i < A_V4 + b_v4; i += 128) {
           float4* src = i < A_V4 ? a + i : b + (i - A_V4);
           float4* dst = i < A_V4 ? alo + i : blo + (i - A_V4);
           float4 v = *src, h, l;
@@ -234,8 +300,6 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
     // ---- epilogue ----
     mbar_wait(accum, 0);
     tc_fence_after();
-    const int q = warp & 3;
-    const int r = q * 32 + lane;  // row of the tile == TMEM lane
     bool row_ok;
     long long row_off;
     if (MODE == 0 && prog.spatial) {
@@ -247,8 +311,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
       row_off = n * epi.sN + h * epi.sH + w * epi.sW;
     } else {
       row_ok = (m0 + r) < prog.M;
-      row_off = (long long)(m0 + r) * epi.ld +
-                (MODE == 1 ? (long long)prog.tap_bk[wg_tap] * prog.N : epi.col_base);
+      row_off = (long long)(m0 + r) * epi.ld;
     }
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
                           reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0 &&
@@ -305,16 +368,16 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, int PASSES, int MODE>
+template <int BN, int PASSES, int MODE, int TS>
 static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const GemmEpilogue& epi, dim3 grid,
                        cudaStream_t st) {
-  using Cfg = GemmCfg<BN, PASSES>;
+  using Cfg = GemmCfg<BN, PASSES, TS>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, MODE>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, MODE, TS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute(%d bytes) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -322,17 +385,19 @@ static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const Gemm
     }
     attr = true;
   }
-  gemm_tc_kernel<BN, PASSES, MODE><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
+  gemm_tc_kernel<BN, PASSES, MODE, TS><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
   return check_launch("gemm_tc_kernel");
 }
 
+// ts: use the A-in-TMEM path (MODE 0, passes 3, pre-split weights)
 template <int MODE>
-static int dispatch_gemm(int BN, int passes, const GemmMaps& maps, const GemmProgram& prog,
+static int dispatch_gemm(int BN, int passes, int ts, const GemmMaps& maps, const GemmProgram& prog,
                          const GemmEpilogue& epi, dim3 grid, cudaStream_t st) {
-#define OBMAN_GEMM_CASE(bn)                                                   \
-  if (BN == bn) {                                                             \
-    return passes == 3 ? launch_gemm<bn, 3, MODE>(maps, prog, epi, grid, st)  \
-                       : launch_gemm<bn, 1, MODE>(maps, prog, epi, grid, st); \
+#define OBMAN_GEMM_CASE(bn)                                                                     \
+  if (BN == bn) {                                                                               \
+    if (MODE == 0 && ts && passes == 3) return launch_gemm<bn, 3, 0, 1>(maps, prog, epi, grid, st); \
+    return passes == 3 ? launch_gemm<bn, 3, MODE, 0>(maps, prog, epi, grid, st)                 \
+                       : launch_gemm<bn, 1, MODE, 0>(maps, prog, epi, grid, st);                \
   }
   OBMAN_GEMM_CASE(64)
   OBMAN_GEMM_CASE(128)
@@ -343,10 +408,19 @@ static int dispatch_gemm(int BN, int passes, const GemmMaps& maps, const GemmPro
 }
 
 static int pick_bn(int N, long long m_tiles) {
-  // widest tile that does not waste more than half of its columns; prefer filling the SMs
-  if (N > 128 && m_tiles * ((N + 255) / 256) >= num_sms()) return 256;
+  // 256-wide tiles halve the A re-reads; take them whenever the grid still covers most of the SMs
+  if (N > 128 && m_tiles * ((N + 255) / 256) >= (num_sms() * 3) / 4) return 256;
   if (N > 64) return 128;
   return 64;
+}
+
+static bool ts_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OBMAN_GEMM_TS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 }  // namespace obman
@@ -355,19 +429,24 @@ using namespace obman;
 
 // out[M,N] = epilogue(alpha * A[M,K] * W[N,K]^T)   (row-major, leading dimensions in elements)
 // epilogue: + bias[N] + addend[M,N] ; relu ; mask by (mask_src > 0) ; store or atomicAdd.
-extern "C" int obman_gemm(const float* A, long long lda, const float* W, long long ldw, int M, int N,
-                          int K, float* out, long long ldo, const float* bias, const float* addend,
+// W_lo (nullable): with passes == 3, W must then hold tf32-rounded values and W_lo the residual (W_true =
+// W + W_lo, see obman_split_tf32 / obman_fold_conv); enables the A-in-TMEM path.
+extern "C" int obman_gemm(const float* A, long long lda, const float* W, const float* W_lo, long long ldw, int M,
+                          int N, int K, float* out, long long ldo, const float* bias, const float* addend,
                           const float* mask_src, float alpha, int relu, int accumulate, int passes,
                           void* stream) {
   OBMAN_REQUIRE(A && W && out, "obman_gemm: null argument");
   OBMAN_REQUIRE(M > 0 && N > 0 && K > 0, "obman_gemm: bad sizes M=%d N=%d K=%d", M, N, K);
   OBMAN_REQUIRE(passes == 1 || passes == 3, "obman_gemm: passes must be 1 (tf32) or 3 (3xtf32)");
   OBMAN_REQUIRE(lda % 4 == 0 && ldw % 4 == 0, "obman_gemm: lda/ldw must be multiples of 4 floats (TMA 16-byte stride)");
-  OBMAN_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0, "obman_gemm: A/W must be 16-byte aligned");
+  OBMAN_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)W_lo & 15) == 0,
+                "obman_gemm: A/W must be 16-byte aligned");
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
   const long long m_tiles = (M + BM - 1) / BM;
   const int BN = pick_bn(N, m_tiles);
+  const int ts = (W_lo != nullptr) && passes == 3 && ts_enabled();
+  OBMAN_REQUIRE(W_lo == nullptr || passes == 1 || ts, "obman_gemm: pre-split weights need the TS path (OBMAN_GEMM_TS=0 set?)");
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     uint64_t strides[1] = {(uint64_t)lda * 4};
@@ -379,6 +458,10 @@ extern "C" int obman_gemm(const float* A, long long lda, const float* W, long lo
     uint32_t boxb[2] = {BK, (uint32_t)BN};
     rc = make_tensor_map(&maps.b, W, 2, dimsb, stridesb, boxb);
     if (rc) return rc;
+    if (ts) {
+      rc = make_tensor_map(&maps.b_lo, W_lo, 2, dimsb, stridesb, boxb);
+      if (rc) return rc;
+    }
   }
   GemmProgram prog;
   memset(&prog, 0, sizeof(prog));
@@ -392,21 +475,20 @@ extern "C" int obman_gemm(const float* A, long long lda, const float* W, long lo
   epi.out = out; epi.bias = bias; epi.addend = addend; epi.mask_src = mask_src;
   epi.alpha = alpha; epi.relu = relu; epi.accumulate = accumulate; epi.ld = ldo;
   dim3 grid((unsigned)m_tiles, (unsigned)((N + BN - 1) / BN), 1);
-  return dispatch_gemm<0>(BN, passes, maps, prog, epi, grid, (cudaStream_t)stream);
+  return dispatch_gemm<0>(BN, passes, ts, maps, prog, epi, grid, (cudaStream_t)stream);
 }
 
 // NHWC convolution as implicit GEMM (forward and data-gradient share this entry point).
 //   x    : (n_img, h_in, w_in, c_in) NHWC, c_in % 4 == 0
 //   w    : (c_out, w_slots * c_in) K-major; tap t reads weight slot tap_wslot[t] (default t), i.e.
-//          columns [slot*c_in, (slot+1)*c_in)
-//   taps : for tap t the input pixel of output (h, w) is (h*stride_eff + dh[t], w*stride_eff + dw[t])
-//          read through phase view `tap_phase[t]` (ph*2+pw) when in_step == 2, i.e. the input is viewed
-//          as x[:, ph::2, pw::2, :] and stride_eff == 1; with in_step == 1 there is a single view.
+//          columns [slot*c_in, (slot+1)*c_in).  w_lo (nullable): residual of pre-split weights (see obman_gemm).
+//   taps : for tap t the input pixel of output (h, w) is (h + dh[t], w + dw[t]) of phase view `tap_phase[t]`
+//          (ph*2+pw) when in_step == 2, i.e. of x[:, ph::2, pw::2, :]; with in_step == 1 there is a single view.
 //   out  : written at element offset n*o_sN + h*o_sH + w*o_sW + c   (lets dgrad write strided phases)
 extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, int c_in, int in_step,
-                               const float* w, int c_out, int w_slots, int num_taps, const int* tap_dh,
-                               const int* tap_dw, const int* tap_phase, const int* tap_wslot, float* out,
-                               int h_out, int w_out, long long o_sN, long long o_sH, long long o_sW,
+                               const float* w, const float* w_lo, int c_out, int w_slots, int num_taps,
+                               const int* tap_dh, const int* tap_dw, const int* tap_phase, const int* tap_wslot,
+                               float* out, int h_out, int w_out, long long o_sN, long long o_sH, long long o_sW,
                                const float* bias, const float* addend, const float* mask_src, int relu,
                                int passes, void* stream) {
   OBMAN_REQUIRE(x && w && out && tap_dh && tap_dw, "obman_conv_nhwc: null argument");
@@ -418,7 +500,8 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
   OBMAN_REQUIRE(w_slots >= 1, "obman_conv_nhwc: w_slots must be >= 1");
   OBMAN_REQUIRE(in_step == 1 || (h_in % 2 == 0 && w_in % 2 == 0), "obman_conv_nhwc: phase views need even h_in/w_in");
   OBMAN_REQUIRE(passes == 1 || passes == 3, "obman_conv_nhwc: passes must be 1 or 3");
-  OBMAN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0, "obman_conv_nhwc: x/w must be 16-byte aligned");
+  OBMAN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)w_lo & 15) == 0,
+                "obman_conv_nhwc: x/w must be 16-byte aligned");
   // output tile shape: TW = largest power of two <= min(w_out, 128) ... keep TN*TH*TW == 128
   int TW = 1;
   while (TW * 2 <= w_out && TW * 2 <= 128) TW *= 2;
@@ -435,9 +518,10 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
   prog.tiles_h = (h_out + TH - 1) / TH;
   prog.tiles_w = (w_out + TW - 1) / TW;
   prog.n_img = n_img; prog.h_out = h_out; prog.w_out = w_out;
-  prog.a_stride = 1;
   const long long m_tiles = (long long)((n_img + TN - 1) / TN) * prog.tiles_h * prog.tiles_w;
   const int BN = pick_bn(c_out, m_tiles);
+  const int ts = (w_lo != nullptr) && passes == 3 && ts_enabled();
+  OBMAN_REQUIRE(w_lo == nullptr || passes == 1 || ts, "obman_conv_nhwc: pre-split weights need the TS path");
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
   bool used[4] = {false, false, false, false};
@@ -467,6 +551,10 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
     uint32_t boxb[2] = {BK, (uint32_t)BN};
     int rc = make_tensor_map(&maps.b, w, 2, dimsb, stridesb, boxb);
     if (rc) return rc;
+    if (ts) {
+      rc = make_tensor_map(&maps.b_lo, w_lo, 2, dimsb, stridesb, boxb);
+      if (rc) return rc;
+    }
   }
   GemmEpilogue epi;
   memset(&epi, 0, sizeof(epi));
@@ -474,23 +562,23 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
   epi.alpha = 1.f; epi.relu = relu; epi.accumulate = 0;
   epi.sN = o_sN; epi.sH = o_sH; epi.sW = o_sW;
   dim3 grid((unsigned)m_tiles, (unsigned)((c_out + BN - 1) / BN), 1);
-  return dispatch_gemm<0>(BN, passes, maps, prog, epi, grid, (cudaStream_t)stream);
+  return dispatch_gemm<0>(BN, passes, ts, maps, prog, epi, grid, (cudaStream_t)stream);
 }
 
 // Weight gradient of the NHWC convolution above (and, with h = 1, of any row-major matrix product):
-//   dw[co, slot(t)*c_in + ci] = sum_{n,h,w} dy[n,h,w,co] * xview_t[n, h + dh[t], w + dw[t], ci]
-// Both operands are read MN-major (channels contiguous, pixels along K) straight from their NHWC
-// layout; the pixel reduction is split over gridDim.z and combined with fp32 atomics.
-// c_out and c_in must be multiples of 32 (pad the channel dimension of the tensors otherwise).
+//   dw[co, t*c_in + ci] = sum_{n,h,w} dy[n,h,w,co] * xview_t[n, h + dh[t], w + dw[t], ci]     t = 0..num_taps-1
+// One GEMM with N = num_taps * c_in: the taps are stacked along N and fetched as shifted boxes, both operands are
+// read MN-major (channels contiguous, pixels along K) straight from NHWC; the pixel reduction is split over
+// gridDim.z (a whole number of waves) and combined with fp32 atomics.  c_out, c_in multiples of 32.
 extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out, int c_out,
                                 const float* x, int h_in, int w_in, int c_in, int in_step, int num_taps,
-                                const int* tap_dh, const int* tap_dw, const int* tap_phase,
-                                const int* tap_wslot, float* dw, int w_slots, int passes, void* stream) {
+                                const int* tap_dh, const int* tap_dw, const int* tap_phase, float* dw,
+                                int passes, void* stream) {
   OBMAN_REQUIRE(dy && x && dw && tap_dh && tap_dw, "obman_wgrad_nhwc: null argument");
   OBMAN_REQUIRE(n_img > 0 && h_out > 0 && w_out > 0 && h_in > 0 && w_in > 0, "obman_wgrad_nhwc: bad sizes");
   OBMAN_REQUIRE(c_out > 0 && c_in > 0 && c_out % 32 == 0 && c_in % 32 == 0,
                 "obman_wgrad_nhwc: c_out=%d and c_in=%d must be multiples of 32", c_out, c_in);
-  OBMAN_REQUIRE(num_taps >= 1 && num_taps <= MAX_TAPS && w_slots >= 1, "obman_wgrad_nhwc: bad tap count");
+  OBMAN_REQUIRE(num_taps >= 1 && num_taps <= MAX_TAPS, "obman_wgrad_nhwc: bad tap count");
   OBMAN_REQUIRE(in_step == 1 || in_step == 2, "obman_wgrad_nhwc: in_step must be 1 or 2");
   OBMAN_REQUIRE(in_step == 1 || (h_in % 2 == 0 && w_in % 2 == 0), "obman_wgrad_nhwc: phase views need even h_in/w_in");
   OBMAN_REQUIRE(passes == 1 || passes == 3, "obman_wgrad_nhwc: passes must be 1 or 3");
@@ -506,22 +594,18 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
   prog.num_taps = num_taps;
   prog.kblocks = 1;
   prog.M = c_out;
-  prog.N = c_in;
+  prog.cg_in = c_in / 32;
+  prog.total_groups = num_taps * prog.cg_in;
+  prog.N = prog.total_groups * 32;
   prog.kTN = kTN; prog.kTH = kTH; prog.kTW = kTW;
   prog.mn_lbo = 4096; prog.mn_sbo = 512; prog.mn_layout = 1;
-  CUtensorMapSwizzle mn_swizzle = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-  if (const char* dbg = getenv("OBMAN_WGRAD_DESC")) {  // bring-up override: "lbo,sbo,layout,tma_swizzle"
-    unsigned a = 0, b = 0, c = 0, d = 0;
-    if (sscanf(dbg, "%u,%u,%u,%u", &a, &b, &c, &d) == 4) {
-      prog.mn_lbo = a; prog.mn_sbo = b; prog.mn_layout = c; mn_swizzle = (CUtensorMapSwizzle)d;
-    }
-  }
+  const CUtensorMapSwizzle mn_swizzle = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   prog.kblocks_n = (n_img + kTN - 1) / kTN;
   prog.kblocks_h = (h_out + kTH - 1) / kTH;
   prog.kblocks_w = (w_out + kTW - 1) / kTW;
   const int m_tiles = (c_out + BM - 1) / BM;
-  const int BN = c_in > 128 ? 256 : (c_in > 64 ? 128 : 64);
-  prog.n_tiles = (c_in + BN - 1) / BN;
+  const int BN = prog.N > 128 ? 256 : (prog.N > 64 ? 128 : 64);
+  prog.n_tiles = (prog.N + BN - 1) / BN;
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
   {
@@ -538,7 +622,6 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
     prog.tap_dh[t] = tap_dh[t];
     prog.tap_dw[t] = tap_dw[t];
     prog.tap_map[t] = ph;
-    prog.tap_bk[t] = (tap_wslot ? tap_wslot[t] : t);
     used[ph] = true;
   }
   for (int ph = 0; ph < 4; ++ph) {
@@ -547,30 +630,44 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
     uint64_t dims[5] = {32, (uint64_t)(w_in / in_step), (uint64_t)(h_in / in_step), (uint64_t)n_img, (uint64_t)(c_in / 32)};
     uint64_t strides[4] = {(uint64_t)c_in * 4 * in_step, (uint64_t)w_in * c_in * 4 * in_step,
                            (uint64_t)h_in * w_in * c_in * 4, 128};
-    uint32_t box[5] = {32, (uint32_t)kTW, (uint32_t)kTH, (uint32_t)kTN, (uint32_t)(BN / 32)};
+    uint32_t box[5] = {32, (uint32_t)kTW, (uint32_t)kTH, (uint32_t)kTN, 1};
     const float* base = x + ((long long)py * w_in + px) * c_in;
     int rc = make_tensor_map(&maps.a[1 + ph], base, 5, dims, strides, box, mn_swizzle);
     if (rc) return rc;
   }
   const long long total_blocks = (long long)prog.kblocks_n * prog.kblocks_h * prog.kblocks_w;
-  const long long tiles = (long long)m_tiles * prog.n_tiles * num_taps;
-  long long splits = (2LL * num_sms() + tiles - 1) / tiles;
-  if (splits > total_blocks / 8) splits = total_blocks / 8;
+  const long long tiles = (long long)m_tiles * prog.n_tiles;
+  // split the pixel reduction so that tiles * splits is a whole number of waves (one CTA per SM)
+  const long long waves = (tiles + num_sms() - 1) / num_sms();
+  long long splits = (waves * num_sms()) / tiles;
+  if (splits > total_blocks / 4) splits = total_blocks / 4;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
-  const long long ld = (long long)w_slots * c_in;
+  const long long ld = (long long)prog.N;
   if (splits > 1) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)c_out * ld, st);
-  // one launch per tap would need a per-launch col_base; instead gridDim.y = taps and the kernel derives the
-  // slot from tap_bk, so encode col_base = slot * c_in through a per-tap table
-  int rc = OBMAN_OK;
   GemmEpilogue epi;
   memset(&epi, 0, sizeof(epi));
   epi.out = dw;
   epi.alpha = 1.f;
   epi.accumulate = splits > 1;
   epi.ld = ld;
-  epi.col_base = -1;  // marker: column base comes from prog.tap_bk[tap] * N
-  dim3 grid((unsigned)(m_tiles * prog.n_tiles), (unsigned)num_taps, (unsigned)splits);
-  rc = dispatch_gemm<1>(BN, passes, maps, prog, epi, grid, st);
-  return rc;
+  dim3 grid((unsigned)(m_tiles * prog.n_tiles), 1, (unsigned)splits);
+  return dispatch_gemm<1>(BN, passes, 0, maps, prog, epi, grid, st);
+}
+
+// hi = tf32-rounded copy of w, lo = w - hi (elementwise, n floats): weights pre-split for the TS path.
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, long long n,
+                                                         float* __restrict__ hi, float* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = w[i];
+  const float h = obman::sm100::to_tf32_rna(v);
+  hi[i] = h;
+  lo[i] = v - h;
+}
+
+extern "C" int obman_split_tf32(const float* w, long long n, float* hi, float* lo, void* stream) {
+  OBMAN_REQUIRE(w && hi && lo && n > 0, "obman_split_tf32: bad arguments");
+  split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, n, hi, lo);
+  return check_launch("split_tf32_kernel");
 }

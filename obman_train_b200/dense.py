@@ -64,17 +64,27 @@ def _chk(t, name):
     return t
 
 
+def split_tf32(w):
+    """(hi, lo) with hi = tf32-rounded w and lo = w - hi: pre-split weights for the A-in-TMEM 3xTF32 path."""
+    _chk(w, "w")
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    call("obman_split_tf32", ptr(w), w.numel(), ptr(hi), ptr(lo), stream_ptr())
+    return hi, lo
+
+
 def gemm(a, w, out=None, bias=None, addend=None, mask_src=None, alpha=1.0, relu=False,
-         accumulate=False, passes=3, n=None, k=None):
+         accumulate=False, passes=3, n=None, k=None, w_lo=None):
     """out[M,N] = epilogue(alpha * a[M,:K] @ w[:N,:K]^T).  ``a`` / ``w`` may have padded leading
-    dimensions (row stride multiple of 4 floats); ``n`` / ``k`` give the logical sizes."""
+    dimensions (row stride multiple of 4 floats); ``n`` / ``k`` give the logical sizes.  ``w_lo``: residual
+    of pre-split weights (``w`` is then the tf32-rounded part), selects the A-in-TMEM kernel."""
     _chk(a, "a"); _chk(w, "w")
     M = a.shape[0]
     K = k if k is not None else a.shape[1]
     N = n if n is not None else w.shape[0]
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32)
-    _tc_call(2.0 * M * N * K, "obman_gemm", ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, ptr(out), out.stride(0),
+    _tc_call(2.0 * M * N * K, "obman_gemm", ptr(a), a.stride(0), ptr(w), ptr(w_lo) if passes == 3 else None,
+             w.stride(0), M, N, K, ptr(out), out.stride(0),
          ptr(bias), ptr(addend), ptr(mask_src), float(alpha), int(relu), int(accumulate), int(passes),
          stream_ptr())
     return out
@@ -111,7 +121,8 @@ def dgrad_taps(ksize, stride, pad, out_phase=(0, 0)):
 
 
 def conv_nhwc(x, w, c_out, taps, in_step, out, h_out, w_out, out_strides=None, out_offset=0,
-              bias=None, addend=None, mask_src=None, relu=False, passes=3, w_slots=None, algo_k=None):
+              bias=None, addend=None, mask_src=None, relu=False, passes=3, w_slots=None, algo_k=None,
+              w_lo=None):
     """Raw obman_conv_nhwc call.  x (N,H,W,C) contiguous; w (c_out, slots*C); taps = (dh, dw, phase, slot).
     ``out`` is any tensor whose storage receives element (n,h,w,c) at out_offset + n*sN + h*sH + w*sW + c."""
     _chk(x, "x"); _chk(w, "w")
@@ -128,7 +139,8 @@ def conv_nhwc(x, w, c_out, taps, in_step, out, h_out, w_out, out_strides=None, o
 
     k_eff = algo_k if algo_k is not None else len(dh) * c_in
     _tc_call(2.0 * n_img * h_out * w_out * c_out * k_eff,
-             "obman_conv_nhwc", ptr(x), n_img, h_in, w_in, c_in, int(in_step), ptr(w), int(c_out),
+             "obman_conv_nhwc", ptr(x), n_img, h_in, w_in, c_in, int(in_step), ptr(w),
+             ptr(w_lo) if passes == 3 else None, int(c_out),
          int(w_slots), len(dh), _ints(dh), _ints(dw), _ints(phase) if phase is not None else None,
          _ints(slot), off(out), int(h_out), int(w_out), int(out_strides[0]), int(out_strides[1]),
          int(out_strides[2]), ptr(bias), off(addend), off(mask_src), int(relu), int(passes),
@@ -136,17 +148,20 @@ def conv_nhwc(x, w, c_out, taps, in_step, out, h_out, w_out, out_strides=None, o
     return out
 
 
-def wgrad_nhwc(dy, x, taps, in_step, dw_out, w_slots, passes=3, algo_k=None):
-    """dw_out (c_out, w_slots*c_in) = sum over pixels dy (N,Ho,Wo,c_out) x shifted x (N,H,W,c_in)."""
+def wgrad_nhwc(dy, x, taps, in_step, dw_out, passes=3, algo_k=None):
+    """dw_out (c_out, num_taps*c_in) = sum over pixels dy (N,Ho,Wo,c_out) x shifted x (N,H,W,c_in); the tap
+    order is the weight-slot order (taps = (dh, dw, phase, slot) with slot == position)."""
     _chk(dy, "dy"); _chk(x, "x"); _chk(dw_out, "dw")
     n_img, h_out, w_out, c_out = dy.shape
     _, h_in, w_in, c_in = x.shape
     dh, dw, phase, slot = taps
+    if list(slot) != list(range(len(dh))):
+        raise RuntimeError("wgrad_nhwc: taps must be listed in weight-slot order")
     k_eff = algo_k if algo_k is not None else len(dh) * c_in
     _tc_call(2.0 * n_img * h_out * w_out * c_out * k_eff,
              "obman_wgrad_nhwc", ptr(dy), n_img, h_out, w_out, c_out, ptr(x), h_in, w_in, c_in,
-         int(in_step), len(dh), _ints(dh), _ints(dw), _ints(phase) if phase is not None else None,
-         _ints(slot), ptr(dw_out), int(w_slots), int(passes), stream_ptr())
+             int(in_step), len(dh), _ints(dh), _ints(dw), _ints(phase) if phase is not None else None,
+             ptr(dw_out), int(passes), stream_ptr())
     return dw_out
 
 
@@ -156,4 +171,4 @@ def wgrad_matrix(dy, x, dw_out=None, passes=3):
     K = x.shape[1]
     if dw_out is None:
         dw_out = torch.empty((N, K), device=dy.device, dtype=torch.float32)
-    return wgrad_nhwc(dy.view(1, 1, M, N), x.view(1, 1, M, K), ([0], [0], None, [0]), 1, dw_out, 1, passes)
+    return wgrad_nhwc(dy.view(1, 1, M, N), x.view(1, 1, M, K), ([0], [0], None, [0]), 1, dw_out, passes)

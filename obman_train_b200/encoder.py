@@ -46,12 +46,15 @@ class _Unit(object):
         self.k, self.stride, self.stem = ksize, stride, stem
         self.Ip = 32 if stem else self.I
         self.slots = 16 if stem else ksize * ksize
-        self.wf = _empty(self.O, self.slots * self.Ip)
-        self.wft = _empty(self.I, self.slots * self.O) if (need_dgrad and not stem) else None
+        # weights are folded AND pre-split into tf32 hi / lo parts (3xTF32 with the A operand in tensor memory)
+        self.wf, self.wf_lo = _empty(self.O, self.slots * self.Ip), _empty(self.O, self.slots * self.Ip)
+        self.wft = self.wft_lo = None
+        if need_dgrad and not stem:
+            self.wft, self.wft_lo = _empty(self.I, self.slots * self.O), _empty(self.I, self.slots * self.O)
         self.shift, self.scale, self.rstd = _empty(self.O), _empty(self.O), _empty(self.O)
         call("obman_fold_conv", ptr(w), None, ptr(gamma), ptr(beta), ptr(mean), ptr(var), BN_EPS, self.O, self.I,
-             ksize, ksize, self.Ip, int(stem), ptr(self.wf), ptr(self.wft), ptr(self.shift),
-             ptr(self.scale), ptr(self.rstd), stream_ptr())
+             ksize, ksize, self.Ip, int(stem), ptr(self.wf), ptr(self.wf_lo), ptr(self.wft), ptr(self.wft_lo),
+             ptr(self.shift), ptr(self.scale), ptr(self.rstd), stream_ptr())
         if stem:
             dh = [a for a in range(-2, 2) for _ in range(4)]
             dw = [b for _ in range(4) for b in range(-2, 2)]
@@ -66,7 +69,7 @@ class _Unit(object):
         out = _empty(x.shape[0], h_out, w_out, self.O)
         dense.conv_nhwc(x, self.wf, self.O, self.taps, self.in_step, out, h_out, w_out, bias=self.shift,
                         addend=addend, relu=relu, passes=passes, w_slots=self.slots,
-                        algo_k=147 if self.stem else None)
+                        algo_k=147 if self.stem else None, w_lo=self.wf_lo)
         return out
 
     def dgrad(self, g, h_in, w_in, addend=None, mask_src=None, passes=3):
@@ -89,12 +92,12 @@ class _Unit(object):
                     continue
                 dense.conv_nhwc(g, self.wft, self.I, (dh, dw, None, slot), 1, gx, h_in // s, w_in // s,
                                 out_strides=strides, out_offset=off, addend=addend, mask_src=mask_src,
-                                passes=passes, w_slots=k * k)
+                                passes=passes, w_slots=k * k, w_lo=self.wft_lo)
         return gx
 
     def wgrad(self, g, x, passes=3):
         dwraw = _empty(self.O, self.slots * self.Ip)
-        dense.wgrad_nhwc(g, x, self.taps, self.in_step, dwraw, self.slots, passes=passes,
+        dense.wgrad_nhwc(g, x, self.taps, self.in_step, dwraw, passes=passes,
                          algo_k=147 if self.stem else None)
         return dwraw
 

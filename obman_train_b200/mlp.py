@@ -92,14 +92,16 @@ class _Layer(object):
         self.bn = None if bn is None else [t.detach().contiguous() for t in bn]
         gamma, beta, mean, var = self.bn if self.bn is not None else (None, None, None, None)
         self.ld = (self.I + 3) // 4 * 4
-        self.wf = _empty(self.O, self.ld)
-        self.wft = _zeros(self.I, _r32(self.O))   # (I, O padded): dgrad operand
-        wft_tmp = _empty(self.I, self.O)
+        # folded weights, pre-split into tf32 hi / lo parts: wf + wf_lo = scale * w (fprop), wft + wft_lo (dgrad)
+        self.wf, self.wf_lo = _empty(self.O, self.ld), _empty(self.O, self.ld)
+        self.wft, self.wft_lo = _zeros(self.I, _r32(self.O)), _zeros(self.I, _r32(self.O))   # (I, O padded)
+        wft_tmp, wft_tmp_lo = _empty(self.I, self.O), _empty(self.I, self.O)
         self.shift, self.scale, self.rstd = _empty(self.O), _empty(self.O), _empty(self.O)
         call("obman_fold_conv", ptr(self.w), ptr(self.cbias), ptr(gamma), ptr(beta), ptr(mean), ptr(var),
-             BN_EPS, self.O, self.I, 1, 1, self.ld, 0, ptr(self.wf), ptr(wft_tmp), ptr(self.shift),
-             ptr(self.scale), ptr(self.rstd), stream_ptr())
+             BN_EPS, self.O, self.I, 1, 1, self.ld, 0, ptr(self.wf), ptr(self.wf_lo), ptr(wft_tmp),
+             ptr(wft_tmp_lo), ptr(self.shift), ptr(self.scale), ptr(self.rstd), stream_ptr())
         self.wft[:, :self.O] = wft_tmp
+        self.wft_lo[:, :self.O] = wft_tmp_lo
 
     def finish(self, dwraw, gsum):
         """dwraw (>=O rows, row stride ld_raw, first I columns valid) -> (gw, gcbias, ggamma, gbeta)."""
@@ -138,17 +140,19 @@ class _PointDecoderFn(torch.autograd.Function):
         l4 = _Layer(p[6], p[7], None)
         C1, C2, C3 = l1.O, l2.O, l3.O
         # layer 1: grid part (K = 3, batch independent) + feature part (B x F GEMM) -> relu(G + F)
-        wg = l1.wf[:, :3]                                    # (C1,3) folded
-        wfeat = l1.wf[:, 3:3 + Fdim].contiguous()            # (C1,F) folded
+        w1 = l1.wf + l1.wf_lo                                # full-precision folded conv1 weights
+        wg = w1[:, :3]                                       # (C1,3)
+        wfeat = w1[:, 3:3 + Fdim].contiguous()               # (C1,F)
         G = (grid.unsqueeze(-2) * wg).sum(-1).contiguous()   # (N,C1) or (B,N,C1)
         Fb = dense.gemm(feat, wfeat, bias=l1.shift, passes=pf)        # (B,C1)
         ld1, ld2 = _r32(C1), _r32(C2)
         h1 = _empty(B * N, ld1)
         call("obman_pointmlp_l1_fwd", ptr(G), N * C1 if per_sample else 0, ptr(Fb), B, N, C1, ld1, ptr(h1), st)
         h2 = _zeros(B * N, ld2)
-        dense.gemm(h1, l2.wf, out=h2, bias=l2.shift, relu=True, passes=pf, n=C2, k=C1)
-        h3 = dense.gemm(h2, l3.wf, bias=l3.shift, relu=True, passes=pf, n=C3, k=C2)
-        y = dense.gemm(h3, l4.wf, bias=l4.shift * out_factor, alpha=out_factor, passes=pf, n=3, k=C3)
+        dense.gemm(h1, l2.wf, out=h2, bias=l2.shift, relu=True, passes=pf, n=C2, k=C1, w_lo=l2.wf_lo)
+        h3 = dense.gemm(h2, l3.wf, bias=l3.shift, relu=True, passes=pf, n=C3, k=C2, w_lo=l3.wf_lo)
+        y = dense.gemm(h3, l4.wf, bias=l4.shift * out_factor, alpha=out_factor, passes=pf, n=3, k=C3,
+                       w_lo=l4.wf_lo)
         ctx.layers = (l1, l2, l3, l4)
         ctx.param_shapes = [tuple(t.shape) for t in p]
         ctx.saved = (feat, grid, wfeat, h1, h2, h3, B, N, per_sample, out_factor)
@@ -165,13 +169,13 @@ class _PointDecoderFn(torch.autograd.Function):
         g4 = _zeros(M, 32)
         g4[:, :3] = gy.reshape(M, 3) * out_factor
         gw4, gb4, _, _ = l4.finish(dense.wgrad_matrix(g4, h3, passes=pb), colsum(g4, 3))
-        g3 = dense.gemm(g4, l4.wft, mask_src=h3, passes=pb, n=C3, k=3)                       # (M,C3)
+        g3 = dense.gemm(g4, l4.wft, mask_src=h3, passes=pb, n=C3, k=3, w_lo=l4.wft_lo)       # (M,C3)
         gw3, gb3, gg3, gbt3 = l3.finish(dense.wgrad_matrix(g3, h2, passes=pb), colsum(g3, C3))
         g2 = _zeros(M, h2.shape[1])
-        dense.gemm(g3, l3.wft, out=g2, mask_src=h2, passes=pb, n=C2, k=C3)
+        dense.gemm(g3, l3.wft, out=g2, mask_src=h2, passes=pb, n=C2, k=C3, w_lo=l3.wft_lo)
         gw2, gb2, gg2, gbt2 = l2.finish(dense.wgrad_matrix(g2, h1, passes=pb), colsum(g2, C2))
         g1 = _zeros(M, h1.shape[1])
-        dense.gemm(g2, l2.wft, out=g1, mask_src=h1, passes=pb, n=C1, k=C2)
+        dense.gemm(g2, l2.wft, out=g1, mask_src=h1, passes=pb, n=C1, k=C2, w_lo=l2.wft_lo)
         gF = _zeros(B, _r32(C1))
         gFc = _empty(B, C1)
         gG = None if per_sample else _empty(N, C1)

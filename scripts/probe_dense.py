@@ -38,6 +38,8 @@ def case_gemm(M, N, K, passes, epilogue=False):
         mask = torch.randn(M, N, device="cuda", generator=g)
         ref = torch.relu(0.5 * ref + bias.double() + addend.double()) * (mask > 0).double()
         kw = dict(bias=bias, addend=addend, mask_src=mask, alpha=0.5, relu=True)
+    if os.environ.get("PROBE_PRESPLIT", "1") == "1" and passes == 3:
+        w, kw["w_lo"] = dense.split_tf32(w)
     out = dense.gemm(a, w, passes=passes, n=N, k=K, **kw)
     torch.cuda.synchronize()
     return _stats(out, ref)
@@ -66,6 +68,8 @@ def case_conv(n, h, cin, cout, k, stride, passes, epilogue=False):
         res = torch.randn(n, ho, ho, cout, device="cuda", generator=g)
         ref = torch.relu(ref + bias.double().view(1, -1, 1, 1) + res.double().permute(0, 3, 1, 2))
         kw = dict(bias=bias, addend=res, relu=True)
+    if os.environ.get("PROBE_PRESPLIT", "1") == "1" and passes == 3:
+        wk, kw["w_lo"] = dense.split_tf32(wk)
     dense.conv_nhwc(_nhwc(x), wk, cout, (dh, dw, phase, slot), step, out, ho, ho, passes=passes, **kw)
     torch.cuda.synchronize()
     return _stats(out.permute(0, 3, 1, 2), ref)
@@ -86,6 +90,9 @@ def case_dgrad(n, h, cin, cout, k, stride, passes):
     ho = y.shape[2]
     wt = w.permute(1, 2, 3, 0).reshape(cin, k * k * cout).contiguous()  # (C_in, KH*KW*C_out)
     gy_nhwc = _nhwc(gy)
+    wt_lo = None
+    if os.environ.get("PROBE_PRESPLIT", "1") == "1" and passes == 3:
+        wt, wt_lo = dense.split_tf32(wt)
     dx = torch.zeros(n, h, h, cin, device="cuda")
     for ph in range(stride):
         for pw in range(stride):
@@ -94,7 +101,7 @@ def case_dgrad(n, h, cin, cout, k, stride, passes):
                 continue
             dense.conv_nhwc(gy_nhwc, wt, cin, (dh, dw, None, slot), 1, dx, h // stride, h // stride,
                             out_strides=(h * h * cin, stride * h * cin, stride * cin),
-                            out_offset=(ph * h + pw) * cin, passes=passes, w_slots=k * k)
+                            out_offset=(ph * h + pw) * cin, passes=passes, w_slots=k * k, w_lo=wt_lo)
     torch.cuda.synchronize()
     return _stats(dx.permute(0, 3, 1, 2), ref)
 
@@ -113,7 +120,7 @@ def case_wgrad(n, h, cin, cout, k, stride, passes):
     ref = w.grad.permute(0, 2, 3, 1).reshape(cout, k * k * cin)
     dh, dw, phase, slot, step = dense.fprop_taps(k, stride, pad)
     dwt = torch.empty(cout, k * k * cin, device="cuda")
-    dense.wgrad_nhwc(_nhwc(gy), _nhwc(x), (dh, dw, phase, slot), step, dwt, k * k, passes=passes)
+    dense.wgrad_nhwc(_nhwc(gy), _nhwc(x), (dh, dw, phase, slot), step, dwt, passes=passes)
     torch.cuda.synchronize()
     return _stats(dwt, ref)
 
@@ -167,14 +174,33 @@ CASES = {
 }
 
 
-def _variant(v):
-    os.environ["OBMAN_WGRAD_DESC"] = v
-    return case_wgrad_matrix(4096, 128, 256, 1)
+def case_rounding_mode():
+    """Does the tensor core truncate or round fp32 operands to tf32?  1-pass GEMM vs fp64 references built
+    from truncated / nearest-rounded inputs."""
+    import torch
+    from obman_train_b200 import dense
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(128, 64, device="cuda", generator=g)
+    w = torch.randn(128, 64, device="cuda", generator=g)
+    out = dense.gemm(a, w, passes=1).double()
+
+    def trunc(t):
+        return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+    def rna(t):
+        return ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    res = {}
+    for name, f in (("trunc", trunc), ("rna", rna)):
+        ref = f(a).double() @ f(w).double().t()
+        res["err_vs_" + name] = (out - ref).abs().max().item()
+    res.update({"max_err": min(res.values()), "rel": 0.0, "ref_max": 1.0, "nan": False, "frac_bad": 0.0})
+    return res
 
 
-for _v in ("4096,512,1,4", "512,4096,1,4", "4096,1024,1,4", "4096,512,1,3", "4096,1024,2,3", "1024,4096,2,3",
-           "4096,512,2,4", "4096,256,1,4"):
-    CASES["wgradv_" + _v.replace(",", "_")] = (lambda v=_v: _variant(v))
+CASES["rounding_mode_p1"] = case_rounding_mode
+CASES["stemlike_wgrad_4x4_128_32_64_p3"] = lambda: case_wgrad(2, 64, 32, 64, 3, 1, 3)
+CASES["wgrad3x3_s1_32_128_128_p3"] = lambda: case_wgrad(3, 32, 128, 128, 3, 1, 3)
+CASES["wgrad3x3_s1_20_96_160_p3"] = lambda: case_wgrad(2, 20, 96, 160, 3, 1, 3)
 
 
 def main():

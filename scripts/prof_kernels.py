@@ -22,7 +22,10 @@ def conv_case(h, cin, cout, k=3, stride=1):
     out = torch.empty(B, ho, ho, cout, device="cuda")
     bias = torch.randn(cout, device="cuda")
     flops = 2.0 * B * ho * ho * cout * k * k * cin
-    return (lambda: dense.conv_nhwc(x, w, cout, (dh, dw, phase, slot), step, out, ho, ho, bias=bias, relu=True, passes=PASSES)), flops
+    w_lo = None
+    if PASSES == 3 and os.environ.get("PROF_PRESPLIT", "1") == "1":
+        w, w_lo = dense.split_tf32(w)
+    return (lambda: dense.conv_nhwc(x, w, cout, (dh, dw, phase, slot), step, out, ho, ho, bias=bias, relu=True, passes=PASSES, w_lo=w_lo)), flops
 
 
 def wgrad_case(h, cin, cout, k=3, stride=1):
@@ -32,13 +35,16 @@ def wgrad_case(h, cin, cout, k=3, stride=1):
     dh, dw, phase, slot, step = dense.fprop_taps(k, stride, k // 2)
     dwt = torch.empty(cout, k * k * cin, device="cuda")
     flops = 2.0 * B * ho * ho * cout * k * k * cin
-    return (lambda: dense.wgrad_nhwc(dy, x, (dh, dw, phase, slot), step, dwt, k * k, passes=PASSES)), flops
+    return (lambda: dense.wgrad_nhwc(dy, x, (dh, dw, phase, slot), step, dwt, passes=PASSES)), flops
 
 
 def gemm_case(M, N, K):
     a = torch.randn(M, (K + 31) // 32 * 32, device="cuda")
     w = torch.randn(N, (K + 3) // 4 * 4, device="cuda")
-    return (lambda: dense.gemm(a, w, relu=True, passes=PASSES, n=N, k=K)), 2.0 * M * N * K
+    w_lo = None
+    if PASSES == 3 and os.environ.get("PROF_PRESPLIT", "1") == "1":
+        w, w_lo = dense.split_tf32(w)
+    return (lambda: dense.gemm(a, w, relu=True, passes=PASSES, n=N, k=K, w_lo=w_lo)), 2.0 * M * N * K
 
 
 CASES = [
@@ -51,7 +57,7 @@ CASES = [
     ("wgrad3x3 16x16 256->256", wgrad_case(16, 256, 256)),
     ("wgrad3x3 8x8 512->512", wgrad_case(8, 512, 512)),
     ("gemm 41088x257x515", gemm_case(B * 642, 257, 515)),
-    ("stem 4x4 128x128 32->64", None),
+    ("stem-like wgrad 128x128 32->64 (16 taps)", None),
 ]
 
 

@@ -154,7 +154,8 @@ def workload_config(n_gpus):
                         "AtlasNet(642 pts) + Chamfer(600 GT) + Mano/Atlas losses, 256x256",
             "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * n_gpus,
             "parallelism": "dp%d" % n_gpus, "precision": "3xTF32 tensor-core passes (fp32-equivalent) fwd+bwd",
-            "l2_policy": "activations per step (~3 GB) exceed the 126 MB L2; no explicit flush"}
+            "l2_policy": "activations per step (~3 GB) exceed the 126 MB L2; no explicit flush",
+            "launch": "whole step replayed as one CUDA graph (--no-graph for eager launches)"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -212,23 +213,41 @@ def run_b200(args):
             dist.barrier()
         return ms.item()
 
+    use_graph = not args.no_graph
+    if use_graph:
+        trainer.capture(resident)  # whole step (fwd + bwd + all-reduce + Adam) as one CUDA graph
+
     def step_resident():
-        trainer.step(resident)
+        if use_graph:
+            trainer.replay()
+        else:
+            trainer.step(resident)
 
     loss_host = torch.zeros(1).pin_memory()
+    tensor_keys = [(TransQueries.images, "images"), (TransQueries.joints3d, "joints3d"),
+                   (TransQueries.verts3d, "verts3d"), (TransQueries.objpoints3d, "objpoints3d")]
 
     def step_e2e():
-        loss = trainer.step(to_device(pinned))
+        if use_graph:
+            for q, name in tensor_keys:  # pinned host -> static device buffers, every step
+                resident[q].copy_(pinned[name], non_blocking=True)
+            loss = trainer.replay()
+        else:
+            loss = trainer.step(to_device(pinned))
         loss_host.copy_(loss.detach(), non_blocking=False)  # the user's read of the step result
 
-    for _ in range(max(3, args.warmup)):
-        step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # sampled through warm-up and the timed region (both under load)
+    for _ in range(max(3, args.warmup)):
+        step_resident()
     kern0 = _lib.kernel_count
     ms = timed(args.steps, step_resident)
     kernels = _lib.kernel_count - kern0
+    if use_graph:  # replays issue no Python-side calls: count the kernels of one eager step instead
+        k0 = _lib.kernel_count
+        trainer.step(resident)
+        kernels = (_lib.kernel_count - k0) * args.steps
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
@@ -238,9 +257,15 @@ def run_b200(args):
     dense.profile_begin()
     nprof = min(args.steps, 3)
     for _ in range(nprof):
-        step_resident()
+        trainer.step(resident)  # eager (not the graph): per-launch events need individual launches
     dense.profile_end.steps = nprof
     prof = dense.profile_end()
+    if rank == 0 and args.dump_launches:
+        per = len(dense.last_profile) // nprof
+        with open(args.dump_launches, "w") as f:
+            f.write("# tensor-core launches of one training step (CUDA events, passes=%s): call shape | GFLOP | ms | TFLOP/s\n" % args.precision)
+            for tag, fl, t in dense.last_profile[-per:]:
+                f.write("%-60s %9.3f %8.4f %8.1f\n" % (tag, fl / 1e9, t, fl / t / 1e9 if t > 0 else 0))
 
     if rank != 0:
         return
@@ -281,11 +306,13 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--dump-launches", default=None, help="write the per-launch tensor-core profile of one step here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -165,9 +165,10 @@ int obman_pointmlp_l1_fwd(const float* G, long long g_bstride, const float* F, i
 /* g (B,N, ld) -> gF[b,c] = sum_n g, gG[n,c] = sum_b g (gG may be NULL). */
 int obman_pointmlp_l1_bwd(const float* g, int B, int N, int C, int ld, float* gF, float* gG,
                           void* stream);
-/* Fused torch.optim.Adam step (traineval.py:113-116) on flat fp32 buffers; g is multiplied by grad_scale. */
+/* Fused torch.optim.Adam step (traineval.py:113-116) on flat fp32 buffers; g is multiplied by grad_scale.
+ * step_dev: device float holding the 1-based step number (device memory so that CUDA graphs can replay it). */
 int obman_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                    float beta2, float eps, float weight_decay, int step, float grad_scale,
+                    float beta2, float eps, float weight_decay, const float* step_dev, float grad_scale,
                     void* stream);
 
 #ifdef __cplusplus

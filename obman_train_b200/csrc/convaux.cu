@@ -260,9 +260,13 @@ bn_wgrad_finish_kernel(const float* __restrict__ dwraw, long long dw_ld, const f
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps, float wd,
-            float bc1, float bc2_sqrt, float gscale) {
+            const float* __restrict__ step_dev, float gscale) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  // the step number lives in device memory so that a captured CUDA graph applies the right bias correction
+  const float step = step_dev[0];
+  const float bc1 = 1.f - powf(beta1, step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
   float grad = g[i] * gscale;
   const float pv = p[i];
   if (wd != 0.f) grad = fmaf(wd, pv, grad);
@@ -431,12 +435,10 @@ extern "C" int obman_bn_wgrad_finish(const float* dwraw, long long dw_ld, const 
 }
 
 extern "C" int obman_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr,
-                               float beta1, float beta2, float eps, float weight_decay, int step,
-                               float grad_scale, void* stream) {
-  OBMAN_REQUIRE(p && g && m && v && n > 0 && step >= 1, "obman_adam_step: bad arguments");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2 = 1.f - powf(beta2, (float)step);
+                               float beta1, float beta2, float eps, float weight_decay,
+                               const float* step_dev, float grad_scale, void* stream) {
+  OBMAN_REQUIRE(p && g && m && v && n > 0 && step_dev, "obman_adam_step: bad arguments");
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale);
+      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale);
   return check_launch("adam_kernel");
 }

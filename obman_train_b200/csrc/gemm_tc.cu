@@ -287,10 +287,12 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         for (int i = tid; i < A_V4 + b_v4; i += 128) {
           float4* src = i < A_V4 ? a + i : b + (i - A_V4);
           float4* dst = i < A_V4 ? alo + i : blo + (i - A_V4);
-          float4 v = *src, h, l;
-          h.x = to_tf32_rna(v.x); h.y = to_tf32_rna(v.y); h.z = to_tf32_rna(v.z); h.w = to_tf32_rna(v.w);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          *src = h;
+          // The tensor core TRUNCATES fp32 operands to tf32 (measured: scripts/probe_dense.py rounding_mode),
+          // so the raw tile already acts as `hi`; only lo = v - trunc(v) has to be written.
+          const float4 v = *src;
+          float4 l;
+          l.x = v.x - tf32_trunc(v.x); l.y = v.y - tf32_trunc(v.y);
+          l.z = v.z - tf32_trunc(v.z); l.w = v.w - tf32_trunc(v.w);
           *dst = l;
         }
         fence_proxy_async_smem();

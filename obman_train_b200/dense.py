@@ -37,21 +37,26 @@ def profile_end():
     global _prof
     rec, _prof = _prof, None
     torch.cuda.synchronize()
-    ms = sum(e0.elapsed_time(e1) for _, e0, e1 in rec)
-    flops = sum(f for f, _, _ in rec)
+    global last_profile
+    last_profile = [(tag, f, e0.elapsed_time(e1)) for f, e0, e1, tag in rec]
+    ms = sum(t for _, _, t in last_profile)
+    flops = sum(f for _, f, _ in last_profile)
     steps = max(1, getattr(profile_end, "steps", 1))
     return {"tflops": flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0, "ms_total": ms, "launches": len(rec),
             "ms_per_step": ms / steps, "launches_per_step": len(rec) / steps, "flops": flops}
 
 
-def _tc_call(flops, name, *args):
+last_profile = []
+
+
+def _tc_call(flops, name, *args, tag=""):
     if _prof is None:
         return call(name, *args)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     call(name, *args)
     e1.record()
-    _prof.append((float(flops), e0, e1))
+    _prof.append((float(flops), e0, e1, name[6:] + " " + tag))
 
 
 def _ints(vals):
@@ -85,8 +90,8 @@ def gemm(a, w, out=None, bias=None, addend=None, mask_src=None, alpha=1.0, relu=
         out = torch.empty((M, N), device=a.device, dtype=torch.float32)
     _tc_call(2.0 * M * N * K, "obman_gemm", ptr(a), a.stride(0), ptr(w), ptr(w_lo) if passes == 3 else None,
              w.stride(0), M, N, K, ptr(out), out.stride(0),
-         ptr(bias), ptr(addend), ptr(mask_src), float(alpha), int(relu), int(accumulate), int(passes),
-         stream_ptr())
+             ptr(bias), ptr(addend), ptr(mask_src), float(alpha), int(relu), int(accumulate), int(passes),
+             stream_ptr(), tag="M%d N%d K%d" % (M, N, K))
     return out
 
 
@@ -144,7 +149,7 @@ def conv_nhwc(x, w, c_out, taps, in_step, out, h_out, w_out, out_strides=None, o
          int(w_slots), len(dh), _ints(dh), _ints(dw), _ints(phase) if phase is not None else None,
          _ints(slot), off(out), int(h_out), int(w_out), int(out_strides[0]), int(out_strides[1]),
          int(out_strides[2]), ptr(bias), off(addend), off(mask_src), int(relu), int(passes),
-         stream_ptr())
+         stream_ptr(), tag="n%d %dx%d c%d->%d taps%d" % (n_img, h_out, w_out, c_in, c_out, len(dh)))
     return out
 
 
@@ -161,7 +166,8 @@ def wgrad_nhwc(dy, x, taps, in_step, dw_out, passes=3, algo_k=None):
     _tc_call(2.0 * n_img * h_out * w_out * c_out * k_eff,
              "obman_wgrad_nhwc", ptr(dy), n_img, h_out, w_out, c_out, ptr(x), h_in, w_in, c_in,
              int(in_step), len(dh), _ints(dh), _ints(dw), _ints(phase) if phase is not None else None,
-             ptr(dw_out), int(passes), stream_ptr())
+             ptr(dw_out), int(passes), stream_ptr(),
+             tag="n%d %dx%d c%d->%d taps%d" % (n_img, h_out, w_out, c_in, c_out, len(dh)))
     return dw_out
 
 

@@ -109,9 +109,23 @@ class AtlasBranch(nn.Module):
         return results
 
 
+_faces_cache = {}
+
+
+def _faces_on(faces, device):
+    """(F,3) int64 face tensor on ``device``, cached (no host->device copy per step, CUDA-graph safe)."""
+    if torch.is_tensor(faces):
+        return faces.to(device)
+    arr = np.ascontiguousarray(np.asarray(faces).astype(np.int64))
+    key = (arr.shape, hash(arr.tobytes()), str(device))
+    if key not in _faces_cache:
+        _faces_cache[key] = torch.from_numpy(arr).to(device)
+    return _faces_cache[key]
+
+
 def edge_loss(edges, faces):
     """atlasbranch.py:153-167: mean absolute deviation of the squared edge lengths from their per-sample mean."""
-    faces = torch.as_tensor(np.asarray(faces).astype(np.int64), device=edges.device)
+    faces = _faces_on(faces, edges.device)
     edges_A = edges[:, faces[:, 0]]
     edges_B = edges[:, faces[:, 1]]
     edges_C = edges[:, faces[:, 2]]

@@ -69,6 +69,16 @@ class ManoBranch(nn.Module):
             self.right_skeleton_reg.weight.data = torch.eye(joint_nb)
         self.faces = self.mano_layer_right.th_faces
 
+    def _side_indices(self, flags, device):
+        """Row indices of the right / left hands, cached per side pattern (built from the Python list: no
+        device synchronisation, and safe to call while a CUDA graph is being captured once warmed up)."""
+        cache = self.__dict__.setdefault("_side_cache", {})
+        key = (flags, str(device))
+        if key not in cache:
+            cache[key] = (torch.tensor([i for i, f in enumerate(flags) if f], dtype=torch.long, device=device),
+                          torch.tensor([i for i, f in enumerate(flags) if not f], dtype=torch.long, device=device))
+        return cache[key]
+
     def forward(self, inp, sides, root_palm=False, shape=None, pose=None, use_stereoshape=False):
         base_features = self.base_layer(inp)
         pose = mlp.linear(base_features, self.pose_reg.weight, self.pose_reg.bias)
@@ -95,9 +105,7 @@ class ManoBranch(nn.Module):
             if self.adapt_skeleton:
                 joints = adapt(joints, self.right_skeleton_reg if n_right == B else self.left_skeleton_reg)
         else:
-            is_rights = torch.tensor(flags, dtype=torch.bool, device=inp.device)
-            idx_r = torch.nonzero(is_rights).squeeze(1)
-            idx_l = torch.nonzero(~is_rights).squeeze(1)
+            idx_r, idx_l = self._side_indices(tuple(flags), inp.device)
             verts_r, joints_r = self.mano_layer_right(
                 mano_pose[idx_r], th_betas=None if shape is None else shape[idx_r], th_trans=trans,
                 root_palm=root_palm)

@@ -47,6 +47,8 @@ class FlatAdamTrainer(object):
         self.numel = total
         self.param_numel = sum(p.numel() for _, p in params)
         self.step_count = 0
+        self._step_dev = torch.zeros(1, device=dev, dtype=torch.float32)  # step number for captured graphs
+        self._graph = None
 
     def zero_grad(self):
         self.flat_g.zero_()
@@ -71,10 +73,48 @@ class FlatAdamTrainer(object):
     def adam_update(self):
         if not self.flat_p.is_cuda:
             raise RuntimeError("FlatAdamTrainer.adam_update: the fused Adam kernel needs CUDA buffers (no CPU path)")
-        self.step_count += 1
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self.step_count += 1
+            self._step_dev.fill_(float(self.step_count))
         call("obman_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.exp_avg), ptr(self.exp_avg_sq),
              self.numel, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-             float(self.weight_decay), int(self.step_count), 1.0 / float(self.world_size), stream_ptr())
+             float(self.weight_decay), ptr(self._step_dev), 1.0 / float(self.world_size), stream_ptr())
+
+    # ---- CUDA-graph mode: the whole step (forward, backward, all-reduce, Adam) replayed as one graph ----------
+    def capture(self, sample, warmup=3):
+        """Capture ``step`` on ``sample`` (whose tensors become the static input buffers).  ~1000 kernel
+        launches per step otherwise cost more CPU time than the GPU needs to execute them."""
+        if self.world_size > 1:
+            # NCCL inside a captured graph needs the communicator warmed up outside of capture
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(sample)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._static_sample = sample
+        self._graph = torch.cuda.CUDAGraph()
+        steps_before = self.step_count
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self.step(sample)
+        # the Adam bias corrections are baked into the captured launch; keep them exact by passing the
+        # step number through device memory instead (see adam_update)
+        self.step_count = steps_before
+        return self._graph
+
+    def replay(self, sample=None):
+        """Run the captured step; ``sample`` tensors (if given) are copied into the static input buffers."""
+        if sample is not None and sample is not self._static_sample:
+            for k, v in sample.items():
+                if torch.is_tensor(v):
+                    self._static_sample[k].copy_(v, non_blocking=True)
+        self.step_count += 1
+        self._step_dev.fill_(float(self.step_count))
+        self._graph.replay()
+        return self._static_loss
 
     def grads_are_views(self):
         """Autograd must have accumulated in place into the flat buffer (sanity check for tests)."""

@@ -70,25 +70,28 @@ struct GemmEpilogue {
   long long ld, sN, sH, sW;
 };
 
-template <int BN, int PASSES, int TS>
+// OCC = CTAs per SM the configuration is sized for: with 2, one CTA's prologue / epilogue overlaps the other's
+// main loop (the kernel is not persistent), at the price of a shallower per-CTA pipeline.
+template <int BN, int PASSES, int TS, int OCC>
 struct GemmCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES =
       TS ? (A_TILE_BYTES + 2 * B_TILE_BYTES) : (A_TILE_BYTES + B_TILE_BYTES) * (PASSES == 3 ? 2 : 1);
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = ((OCC == 2 ? 104 : 200) * 1024) / STAGE_BYTES;
   static constexpr int STAGES_SMEM = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  // TS: every stage also owns 64 TMEM columns (A hi | A lo); 512 columns in total
-  static constexpr int STAGES_TMEM = (512 - BN) / 64;
+  // TS: every stage also owns 64 TMEM columns (A hi | A lo); 512 columns per SM in total
+  static constexpr int STAGES_TMEM = ((OCC == 2 ? 256 : 512) - BN) / 64;
   static constexpr int STAGES = TS ? (STAGES_SMEM < STAGES_TMEM ? STAGES_SMEM : STAGES_TMEM) : STAGES_SMEM;
   static constexpr int TMEM_NEED = TS ? BN + STAGES * 64 : BN;
   static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int PASSES, int MODE, int TS>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, int PASSES, int MODE, int TS, int OCC>
+__global__ void __launch_bounds__(GEMM_THREADS, OCC)
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, const GemmEpilogue epi) {
-  using Cfg = GemmCfg<BN, PASSES, TS>;
+  using Cfg = GemmCfg<BN, PASSES, TS, OCC>;
+  static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
   constexpr int S = Cfg::STAGES;
   constexpr int B_TILE_BYTES = Cfg::B_TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -373,13 +376,13 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, int PASSES, int MODE, int TS>
+template <int BN, int PASSES, int MODE, int TS, int OCC>
 static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const GemmEpilogue& epi, dim3 grid,
                        cudaStream_t st) {
-  using Cfg = GemmCfg<BN, PASSES, TS>;
+  using Cfg = GemmCfg<BN, PASSES, TS, OCC>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, MODE, TS>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, MODE, TS, OCC>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute(%d bytes) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -387,7 +390,7 @@ static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const Gemm
     }
     attr = true;
   }
-  gemm_tc_kernel<BN, PASSES, MODE, TS><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
+  gemm_tc_kernel<BN, PASSES, MODE, TS, OCC><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -395,11 +398,19 @@ static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const Gemm
 template <int MODE>
 static int dispatch_gemm(int BN, int passes, int ts, const GemmMaps& maps, const GemmProgram& prog,
                          const GemmEpilogue& epi, dim3 grid, cudaStream_t st) {
-#define OBMAN_GEMM_CASE(bn)                                                                     \
-  if (BN == bn) {                                                                               \
-    if (MODE == 0 && ts && passes == 3) return launch_gemm<bn, 3, 0, 1>(maps, prog, epi, grid, st); \
-    return passes == 3 ? launch_gemm<bn, 3, MODE, 0>(maps, prog, epi, grid, st)                 \
-                       : launch_gemm<bn, 1, MODE, 0>(maps, prog, epi, grid, st);                \
+  static int occ2 = -1;
+  if (occ2 < 0) {
+    const char* e = getenv("OBMAN_GEMM_OCC");
+    occ2 = (e && e[0] == '1') ? 0 : 1;
+  }
+#define OBMAN_GEMM_CASE(bn)                                                                         \
+  if (BN == bn) {                                                                                   \
+    if (MODE == 0 && ts && passes == 3) {                                                           \
+      if (bn <= 128 && occ2) return launch_gemm<bn, 3, 0, 1, (bn <= 128 ? 2 : 1)>(maps, prog, epi, grid, st); \
+      return launch_gemm<bn, 3, 0, 1, 1>(maps, prog, epi, grid, st);                                \
+    }                                                                                               \
+    return passes == 3 ? launch_gemm<bn, 3, MODE, 0, 1>(maps, prog, epi, grid, st)                  \
+                       : launch_gemm<bn, 1, MODE, 0, 1>(maps, prog, epi, grid, st);                 \
   }
   OBMAN_GEMM_CASE(64)
   OBMAN_GEMM_CASE(128)

@@ -30,6 +30,30 @@ CFG = dict(resnet_version=18, mano_root="synthetic", mano_comps=30, mano_use_sha
 PER_GPU_BATCH = 64
 IMG = 256
 N_GT = 600
+WORKLOAD = "BASELINE.json configs[1]: train step fwd+bwd+Adam, ResNet-18 + ManoLayer(778v) + AtlasNet(642 pts) + " \
+           "Chamfer(600 GT) + Mano/Atlas losses, 256x256"
+
+
+def use_config3():
+    """BASELINE.json configs[2]: batch 256, separate Atlas encoder, ico-4 sphere (2562 points / 5120 faces),
+    2500 GT points, Chamfer + contact_zones loss (dist_tanh, thresh 10/20)."""
+    global PER_GPU_BATCH, N_GT, WORKLOAD
+    PER_GPU_BATCH, N_GT = 256, 2500
+    CFG.update(atlas_separate_encoder=True, atlas_ico_divisions=4, atlas_points_nb=2500, contact_lambda=1,
+               collision_lambda=1, contact_zones="zones", contact_mode="dist_tanh", collision_mode="dist_tanh",
+               contact_thresh=10, collision_thresh=20)
+    WORKLOAD = ("BASELINE.json configs[2]: train step fwd+bwd+Adam, 2x ResNet-18 (separate Atlas encoder) + "
+                "ManoLayer + AtlasNet(ico-4, 2562 pts) + Chamfer(2500 GT) + contact_zones loss, 256x256")
+
+
+def _hand_targets(B, g):
+    if CFG.get("contact_lambda"):
+        # hand-shaped targets (MANO template, mm) so that the contact masks are non-trivial (SURVEY.md 8d config 3)
+        from obman_train_b200.assets import load_contacts
+        verts, _ = load_contacts()
+        hand = torch.tensor(verts * 1000, dtype=torch.float32).unsqueeze(0).repeat(B, 1, 1)
+        return hand + torch.randn(B, 778, 3, generator=g) * 5
+    return torch.randn(B, 778, 3, generator=g) * 40
 
 
 def synthetic_sample(B, seed):
@@ -40,7 +64,7 @@ def synthetic_sample(B, seed):
         "sides": ["right" if i % 2 == 0 else "left" for i in range(B)],
         "root": "wrist",
         "joints3d": torch.randn(B, 21, 3, generator=g) * 40,
-        "verts3d": torch.randn(B, 778, 3, generator=g) * 40,
+        "verts3d": _hand_targets(B, g),
         "objpoints3d": torch.randn(B, N_GT, 3, generator=g) * 40 + 30,
     }
 
@@ -117,12 +141,14 @@ def cpu_reference_steps(batch, steps, warmup):
     tables = {s: {k: v.detach() for k, v in getattr(model.mano_branch, "mano_layer_" + s).named_buffers()
                   if k != "th_faces"} for s in ("right", "left")}
     grid, faces = model.atlas_branch.test_verts, model.atlas_branch.test_faces
+    from obman_train_b200.assets import load_contacts
+    zones = load_contacts()[1]
     sample = synthetic_sample(batch, 0)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad()
-        total, _, _ = nets.handnet_forward(state, CFG, sample, tables, grid, faces, None)
+        total, _, _ = nets.handnet_forward(state, CFG, sample, tables, grid, faces, zones)
         total.backward()
         opt.step()
         if it >= warmup:
@@ -150,8 +176,7 @@ def run_reference(args):
 
 
 def workload_config(n_gpus):
-    return {"workload": "BASELINE.json configs[1]: train step fwd+bwd+Adam, ResNet-18 + ManoLayer(778v) + "
-                        "AtlasNet(642 pts) + Chamfer(600 GT) + Mano/Atlas losses, 256x256",
+    return {"workload": WORKLOAD,
             "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * n_gpus,
             "parallelism": "dp%d" % n_gpus, "precision": "3xTF32 tensor-core passes (fp32-equivalent) fwd+bwd",
             "l2_policy": "activations per step (~3 GB) exceed the 126 MB L2; no explicit flush",
@@ -312,8 +337,12 @@ def main():
     ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
+                    help="2 = BASELINE configs[1] (default, the headline); 3 = BASELINE configs[2] (B=256, contact)")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch tensor-core profile of one step here")
     args = ap.parse_args()
+    if args.config == 3:
+        use_config3()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -421,10 +421,20 @@ static int dispatch_gemm(int BN, int passes, int ts, const GemmMaps& maps, const
 }
 
 static int pick_bn(int N, long long m_tiles) {
-  // 256-wide tiles halve the A re-reads; take them whenever the grid still covers most of the SMs
-  if (N > 128 && m_tiles * ((N + 255) / 256) >= (num_sms() * 3) / 4) return 256;
-  if (N > 64) return 128;
-  return 64;
+  // Column tile: minimise padded columns / relative tile efficiency (measured: 256-wide tiles are the most
+  // efficient per column, 64-wide the least), but only take 256 when the grid still covers most of the SMs.
+  if (N <= 64) return 64;
+  const double eff[3] = {0.6, 0.85, 1.0};
+  const int bn[3] = {64, 128, 256};
+  int best = 128;
+  double best_cost = 1e30;
+  for (int i = 1; i < 3; ++i) {
+    const long long tiles_n = (N + bn[i] - 1) / bn[i];
+    if (bn[i] == 256 && m_tiles * tiles_n < (num_sms() * 3) / 4) continue;
+    const double cost = (double)(tiles_n * bn[i]) / eff[i];
+    if (cost < best_cost) { best_cost = cost; best = bn[i]; }
+  }
+  return best;
 }
 
 static bool ts_enabled() {

@@ -63,10 +63,14 @@ def thresh_ious(gt_dists, pred_dists, thresh):
 
 
 def meshiou(gt_dists, pred_dists, threshs=(1, 2, 3, 4, 5, 6, 7, 8, 9, 10)):
-    """contactloss.py:35-47: IoU of thresholded contact maps, averaged over the batch, and its AUC."""
+    """contactloss.py:35-47: IoU of thresholded contact maps, averaged over the batch, and its AUC.
+    The AUC is integrated on the device (the reference pulls the IoU table to the host for ``np.trapz``,
+    one more sync per step); it is returned as a 0-dim tensor, ``float()`` / ``.item()`` give the number."""
     all_ious = torch.stack([thresh_ious(gt_dists, pred_dists, t) for t in threshs])
-    trapz = getattr(np, "trapezoid", None) or np.trapz
-    iou_auc = np.mean(trapz(all_ious.cpu().numpy(), axis=0, x=list(threshs)))
+    key = ("threshs", tuple(threshs), str(all_ious.device))
+    if key not in _cache:
+        _cache[key] = torch.tensor([float(t) for t in threshs], device=all_ious.device)
+    iou_auc = torch.trapezoid(all_ious, x=_cache[key], dim=0).mean()
     return all_ious.mean(1), iou_auc
 
 

@@ -128,14 +128,15 @@ int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out, int c_out
                      const int* tap_dw, const int* tap_phase, float* dw, int passes, void* stream);
 
 /* ---- Encoder helpers (bandwidth-bound; mano_train/networks/bases/resnet.py:154-188) -----------------------
- * obman_stem_pack: x (B,3,H,W) NCHW -> out (B,H/2,W/2,32) NHWC space-to-depth (channel (ph*2+pw)*3+c,
- * 20 zero channels) so that the 7x7/2 stem runs as a 4x4/1 obman_conv_nhwc. */
+ * obman_stem_pack: x (B,3,H,W) NCHW -> out (B,H/2,W/2,64) NHWC: 2x2 space-to-depth (12 channels) with the four
+ * horizontal taps of the 7x7/2 stem packed along channels (q*12 + (ph*2+pw)*3 + c, 16 zero channels), so that the
+ * stem runs as a 4-tap (vertical), 64-channel obman_conv_nhwc (K = 256). */
 int obman_stem_pack(const float* x, int B, int H, int W, float* out, void* stream);
 /* BatchNorm(eval) folding + weight re-layout, once per step.  w (O,I,KH,KW); gamma/beta/mean/var (O) or NULL
  * (no BN), cbias (O) conv bias or NULL: shift = beta + (cbias - mean)*scale (no BN: shift = cbias).
  * wf_lo / wft_lo (NULL or): pre-split mode, wf/wft = tf32-rounded value, *_lo = residual.
  * wf (O, KH*KW*Ip) fprop operand, wft (I, KH*KW*O) dgrad operand
- * (NULL to skip), shift/scale/rstd (O).  stem=1: (O,3,7,7) filter -> (O, 16*32) space-to-depth layout. */
+ * (NULL to skip), shift/scale/rstd (O).  stem=1: (O,3,7,7) filter -> (O, 4*64) layout of obman_stem_pack. */
 int obman_fold_conv(const float* w, const float* cbias, const float* gamma, const float* beta, const float* mean,
                     const float* var, float eps, int O, int I, int KH, int KW, int Ip, int stem,
                     float* wf, float* wf_lo, float* wft, float* wft_lo, float* shift, float* scale,

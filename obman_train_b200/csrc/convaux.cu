@@ -1,7 +1,8 @@
 // Bandwidth-bound helpers around the tensor-core convolutions of the ResNet-18 encoder
 // (mano_train/networks/bases/resnet.py:154-188) and the parameter update:
-//   stem_pack        NCHW image -> space-to-depth NHWC (2x2 blocks, 12 real + 20 zero channels) so that the
-//                    7x7/2 stem becomes a 4x4/1 shifted-box convolution on the same TMA path as every other conv
+//   stem_pack        NCHW image -> space-to-depth NHWC with the 4 horizontal taps packed along channels (48 real + 16
+//                    zero channels) so that the 7x7/2 stem becomes a 4-tap shifted-box convolution (K = 256) on the same
+//                    TMA path as every other conv
 //   fold_conv        BatchNorm(eval) folding + OIHW -> (O, KH*KW*I) / (I, KH*KW*O) re-layout, once per step
 //   maxpool 3x3/2    forward (with arg-max) and backward
 //   meanpool         spatial mean forward; backward fused with the ReLU mask of the last block
@@ -18,25 +19,30 @@ __device__ __forceinline__ float to_tf32_rna_dev(float x) {
   return __uint_as_float(r);
 }
 
-// x (B,3,H,W) NCHW  ->  out (B, H/2, W/2, 32): channel (ph*2+pw)*3 + c = x[b, c, 2i+ph, 2j+pw], channels 12..31 = 0
+// x (B,3,H,W) NCHW -> out (B, H/2, W/2, 64): space-to-depth (2x2 blocks -> 12 channels) with the FOUR horizontal
+// taps of the 7x7/2 stem packed along the channel axis:
+//   out[b,i,j, q*12 + (ph*2+pw)*3 + c] = x[b, c, 2i+ph, 2(j+q-2)+pw]   (0 outside the image), q = 0..3; channels 48..63 = 0
+// so that the stem becomes a 4-tap (vertical) x 64-channel shifted-box convolution: K = 256 instead of 16 x 32 = 512.
 __global__ void __launch_bounds__(256)
 stem_pack_kernel(const float* __restrict__ x, int B, int H, int W, float* __restrict__ out) {
   const int Ho = H / 2, Wo = W / 2;
-  const size_t total = (size_t)B * Ho * Wo * 8;  // one float4 (4 channels) per thread
+  const size_t total = (size_t)B * Ho * Wo * 16;  // one float4 (4 channels) per thread
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
-  const int q = (int)(t & 7);
-  size_t p = t >> 3;
+  const int q4 = (int)(t & 15);
+  size_t p = t >> 4;
   const int j = (int)(p % Wo); p /= Wo;
   const int i = (int)(p % Ho);
   const int b = (int)(p / Ho);
   float v[4] = {0.f, 0.f, 0.f, 0.f};
-  if (q < 3) {
+  if (q4 < 12) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int ch = q * 4 + e;  // 0..11
+      const int chn = q4 * 4 + e;  // 0..47
+      const int q = chn / 12, ch = chn - q * 12;
       const int ph = ch / 6, pw = (ch / 3) & 1, c = ch % 3;
-      v[e] = __ldg(x + (((size_t)b * 3 + c) * H + (2 * i + ph)) * W + (2 * j + pw));
+      const int jj = j + q - 2;
+      if (jj >= 0 && jj < Wo) v[e] = __ldg(x + (((size_t)b * 3 + c) * H + (2 * i + ph)) * W + (2 * jj + pw));
     }
   }
   reinterpret_cast<float4*>(out)[t] = make_float4(v[0], v[1], v[2], v[3]);
@@ -48,7 +54,7 @@ stem_pack_kernel(const float* __restrict__ x, int B, int H, int W, float* __rest
 //   wf [o][(kh*KW+kw)*Ip + i] = s[o]*w[o,i,kh,kw]        (fprop B operand; Ip = padded input channels)
 //   wft[i][(kh*KW+kw)*O  + o] = s[o]*w[o,i,kh,kw]        (dgrad B operand), i < I only
 //   shift[o] = beta + (conv_bias - mean)*s ; scale[o] = s ; rstd[o]
-// stem == 1: w is the (64,3,7,7) stem filter, written in the 4x4 x 32-channel space-to-depth layout.
+// stem == 1: w is the (64,3,7,7) stem filter, written in the 4-tap x 64-channel layout of stem_pack_kernel.
 __global__ void __launch_bounds__(256)
 fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
                  const float* __restrict__ gamma,
@@ -70,19 +76,19 @@ fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
     shift[o] = gamma ? beta[o] + (cb - mean[o]) * s : cb;
   }
   if (stem) {
-    // taps (a,b) in [-2,1]^2 -> slot (a+2)*4 + (b+2); channel (ph*2+pw)*3 + c <-> kh = 2a+ph+3, kw = 2b+pw+3
-    for (int k = threadIdx.x; k < 16 * 32; k += blockDim.x) {
-      const int slot = k >> 5, ch = k & 31;
+    // vertical tap a in [-2,1] -> slot a+2; channel q*12 + (ph*2+pw)*3 + c <-> kh = 2a+ph+3, kw = 2(q-2)+pw+3
+    for (int k = threadIdx.x; k < 4 * 64; k += blockDim.x) {
+      const int slot = k >> 6, chn = k & 63;
       float v = 0.f;
-      if (ch < 12) {
-        const int a = (slot >> 2) - 2, b = (slot & 3) - 2;
+      if (chn < 48) {
+        const int a = slot - 2, q = chn / 12, ch = chn - q * 12;
         const int ph = ch / 6, pw = (ch / 3) & 1, c = ch % 3;
-        const int kh = 2 * a + ph + 3, kw = 2 * b + pw + 3;
+        const int kh = 2 * a + ph + 3, kw = 2 * (q - 2) + pw + 3;
         if (kh >= 0 && kh < 7 && kw >= 0 && kw < 7) v = s * w[((o * 3 + c) * 7 + kh) * 7 + kw];
       }
       const float h = to_tf32_rna_dev(v);
-      wf[(size_t)o * 512 + k] = wf_lo ? h : v;
-      if (wf_lo) wf_lo[(size_t)o * 512 + k] = v - h;
+      wf[(size_t)o * 256 + k] = wf_lo ? h : v;
+      if (wf_lo) wf_lo[(size_t)o * 256 + k] = v - h;
     }
     return;
   }
@@ -217,7 +223,7 @@ colsum_kernel(const float* __restrict__ x, long long rows, int C, long long ld, 
 }
 
 // dwraw [O][(kh*KW+kw)*Ip + i] -> gw (O,I,KH,KW) = s[o]*dwraw ; ggamma[o] = rstd*(sum_k w*dwraw - mean*gbeta) ; gbeta = colsum
-// stem == 1: dwraw is in the 16-slot x 32-channel space-to-depth layout of the 7x7 stem.
+// stem == 1: dwraw is in the 4-tap x 64-channel layout of stem_pack_kernel.
 __global__ void __launch_bounds__(256)
 bn_wgrad_finish_kernel(const float* __restrict__ dwraw, long long dw_ld, const float* __restrict__ w,
                        const float* __restrict__ cbias,
@@ -235,8 +241,8 @@ bn_wgrad_finish_kernel(const float* __restrict__ dwraw, long long dw_ld, const f
     float raw;
     if (stem) {
       const int kh = t / 7, kw = t % 7;
-      const int a = (kh - 3) >> 1, ph = (kh - 3) & 1, b = (kw - 3) >> 1, pw = (kw - 3) & 1;
-      raw = dwraw[(size_t)o * dw_ld + ((a + 2) * 4 + (b + 2)) * 32 + (ph * 2 + pw) * 3 + i];
+      const int a = (kh - 3) >> 1, ph = (kh - 3) & 1, q = ((kw - 3) >> 1) + 2, pw = (kw - 3) & 1;
+      raw = dwraw[(size_t)o * dw_ld + (a + 2) * 64 + q * 12 + (ph * 2 + pw) * 3 + i];
     } else {
       raw = dwraw[(size_t)o * dw_ld + (size_t)t * Ip + i];
     }
@@ -360,7 +366,7 @@ extern "C" int obman_pointmlp_l1_bwd(const float* g, int B, int N, int C, int ld
 
 extern "C" int obman_stem_pack(const float* x, int B, int H, int W, float* out, void* stream) {
   OBMAN_REQUIRE(x && out && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "obman_stem_pack: bad arguments");
-  const size_t total = (size_t)B * (H / 2) * (W / 2) * 8;
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * 16;
   stem_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, out);
   return check_launch("stem_pack_kernel");
 }

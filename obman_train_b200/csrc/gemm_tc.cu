@@ -303,45 +303,60 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
       }
     }
     // ---- epilogue ----
+    // TMEM -> registers (lane = tile row) -> XOR-swizzled shared-memory transpose -> each store / addend / mask
+    // instruction touches 4 rows x 128 contiguous bytes (the row-per-lane layout would touch 32 rows x 16 bytes).
     mbar_wait(accum, 0);
     tc_fence_after();
-    bool row_ok;
-    long long row_off;
-    if (MODE == 0 && prog.spatial) {
-      const int tw = r % prog.TW;
-      const int th = (r / prog.TW) % prog.TH;
-      const int tn = r / (prog.TW * prog.TH);
-      const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
-      row_ok = n < prog.n_img && h < prog.h_out && w < prog.w_out;
-      row_off = n * epi.sN + h * epi.sH + w * epi.sW;
-    } else {
-      row_ok = (m0 + r) < prog.M;
-      row_off = (long long)(m0 + r) * epi.ld;
+    // all MMAs (and therefore all TMA loads and operand reads) have retired: stage 0 is free for staging
+    uint8_t* wbase = smem + q * 4096;                                   // 32 rows x 128 B per warp
+    long long* rowinfo = reinterpret_cast<long long*>(smem + 16384);    // element offset of every tile row, -1 = none
+    {
+      bool row_ok;
+      long long row_off;
+      if (MODE == 0 && prog.spatial) {
+        const int tw = r % prog.TW;
+        const int th = (r / prog.TW) % prog.TH;
+        const int tn = r / (prog.TW * prog.TH);
+        const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
+        row_ok = n < prog.n_img && h < prog.h_out && w < prog.w_out;
+        row_off = n * epi.sN + h * epi.sH + w * epi.sW;
+      } else {
+        row_ok = (m0 + r) < prog.M;
+        row_off = (long long)(m0 + r) * epi.ld;
+      }
+      rowinfo[r] = row_ok ? row_off : -1;
     }
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
-                          reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0 &&
-                        (row_off & 3) == 0 && !epi.accumulate;
+    __syncwarp();  // each warp only ever reads the rowinfo entries of its own 32 rows
+    const bool ptr_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
+                          reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0 && !epi.accumulate;
+    const int cc = lane & 7;     // 16-byte column chunk handled by this lane after the transpose
+    const int rsub = lane >> 3;  // row within each group of 4
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= prog.N) break;  // warp-uniform
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
-      if (!row_ok) continue;
-      const int col0 = n0 + c0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int col = col0 + j;
-        if (col >= prog.N) break;
-        float x[4];
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(wbase + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+            make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      __syncwarp();
+      const int col = n0 + c0 + 4 * cc;
+      float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (epi.bias) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) x[e] = epi.alpha * __uint_as_float(v[j + e]);
-        const bool full4 = (col + 3 < prog.N) && vec_ok && ((col & 3) == 0);
-        if (epi.bias) {
+        for (int e = 0; e < 4; ++e) if (col + e < prog.N) bias4[e] = __ldg(epi.bias + col + e);
+      }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) if (col + e < prog.N) x[e] += __ldg(epi.bias + col + e);
-        }
-        if (full4) {
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + rsub;
+        const long long row_off = rowinfo[q * 32 + rr];
+        if (row_off < 0 || col >= prog.N) continue;
+        const float4 a = *reinterpret_cast<const float4*>(wbase + rr * 128 + ((cc ^ (rr & 7)) << 4));
+        float x[4] = {epi.alpha * a.x + bias4[0], epi.alpha * a.y + bias4[1], epi.alpha * a.z + bias4[2],
+                      epi.alpha * a.w + bias4[3]};
+        if ((col + 3 < prog.N) && ptr_ok && ((row_off & 3) == 0)) {
           if (epi.addend) {
             const float4 a4 = *reinterpret_cast<const float4*>(epi.addend + row_off + col);
             x[0] += a4.x; x[1] += a4.y; x[2] += a4.z; x[3] += a4.w;
@@ -369,6 +384,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
           }
         }
       }
+      __syncwarp();  // staging is overwritten by the next chunk
     }
   }
   tc_fence_before();

@@ -44,8 +44,8 @@ class _Unit(object):
         self.w, self.gamma, self.mean = w, gamma, mean
         self.O, self.I = w.shape[0], w.shape[1]
         self.k, self.stride, self.stem = ksize, stride, stem
-        self.Ip = 32 if stem else self.I
-        self.slots = 16 if stem else ksize * ksize
+        self.Ip = 64 if stem else self.I
+        self.slots = 4 if stem else ksize * ksize
         # weights are folded AND pre-split into tf32 hi / lo parts (3xTF32 with the A operand in tensor memory)
         self.wf, self.wf_lo = _empty(self.O, self.slots * self.Ip), _empty(self.O, self.slots * self.Ip)
         self.wft = self.wft_lo = None
@@ -56,9 +56,7 @@ class _Unit(object):
              ksize, ksize, self.Ip, int(stem), ptr(self.wf), ptr(self.wf_lo), ptr(self.wft), ptr(self.wft_lo),
              ptr(self.shift), ptr(self.scale), ptr(self.rstd), stream_ptr())
         if stem:
-            dh = [a for a in range(-2, 2) for _ in range(4)]
-            dw = [b for _ in range(4) for b in range(-2, 2)]
-            self.taps = (dh, dw, [0] * 16, list(range(16)))
+            self.taps = ([-2, -1, 0, 1], [0, 0, 0, 0], [0] * 4, list(range(4)))
             self.in_step = 1
         else:
             dh, dw, phase, slot, step = dense.fprop_taps(ksize, stride, ksize // 2)
@@ -135,7 +133,7 @@ class _EncoderFn(torch.autograd.Function):
             w, gamma, beta, mean, var = [p.detach().contiguous() for p in params[5 * i:5 * i + 5]]
             units.append(_Unit(w, gamma, beta, mean, var, k, s, stem=(i == 0)))
         st = stream_ptr()
-        xs = _empty(B, H // 2, W // 2, 32)
+        xs = _empty(B, H // 2, W // 2, 64)
         call("obman_stem_pack", ptr(images), B, H, W, ptr(xs), st)
         c1 = units[0].fprop(xs, H // 2, W // 2, relu=True, passes=pf)
         if DEBUG is not None:

@@ -38,11 +38,13 @@ class FlatAdamTrainer(object):
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
         self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad_views = []
         for (_, p), off in zip(params, offsets):
             n = p.numel()
             self.flat_p[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + n].view_as(p)
-            p.grad = self.flat_g[off:off + n].view_as(p)
+            self.grad_views.append(self.flat_g[off:off + n].view_as(p))
+            p.grad = self.grad_views[-1]
         self.params = [p for _, p in params]
         self.numel = total
         self.param_numel = sum(p.numel() for _, p in params)
@@ -55,11 +57,24 @@ class FlatAdamTrainer(object):
 
     def step(self, sample):
         """Returns the (device) total loss of this rank's shard."""
-        self.zero_grad()
+        # Gradients are produced by autograd as fresh tensors (p.grad = None, so AccumulateGrad adopts them without
+        # an add kernel per parameter) and gathered into the flat buffer with one fused multi-tensor copy.
+        for p in self.params:
+            p.grad = None
         loss, _, _ = self.model.forward(sample)
         loss.backward()
+        self.gather_grads()
         self.reduce_and_update()
         return loss
+
+    def gather_grads(self):
+        have = [(v, p.grad) for v, p in zip(self.grad_views, self.params) if p.grad is not None]
+        missing = [v for v, p in zip(self.grad_views, self.params) if p.grad is None]
+        if missing:
+            torch._foreach_zero_(missing)
+        torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        for v, p in zip(self.grad_views, self.params):
+            p.grad = v
 
     def all_reduce_grads(self):
         """The only data-path collective of the step: one sum all-reduce of the flat gradient buffer."""

@@ -30,10 +30,12 @@ def _worker(rank, world, port, out):
     assert all((p.data_ptr() - base) % 256 == 0 for p in trainer.params)  # CUDA allocations are 512-B aligned
     g = torch.Generator().manual_seed(100 + rank)  # different shard per rank
     x, y = torch.randn(5, 7, generator=g), torch.randn(5, 3, generator=g)
-    trainer.zero_grad()
+    for p in trainer.params:
+        p.grad = None
     loss = ((model(x) - y) ** 2).mean()
     loss.backward()
-    assert trainer.grads_are_views()  # autograd accumulated in place
+    trainer.gather_grads()
+    assert trainer.grads_are_views()  # gradients live in the flat buffer
     local = trainer.flat_g.clone()
     trainer.all_reduce_grads()
     gathered = [torch.zeros_like(local) for _ in range(world)]

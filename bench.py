@@ -186,6 +186,37 @@ def workload_config(n_gpus):
 # ---------------------------------------------------------------------------------------------------------
 # CUDA arm
 # ---------------------------------------------------------------------------------------------------------
+def chamfer_report(peaks):
+    """Second half of BASELINE.json's metric ("Chamfer kernel HBM GB/s vs peak"): the fused nearest-neighbour
+    kernel at the workload's own shapes and at a large sweep point, on algorithmic bytes (20 B per point: 12 read,
+    8 written).  The fused kernel does 200-3300 flop per algorithmic byte, so its bound is the FP32 issue rate
+    (reported as well); the full sweep is profiles/chamfer_sweep_r1.json (scripts/bench_chamfer.py)."""
+    from obman_train_b200 import functional as Fb
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    issue_peak = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6
+    out = {"unit": "GB/s on algorithmic bytes", "hbm_peak_gbs": hbm}
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for tag, (b, n, m, reps) in {"workload": (PER_GPU_BATCH, 642 if N_GT == 600 else 2562, N_GT, 50),
+                                 "sweep_2048x10000": (2048, 10000, 10000, 2)}.items():
+        x = torch.randn(b, n, 3, device="cuda", generator=g) * 60
+        y = torch.randn(b, m, 3, device="cuda", generator=g) * 60
+        for _ in range(3):
+            Fb.nearest_neighbours(x, y)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            Fb.nearest_neighbours(x, y)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = 20.0 * b * (n + m) / ms / 1e6
+        out[tag] = {"B": b, "N": n, "M": m, "ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm,
+                    "pairs_per_s": 2.0 * b * n * m / ms * 1e3,
+                    "frac_of_fp32_issue_peak": 2.0 * b * n * m * 7.3 / (ms * 1e-3) / issue_peak}
+        del x, y
+    return out
+
+
 def run_b200(args):
     import torch.distributed as dist
     from obman_train_b200 import _lib, dense
@@ -321,6 +352,7 @@ def run_b200(args):
                      "gemm_ms_per_step": prof["ms_per_step"], "gemm_launches_per_step": prof["launches_per_step"],
                      "share_of_step": prof["ms_per_step"] / (ms / args.steps), "traffic": None},
     }
+    line["chamfer"] = chamfer_report(peaks)
     if not args.no_cpu_baseline:
         sec, threads = cpu_reference_steps(8, 2, 1)
         line["cpu_baseline"] = {"value": 8 / sec, "unit": "images/s", "cores": threads, "kind": "port",

@@ -45,7 +45,7 @@ def mesh_exterior(points, triangles, return_margin=False):
     threshold, so that tests can skip numerically degenerate rays.
     """
     dt = points.dtype
-    d = torch.tensor(RAY_DIRECTION, dtype=dt)
+    d = torch.tensor(RAY_DIRECTION, dtype=dt, device=points.device)
     v0 = triangles[:, :, 0]
     e1 = triangles[:, :, 1] - v0
     e2 = triangles[:, :, 2] - v0
@@ -80,7 +80,7 @@ def masked_mean(vals, mask):
     n = maskf.sum()
     if n > 0:
         return (maskf * vals).sum() / n
-    return torch.zeros(1, dtype=vals.dtype)
+    return torch.zeros(1, dtype=vals.dtype, device=vals.device)
 
 
 def contact_loss(hand, obj, obj_faces, zones=None, contact_thresh=5, contact_mode="dist_sq",

@@ -59,7 +59,7 @@ def mano_forward(tables, pose_coeffs, betas=None, trans=None, root_palm=False,
         hand = hand @ sel
     full_pose = torch.cat([pose_coeffs[:, :3], T["th_hands_mean"] + hand], dim=1)  # (B,48)
     rots = rodrigues(full_pose.reshape(-1, 3)).view(B, 16, 3, 3)
-    eye = torch.eye(3, dtype=dt)
+    eye = torch.eye(3, dtype=dt, device=pose_coeffs.device)
     pose_map = (rots[:, 1:] - eye).reshape(B, 135)
 
     if betas is None or betas.numel() == 1:

@@ -111,7 +111,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   int m0 = 0, n_img0 = 0, h0 = 0, w0 = 0;
   int n0 = blockIdx.y * BN;
   int pb_begin = 0;
-  if (MODE == 1) {
+  if (MODE >= 1) {
     m0 = (blockIdx.x / prog.n_tiles) * BM;
     n0 = (blockIdx.x % prog.n_tiles) * BN;
     const int total = prog.kblocks_n * prog.kblocks_h * prog.kblocks_w;
@@ -158,9 +158,11 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   // TS: TMEM columns of stage s: [BN + 64 s, +32) = A hi, next 32 = A lo
   auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(BN + 64 * s); };
 
-  // MODE 1: number of 32-column groups of this tile that exist
+  // MODE 1: number of 32-column groups of this tile that exist (B = stacked input taps).
+  // MODE 2 (roles swapped: A = stacked input taps, B = dY channels): number of 32-row groups that exist.
   int valid_groups = BN / 32;
   if (MODE == 1) valid_groups = min(BN / 32, prog.total_groups - n0 / 32);
+  if (MODE == 2) valid_groups = min(BM / 32, prog.total_groups - m0 / 32);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -171,6 +173,21 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(&empty[s], ph ^ 1);
+        if (MODE == 2) {
+          mbar_arrive_expect_tx(&full[s], 4096 * valid_groups + B_TILE_BYTES);
+          int pb = pb_begin + it;
+          const int bw = pb % prog.kblocks_w; pb /= prog.kblocks_w;
+          const int bh = pb % prog.kblocks_h; pb /= prog.kblocks_h;
+          const int pw = bw * prog.kTW, ph_ = bh * prog.kTH, pn = pb * prog.kTN;
+          for (int j = 0; j < valid_groups; ++j) {
+            const int g = m0 / 32 + j;
+            const int tap = g / prog.cg_in, cg = g - tap * prog.cg_in;
+            tma_load_5d(stage_a(s) + j * 4096, &maps.a[1 + prog.tap_map[tap]], &full[s], 0, pw + prog.tap_dw[tap],
+                        ph_ + prog.tap_dh[tap], pn, cg);
+          }
+          tma_load_5d(stage_b(s), &maps.a[0], &full[s], 0, pw, ph_, pn, n0 / 32);
+          continue;
+        }
         if (MODE == 1) {
           mbar_arrive_expect_tx(&full[s], A_TILE_BYTES + 4096 * valid_groups);
           int pb = pb_begin + it;
@@ -201,14 +218,14 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = umma_idesc_tf32(BM, BN, MODE, MODE);
+    const uint32_t idesc = umma_idesc_tf32(BM, BN, MODE != 0, MODE != 0);
     // K-major: 4 k-steps of 32 bytes inside the 128-byte row (SW128, 8-row groups 1024 B apart).
     // MN-major (TF32 => SW128 with 32-byte atoms): 4 k-steps of 8 pixel rows (1024 B), 4-row K atoms 512 B
     // apart (SBO), 32-channel groups 4096 B apart (LBO)
-    constexpr uint32_t KSTEP = MODE == 1 ? 1024 : 32;
-    const uint32_t LBO = MODE == 1 ? prog.mn_lbo : 16;
-    const uint32_t SBO = MODE == 1 ? prog.mn_sbo : 1024;
-    const uint32_t LT = MODE == 1 ? prog.mn_layout : 2;
+    constexpr uint32_t KSTEP = MODE != 0 ? 1024 : 32;
+    const uint32_t LBO = MODE != 0 ? prog.mn_lbo : 16;
+    const uint32_t SBO = MODE != 0 ? prog.mn_sbo : 1024;
+    const uint32_t LT = MODE != 0 ? prog.mn_layout : 2;
     for (int it = 0; it < n_iters; ++it) {
       const int s = it % S;
       const uint32_t ph = (it / S) & 1;
@@ -276,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         mbar_arrive(&conv[s]);
       }
     } else if (PASSES == 3) {
-      constexpr int A_V4 = A_TILE_BYTES / 16;
+      const int a_v4 = (MODE == 2 ? valid_groups * 4096 : A_TILE_BYTES) / 16;
       const int b_v4 = (MODE == 1 ? valid_groups * 4096 : B_TILE_BYTES) / 16;
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % S;
@@ -287,9 +304,9 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         float4* b = reinterpret_cast<float4*>(stage_b(s));
         float4* blo = reinterpret_cast<float4*>(stage_blo(s));
 #pragma unroll 4
-        for (int i = tid; i < A_V4 + b_v4; i += 128) {
-          float4* src = i < A_V4 ? a + i : b + (i - A_V4);
-          float4* dst = i < A_V4 ? alo + i : blo + (i - A_V4);
+        for (int i = tid; i < a_v4 + b_v4; i += 128) {
+          float4* src = i < a_v4 ? a + i : b + (i - a_v4);
+          float4* dst = i < a_v4 ? alo + i : blo + (i - a_v4);
           // The tensor core TRUNCATES fp32 operands to tf32 (measured: scripts/probe_dense.py rounding_mode),
           // so the raw tile already acts as `hi`; only lo = v - trunc(v) has to be written.
           const float4 v = *src;
@@ -307,6 +324,28 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
     // instruction touches 4 rows x 128 contiguous bytes (the row-per-lane layout would touch 32 rows x 16 bytes).
     mbar_wait(accum, 0);
     tc_fence_after();
+    if (MODE == 2) {
+      // D[m, n] with m = stacked (tap, c_in) index and n = output channel; dw is (c_out, taps*c_in) row-major, so
+      // element (m, n) lives at n*ld + m: the 32 lanes of a warp (consecutive m) make every column one coalesced access.
+      const bool row_ok = (m0 + r) < prog.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= prog.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + c0 + j;
+          if (col >= prog.N) break;
+          float* dst = epi.out + (long long)col * epi.ld + (m0 + r);
+          const float y = epi.alpha * __uint_as_float(v[j]);
+          if (epi.accumulate) atomicAdd(dst, y);
+          else *dst = y;
+        }
+      }
+    } else {
     // all MMAs (and therefore all TMA loads and operand reads) have retired: stage 0 is free for staging
     uint8_t* wbase = smem + q * 4096;                                   // 32 rows x 128 B per warp
     long long* rowinfo = reinterpret_cast<long long*>(smem + 16384);    // element offset of every tile row, -1 = none
@@ -386,6 +425,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
       }
       __syncwarp();  // staging is overwritten by the next chunk
     }
+    }  // MODE != 2
   }
   tc_fence_before();
   __syncthreads();
@@ -425,6 +465,9 @@ static int dispatch_gemm(int BN, int passes, int ts, const GemmMaps& maps, const
       if (bn <= 128 && occ2) return launch_gemm<bn, 3, 0, 1, (bn <= 128 ? 2 : 1)>(maps, prog, epi, grid, st); \
       return launch_gemm<bn, 3, 0, 1, 1>(maps, prog, epi, grid, st);                                \
     }                                                                                               \
+    if (MODE == 2 && bn == 64)                                                                      \
+      return passes == 3 ? launch_gemm<bn, 3, MODE, 0, (bn == 64 ? 2 : 1)>(maps, prog, epi, grid, st) \
+                         : launch_gemm<bn, 1, MODE, 0, (bn == 64 ? 2 : 1)>(maps, prog, epi, grid, st); \
     return passes == 3 ? launch_gemm<bn, 3, MODE, 0, 1>(maps, prog, epi, grid, st)                  \
                        : launch_gemm<bn, 1, MODE, 0, 1>(maps, prog, epi, grid, st);                 \
   }
@@ -642,15 +685,26 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
   prog.kblocks_n = (n_img + kTN - 1) / kTN;
   prog.kblocks_h = (h_out + kTH - 1) / kTH;
   prog.kblocks_w = (w_out + kTW - 1) / kTW;
-  const int m_tiles = (c_out + BM - 1) / BM;
-  const int BN = prog.N > 128 ? 256 : (prog.N > 64 ? 128 : 64);
+  // c_out <= 64 would leave half of the 128 accumulator rows empty: swap the roles (rows = stacked taps x c_in,
+  // columns = output channels) so that the tile is full; dw is then written transposed by the epilogue.
+  const bool swapped = c_out <= 64;
+  const int n_total = prog.N;
+  int m_tiles = (c_out + BM - 1) / BM;
+  int BN = prog.N > 128 ? 256 : (prog.N > 64 ? 128 : 64);
   prog.n_tiles = (prog.N + BN - 1) / BN;
+  if (swapped) {
+    prog.M = n_total;
+    prog.N = c_out;
+    m_tiles = (n_total + BM - 1) / BM;
+    BN = 64;
+    prog.n_tiles = 1;
+  }
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
   {
     uint64_t dims[5] = {32, (uint64_t)w_out, (uint64_t)h_out, (uint64_t)n_img, (uint64_t)(c_out / 32)};
     uint64_t strides[4] = {(uint64_t)c_out * 4, (uint64_t)w_out * c_out * 4, (uint64_t)h_out * w_out * c_out * 4, 128};
-    uint32_t box[5] = {32, (uint32_t)kTW, (uint32_t)kTH, (uint32_t)kTN, 4};
+    uint32_t box[5] = {32, (uint32_t)kTW, (uint32_t)kTH, (uint32_t)kTN, swapped ? (uint32_t)(BN / 32) : 4u};
     int rc = make_tensor_map(&maps.a[0], dy, 5, dims, strides, box, mn_swizzle);
     if (rc) return rc;
   }
@@ -677,12 +731,13 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
   const long long total_blocks = (long long)prog.kblocks_n * prog.kblocks_h * prog.kblocks_w;
   const long long tiles = (long long)m_tiles * prog.n_tiles;
   // split the pixel reduction so that tiles * splits is a whole number of waves (one CTA per SM)
-  const long long waves = (tiles + num_sms() - 1) / num_sms();
-  long long splits = (waves * num_sms()) / tiles;
+  const long long slots = (long long)num_sms() * (swapped ? 2 : 1);  // the swapped configuration runs 2 CTAs / SM
+  const long long waves = (tiles + slots - 1) / slots;
+  long long splits = (waves * slots) / tiles;
   if (splits > total_blocks / 4) splits = total_blocks / 4;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
-  const long long ld = (long long)prog.N;
+  const long long ld = (long long)n_total;
   if (splits > 1) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)c_out * ld, st);
   GemmEpilogue epi;
   memset(&epi, 0, sizeof(epi));
@@ -691,6 +746,7 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
   epi.accumulate = splits > 1;
   epi.ld = ld;
   dim3 grid((unsigned)(m_tiles * prog.n_tiles), 1, (unsigned)splits);
+  if (swapped) return dispatch_gemm<2>(BN, passes, 0, maps, prog, epi, grid, st);
   return dispatch_gemm<1>(BN, passes, 0, maps, prog, epi, grid, st);
 }
 

@@ -23,6 +23,10 @@ extern "C" {
 #define OBMAN_ERR_UNSUPPORTED -3
 #define OBMAN_ERR_DRIVER -4
 
+#define OBMAN_PREC_TF32 1
+#define OBMAN_PREC_3XBF16 2
+#define OBMAN_PREC_3XTF32 3
+
 int obman_version(void);
 const char* obman_get_last_error(void);
 /* 0 when the current device is a Blackwell sm_10x part. */
@@ -92,8 +96,10 @@ int obman_mano_bwd(const float* v_template, const float* shapedirs, const float*
                    const float* gjoints, float* ws_gv, float* ws_gtw, float* ws_gacc, float* gpose,
                    float* gbetas, void* stream);
 
-/* ---- Dense contractions on tcgen05 tensor cores (TF32 inputs, FP32 accumulation in TMEM, TMA feeds) ------
- * passes = 1: plain TF32; passes = 3: 3xTF32 split (hi*hi + lo*hi + hi*lo), fp32-equivalent accuracy.
+/* ---- Dense contractions on tcgen05 tensor cores (FP32 accumulation in TMEM, TMA feeds) ------------------
+ * passes = 1: plain TF32; passes = 3: 3xTF32 split (hi*hi + lo*hi + hi*lo), fp32-equivalent accuracy;
+ * passes = 2 (OBMAN_PREC_3XBF16): fp32 operands split into bf16 hi + bf16 lo (16 significant bits), the same
+ * three products at the bf16 rate; W / w must then be in the packed layout of obman_pack_bf16 and W_lo NULL.
  *
  * obman_gemm: out[M,N] = epilogue(alpha * A[M,K] * W[N,K]^T); replaces nn.Linear / Conv1d(k=1) calls
  * (manobranch.py:124-147, atlasbranch.py:44-61, atlasutils.py:65-75).  Row-major, leading dimensions in
@@ -106,6 +112,10 @@ int obman_gemm(const float* A, long long lda, const float* W, const float* W_lo,
 /* hi = tf32-rounded w, lo = w - hi (n floats): weights pre-split for the 3xTF32 path whose A operand is
  * staged in tensor memory (pass them as W / W_lo, w / w_lo). */
 int obman_split_tf32(const float* w, long long n, float* hi, float* lo, void* stream);
+/* Packed weights of the 3xBF16 path: out (rows, ld_out), ld_out = K rounded up to 32; every 32-element block of
+ * a row holds 32 bf16 hi values then 32 bf16 lo = bf16(w - hi) values (the bytes of 32 floats); zero padded. */
+int obman_pack_bf16(const float* w, long long ldw, int rows, int K, float* out, long long ld_out,
+                    void* stream);
 
 /* obman_conv_nhwc: NHWC convolution as implicit GEMM; forward and data-gradient of nn.Conv2d
  * (mano_train/networks/bases/resnet.py:19-23,38-54,110-152) share it.  x (n_img,h_in,w_in,c_in),
@@ -135,12 +145,14 @@ int obman_stem_pack(const float* x, int B, int H, int W, float* out, void* strea
 /* BatchNorm(eval) folding + weight re-layout, once per step.  w (O,I,KH,KW); gamma/beta/mean/var (O) or NULL
  * (no BN), cbias (O) conv bias or NULL: shift = beta + (cbias - mean)*scale (no BN: shift = cbias).
  * wf_lo / wft_lo (NULL or): pre-split mode, wf/wft = tf32-rounded value, *_lo = residual.
+ * packed = 1: wf / wft in the obman_pack_bf16 layout instead (Ip % 32 == 0, *_lo NULL; wft rows are
+ * KH*KW*Op long, Op = O rounded up to 32, padding zeroed by the caller).
  * wf (O, KH*KW*Ip) fprop operand, wft (I, KH*KW*O) dgrad operand
  * (NULL to skip), shift/scale/rstd (O).  stem=1: (O,3,7,7) filter -> (O, 4*64) layout of obman_stem_pack. */
 int obman_fold_conv(const float* w, const float* cbias, const float* gamma, const float* beta, const float* mean,
                     const float* var, float eps, int O, int I, int KH, int KW, int Ip, int stem,
-                    float* wf, float* wf_lo, float* wft, float* wft_lo, float* shift, float* scale,
-                    float* rstd, void* stream);
+                    int packed, float* wf, float* wf_lo, float* wft, float* wft_lo, float* shift,
+                    float* scale, float* rstd, void* stream);
 /* MaxPool2d(3, stride 2, pad 1), NHWC (resnet.py:107): idx (B,H/2,W/2,C) u8 = arg-max window slot. */
 int obman_maxpool_fwd(const float* x, int B, int H, int W, int C, float* out, unsigned char* idx,
                       void* stream);

@@ -9,6 +9,9 @@
 #define OBMAN_ERR_CUDA -2
 #define OBMAN_ERR_UNSUPPORTED -3
 #define OBMAN_ERR_DRIVER -4
+#define OBMAN_PREC_TF32 1
+#define OBMAN_PREC_3XBF16 2
+#define OBMAN_PREC_3XTF32 3
 
 namespace obman {
 

@@ -9,6 +9,8 @@
 //   colsum           per-channel sums of a (rows, C) tensor (BatchNorm beta / bias gradients)
 //   bn_wgrad_finish  raw weight gradient -> gradients of conv weight (OIHW), gamma, beta
 //   adam             fused Adam step on a flat parameter buffer (torch.optim.Adam semantics, traineval.py:113-116)
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace obman {
@@ -55,12 +57,24 @@ stem_pack_kernel(const float* __restrict__ x, int B, int H, int W, float* __rest
 //   wft[i][(kh*KW+kw)*O  + o] = s[o]*w[o,i,kh,kw]        (dgrad B operand), i < I only
 //   shift[o] = beta + (conv_bias - mean)*s ; scale[o] = s ; rstd[o]
 // stem == 1: w is the (64,3,7,7) stem filter, written in the 4-tap x 64-channel layout of stem_pack_kernel.
+// packed == 1 (3xBF16 path): wf / wft hold, per 32-element block of a row, 32 bf16 `hi` values followed by the
+// 32 bf16 `lo` = bf16(v - hi) values (same bytes per row as fp32); wft rows are taps * Op long, Op = O rounded up
+// to 32 (the caller zero-fills the padding).
+__device__ __forceinline__ void store_packed_bf16(float* row, size_t k, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  __nv_bfloat16* r16 = reinterpret_cast<__nv_bfloat16*>(row);
+  const size_t blk = k >> 5, in = k & 31;
+  r16[blk * 64 + in] = h;
+  r16[blk * 64 + 32 + in] = l;
+}
+
 __global__ void __launch_bounds__(256)
 fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
                  const float* __restrict__ gamma,
                  const float* __restrict__ beta, const float* __restrict__ mean,
                  const float* __restrict__ var, float eps, int O, int I, int KH, int KW, int Ip,
-                 int stem, float* __restrict__ wf, float* __restrict__ wf_lo, float* __restrict__ wft,
+                 int stem, int packed, float* __restrict__ wf, float* __restrict__ wf_lo, float* __restrict__ wft,
                  float* __restrict__ wft_lo, float* __restrict__ shift, float* __restrict__ scale,
                  float* __restrict__ rstd_out) {
   const int o = blockIdx.x;
@@ -86,6 +100,7 @@ fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
         const int kh = 2 * a + ph + 3, kw = 2 * (q - 2) + pw + 3;
         if (kh >= 0 && kh < 7 && kw >= 0 && kw < 7) v = s * w[((o * 3 + c) * 7 + kh) * 7 + kw];
       }
+      if (packed) { store_packed_bf16(wf + (size_t)o * 256, k, v); continue; }
       const float h = to_tf32_rna_dev(v);
       wf[(size_t)o * 256 + k] = wf_lo ? h : v;
       if (wf_lo) wf_lo[(size_t)o * 256 + k] = v - h;
@@ -93,10 +108,16 @@ fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
     return;
   }
   const int taps = KH * KW;
+  const int Op = (O + 31) / 32 * 32;
   for (int k = threadIdx.x; k < taps * Ip; k += blockDim.x) {
     const int t = k / Ip, i = k - t * Ip;
     float v = 0.f;
     if (i < I) v = s * w[((size_t)o * I + i) * taps + t];
+    if (packed) {
+      store_packed_bf16(wf + (size_t)o * taps * Ip, k, v);
+      if (i < I && wft) store_packed_bf16(wft + (size_t)i * taps * Op, (size_t)t * Op + o, v);
+      continue;
+    }
     const float h = to_tf32_rna_dev(v);
     if (i < I && wft) {
       const size_t ot = (size_t)i * taps * O + (size_t)t * O + o;
@@ -373,14 +394,16 @@ extern "C" int obman_stem_pack(const float* x, int B, int H, int W, float* out, 
 
 extern "C" int obman_fold_conv(const float* w, const float* cbias, const float* gamma, const float* beta, const float* mean,
                                const float* var, float eps, int O, int I, int KH, int KW, int Ip, int stem,
-                               float* wf, float* wf_lo, float* wft, float* wft_lo, float* shift, float* scale,
-                               float* rstd, void* stream) {
+                               int packed, float* wf, float* wf_lo, float* wft, float* wft_lo, float* shift,
+                               float* scale, float* rstd, void* stream) {
   OBMAN_REQUIRE(w && wf && shift && scale && rstd && O > 0 && I > 0 && KH > 0 && KW > 0 && Ip >= I,
                 "obman_fold_conv: bad arguments");
   OBMAN_REQUIRE(!stem || (I == 3 && KH == 7 && KW == 7), "obman_fold_conv: stem layout needs a (O,3,7,7) filter");
   OBMAN_REQUIRE(!wft_lo || wft, "obman_fold_conv: wft_lo without wft");
+  OBMAN_REQUIRE(!packed || (Ip % 32 == 0 && !wf_lo && !wft_lo),
+                "obman_fold_conv: packed bf16 layout needs Ip %% 32 == 0 and no *_lo outputs");
   fold_conv_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(w, cbias, gamma, beta, mean, var, eps, O, I, KH, KW, Ip, stem,
-                                                        wf, wf_lo, wft, wft_lo, shift, scale, rstd);
+                                                        packed, wf, wf_lo, wft, wft_lo, shift, scale, rstd);
   return check_launch("fold_conv_kernel");
 }
 

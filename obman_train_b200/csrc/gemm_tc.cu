@@ -75,23 +75,32 @@ struct GemmEpilogue {
 template <int BN, int PASSES, int TS, int OCC>
 struct GemmCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES =
-      TS ? (A_TILE_BYTES + 2 * B_TILE_BYTES) : (A_TILE_BYTES + B_TILE_BYTES) * (PASSES == 3 ? 2 : 1);
+  // TS == 1: A_raw | B_hi | B_lo (tf32).  TS == 2: A_raw | B with bf16 hi|lo interleaved per 32-element block.
+  static constexpr int STAGE_BYTES = TS == 2 ? (A_TILE_BYTES + B_TILE_BYTES)
+                                     : TS    ? (A_TILE_BYTES + 2 * B_TILE_BYTES)
+                                             : (A_TILE_BYTES + B_TILE_BYTES) * (PASSES == 3 ? 2 : 1);
+  static constexpr int A_COLS = TS == 2 ? 32 : 64;   // TMEM columns per stage: A hi | A lo
   static constexpr int STAGES_RAW = ((OCC == 2 ? 104 : 200) * 1024) / STAGE_BYTES;
   static constexpr int STAGES_SMEM = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  // TS: every stage also owns 64 TMEM columns (A hi | A lo); 512 columns per SM in total
-  static constexpr int STAGES_TMEM = ((OCC == 2 ? 256 : 512) - BN) / 64;
+  // TS: every stage also owns A_COLS TMEM columns; 512 columns per SM in total
+  static constexpr int STAGES_TMEM = ((OCC == 2 ? 256 : 512) - BN) / A_COLS;
   static constexpr int STAGES = TS ? (STAGES_SMEM < STAGES_TMEM ? STAGES_SMEM : STAGES_TMEM) : STAGES_SMEM;
-  static constexpr int TMEM_NEED = TS ? BN + STAGES * 64 : BN;
+  static constexpr int TMEM_NEED = TS ? BN + STAGES * A_COLS : BN;
   static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, int PASSES, int MODE, int TS, int OCC>
+// CL > 1 (TS path only): thread-block cluster of CL CTAs along the M-tile axis.  They share the weight tile, so
+// each CTA fetches 1/CL of it and TMA-multicasts it to all of them: the kernels were L2->SM bandwidth bound
+// (~9 TB/s measured against ~42 B/clk/SM), the weight tile being 2/3 of the bytes of every K block.
+template <int BN, int PASSES, int MODE, int TS, int OCC, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, OCC)
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, const GemmEpilogue epi) {
   using Cfg = GemmCfg<BN, PASSES, TS, OCC>;
   static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(CL == 1 || (TS >= 1 && MODE == 0), "clusters are only used on the TS path");
+  constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1);
+  const uint32_t cl_rank = CL > 1 ? cluster_ctarank() : 0;
   constexpr int S = Cfg::STAGES;
   constexpr int B_TILE_BYTES = Cfg::B_TILE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -134,7 +143,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&conv[s], 128);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);   // every CTA of the cluster commits to every CTA's empty barriers
     }
     mbar_init(accum, 1);
     fence_barrier_init();
@@ -145,6 +154,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers' barriers must exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -155,8 +165,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   auto stage_blo = [&](int s) {
     return smem + s * Cfg::STAGE_BYTES + (TS ? A_TILE_BYTES + B_TILE_BYTES : 2 * A_TILE_BYTES + B_TILE_BYTES);
   };
-  // TS: TMEM columns of stage s: [BN + 64 s, +32) = A hi, next 32 = A lo
-  auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(BN + 64 * s); };
+  // TS: TMEM columns of stage s: [BN + A_COLS s, + A_COLS/2) = A hi, next A_COLS/2 = A lo
+  auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(BN + Cfg::A_COLS * s); };
 
   // MODE 1: number of 32-column groups of this tile that exist (B = stacked input taps).
   // MODE 2 (roles swapped: A = stacked input taps, B = dY channels): number of 32-row groups that exist.
@@ -203,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
           }
           continue;
         }
-        mbar_arrive_expect_tx(&full[s], A_TILE_BYTES + B_TILE_BYTES * (TS ? 2 : 1));
+        mbar_arrive_expect_tx(&full[s], A_TILE_BYTES + B_TILE_BYTES * (TS == 1 ? 2 : 1));
         const int tap = it / prog.kblocks;
         const int kb = it - tap * prog.kblocks;
         if (prog.spatial) {
@@ -212,13 +222,22 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         } else {
           tma_load_2d(stage_a(s), &maps.a[0], &full[s], kb * BK, m0);
         }
-        tma_load_2d(stage_b(s), &maps.b, &full[s], prog.tap_bk[tap] + kb * BK, n0);
-        if (TS) tma_load_2d(stage_blo(s), &maps.b_lo, &full[s], prog.tap_bk[tap] + kb * BK, n0);
+        if (CL > 1) {
+          // this CTA's 1/CL slice of the weight tile, multicast to the whole cluster
+          constexpr int ROWS = BN / CL;
+          const int kc = prog.tap_bk[tap] + kb * BK;
+          tma_load_2d_mc(stage_b(s) + cl_rank * ROWS * 128, &maps.b, &full[s], kc, n0 + cl_rank * ROWS, CL_MASK);
+          if (TS == 1)
+            tma_load_2d_mc(stage_blo(s) + cl_rank * ROWS * 128, &maps.b_lo, &full[s], kc, n0 + cl_rank * ROWS, CL_MASK);
+        } else {
+          tma_load_2d(stage_b(s), &maps.b, &full[s], prog.tap_bk[tap] + kb * BK, n0);
+          if (TS == 1) tma_load_2d(stage_blo(s), &maps.b_lo, &full[s], prog.tap_bk[tap] + kb * BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = umma_idesc_tf32(BM, BN, MODE != 0, MODE != 0);
+    const uint32_t idesc = TS == 2 ? umma_idesc_bf16(BM, BN) : umma_idesc_tf32(BM, BN, MODE != 0, MODE != 0);
     // K-major: 4 k-steps of 32 bytes inside the 128-byte row (SW128, 8-row groups 1024 B apart).
     // MN-major (TF32 => SW128 with 32-byte atoms): 4 k-steps of 8 pixel rows (1024 B), 4-row K atoms 512 B
     // apart (SBO), 32-channel groups 4096 B apart (LBO)
@@ -235,6 +254,18 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
       if (lane == 0) {
         const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_b(s));
         const uint32_t a_lo = smem_u32(stage_alo(s)), b_lo = smem_u32(stage_blo(s));
+        if (TS == 2) {
+          // bf16 hi|lo: every 128-byte B row holds 32 hi then 32 lo values of this K block; K = 16 per MMA
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint64_t db = umma_desc(b_hi + k * 32, 16, 1024, 2);
+            const uint64_t dbl = umma_desc(b_hi + 64 + k * 32, 16, 1024, 2);
+            const uint32_t ta_hi = tmem_a(s) + k * 8, ta_lo = tmem_a(s) + 16 + k * 8;
+            umma_f16_ts(tmem_base, ta_lo, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_f16_ts(tmem_base, ta_hi, dbl, idesc, 1u);
+            umma_f16_ts(tmem_base, ta_hi, db, idesc, 1u);
+          }
+        } else {
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
           const uint64_t db = umma_desc(b_hi + k * KSTEP, LBO, SBO, LT);
@@ -257,7 +288,9 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
             umma_tf32(tmem_base, da, db, idesc, acc0);
           }
         }
-        umma_commit(&empty[s]);
+        }
+        if (CL > 1) umma_commit_mc(&empty[s], CL_MASK);
+        else umma_commit(&empty[s]);
         if (it == n_iters - 1) umma_commit(accum);
       }
       __syncwarp();
@@ -275,6 +308,21 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         const uint32_t ph = (it / S) & 1;
         mbar_wait(&full[s], ph);
         const uint8_t* row = stage_a(s) + r * 128;
+        if (TS == 2) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
+            split_bf16x2(v.x, v.y, hi[2 * j], lo[2 * j]);
+            split_bf16x2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+          }
+          const uint32_t dst = lane_base + (uint32_t)(BN + Cfg::A_COLS * s);
+          tmem_st_32x16(dst, hi);
+          tmem_st_32x16(dst + 16, lo);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&conv[s]);
+        } else {
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -291,6 +339,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&conv[s]);
+        }
       }
     } else if (PASSES == 3) {
       const int a_v4 = (MODE == 2 ? valid_groups * 4096 : A_TILE_BYTES) / 16;
@@ -429,16 +478,17 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA may exit while peers can still multicast into it / arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, int PASSES, int MODE, int TS, int OCC>
+template <int BN, int PASSES, int MODE, int TS, int OCC, int CL = 1>
 static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const GemmEpilogue& epi, dim3 grid,
                        cudaStream_t st) {
   using Cfg = GemmCfg<BN, PASSES, TS, OCC>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, MODE, TS, OCC>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, MODE, TS, OCC, CL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute(%d bytes) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
@@ -446,8 +496,45 @@ static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const Gemm
     }
     attr = true;
   }
-  gemm_tc_kernel<BN, PASSES, MODE, TS, OCC><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
+  if (CL > 1) {
+    grid.x = (grid.x + CL - 1) / CL * CL;  // padded CTAs work on out-of-range tiles: TMA zero fill, rows masked
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = CL;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PASSES, MODE, TS, OCC, CL>, maps, prog, epi);
+    if (e != cudaSuccess) {
+      set_error("gemm_tc: cluster launch failed: %s", cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return OBMAN_ERR_CUDA;
+    }
+    return OBMAN_OK;
+  }
+  gemm_tc_kernel<BN, PASSES, MODE, TS, OCC, CL><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
   return check_launch("gemm_tc_kernel");
+}
+
+// Cluster size the TS path will run with for a grid of grid_x row tiles (the weight tensor maps are built with a
+// box of BN / cluster rows, so the host code asks before encoding them).
+static int cluster_for(long long grid_x) {
+  static int cl = -1;
+  if (cl < 0) {
+    const char* c = getenv("OBMAN_GEMM_CLUSTER");   // 1 (default), 2 or 4 CTAs share the weight tile by TMA multicast
+    cl = c ? atoi(c) : 1;   // measured: no gain on the 3xTF32 path (tensor-pipe bound), see DESIGN.md
+    if (cl != 1 && cl != 2 && cl != 4) cl = 1;
+  }
+  if (cl == 4 && grid_x >= 4) return 4;
+  if (cl >= 2 && grid_x >= 2) return 2;
+  return 1;
 }
 
 // ts: use the A-in-TMEM path (MODE 0, passes 3, pre-split weights)
@@ -459,10 +546,20 @@ static int dispatch_gemm(int BN, int passes, int ts, const GemmMaps& maps, const
     const char* e = getenv("OBMAN_GEMM_OCC");
     occ2 = (e && e[0] == '1') ? 0 : 1;
   }
+  const int cl = cluster_for(grid.x);
 #define OBMAN_GEMM_CASE(bn)                                                                         \
   if (BN == bn) {                                                                                   \
+    if (MODE == 0 && ts == 2) {                                                                     \
+      constexpr int occ = (bn <= 128 ? 2 : 1);                                                      \
+      if (cl == 4) return launch_gemm<bn, 3, 0, 2, occ, 4>(maps, prog, epi, grid, st);              \
+      if (cl == 2) return launch_gemm<bn, 3, 0, 2, occ, 2>(maps, prog, epi, grid, st);              \
+      return launch_gemm<bn, 3, 0, 2, occ>(maps, prog, epi, grid, st);                              \
+    }                                                                                               \
     if (MODE == 0 && ts && passes == 3) {                                                           \
-      if (bn <= 128 && occ2) return launch_gemm<bn, 3, 0, 1, (bn <= 128 ? 2 : 1)>(maps, prog, epi, grid, st); \
+      constexpr int occ = (bn <= 128 ? 2 : 1);                                                      \
+      if (cl == 4) return launch_gemm<bn, 3, 0, 1, occ, 4>(maps, prog, epi, grid, st);              \
+      if (cl == 2) return launch_gemm<bn, 3, 0, 1, occ, 2>(maps, prog, epi, grid, st);              \
+      if (bn <= 128 && occ2) return launch_gemm<bn, 3, 0, 1, occ>(maps, prog, epi, grid, st);       \
       return launch_gemm<bn, 3, 0, 1, 1>(maps, prog, epi, grid, st);                                \
     }                                                                                               \
     if (MODE == 2 && bn == 64)                                                                      \
@@ -519,7 +616,8 @@ extern "C" int obman_gemm(const float* A, long long lda, const float* W, const f
                           void* stream) {
   OBMAN_REQUIRE(A && W && out, "obman_gemm: null argument");
   OBMAN_REQUIRE(M > 0 && N > 0 && K > 0, "obman_gemm: bad sizes M=%d N=%d K=%d", M, N, K);
-  OBMAN_REQUIRE(passes == 1 || passes == 3, "obman_gemm: passes must be 1 (tf32) or 3 (3xtf32)");
+  OBMAN_REQUIRE(passes == 1 || passes == 3 || passes == OBMAN_PREC_3XBF16,
+                "obman_gemm: passes must be 1 (tf32), 3 (3xtf32) or 2 (3xbf16, packed weights)");
   OBMAN_REQUIRE(lda % 4 == 0 && ldw % 4 == 0, "obman_gemm: lda/ldw must be multiples of 4 floats (TMA 16-byte stride)");
   OBMAN_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)W_lo & 15) == 0,
                 "obman_gemm: A/W must be 16-byte aligned");
@@ -527,20 +625,24 @@ extern "C" int obman_gemm(const float* A, long long lda, const float* W, const f
   memset(&maps, 0, sizeof(maps));
   const long long m_tiles = (M + BM - 1) / BM;
   const int BN = pick_bn(N, m_tiles);
-  const int ts = (W_lo != nullptr) && passes == 3 && ts_enabled();
-  OBMAN_REQUIRE(W_lo == nullptr || passes == 1 || ts, "obman_gemm: pre-split weights need the TS path (OBMAN_GEMM_TS=0 set?)");
+  const bool bf = passes == OBMAN_PREC_3XBF16;
+  const int ts = bf ? 2 : ((W_lo != nullptr) && passes == 3 && ts_enabled());
+  OBMAN_REQUIRE(W_lo == nullptr || passes == 1 || ts == 1, "obman_gemm: pre-split weights need the TS path (OBMAN_GEMM_TS=0 set?)");
+  OBMAN_REQUIRE(!bf || (ldw % 32 == 0 && ldw >= (K + 31) / 32 * 32),
+                "obman_gemm: packed bf16 weights need ldw = K rounded up to 32 (see obman_pack_bf16)");
+  if (bf) passes = 3;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
     uint64_t strides[1] = {(uint64_t)lda * 4};
     uint32_t box[2] = {BK, BM};
     int rc = make_tensor_map(&maps.a[0], A, 2, dims, strides, box);
     if (rc) return rc;
-    uint64_t dimsb[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t dimsb[2] = {(uint64_t)(bf ? (K + 31) / 32 * 32 : K), (uint64_t)N};
     uint64_t stridesb[1] = {(uint64_t)ldw * 4};
-    uint32_t boxb[2] = {BK, (uint32_t)BN};
+    uint32_t boxb[2] = {BK, (uint32_t)(ts ? BN / cluster_for(m_tiles) : BN)};
     rc = make_tensor_map(&maps.b, W, 2, dimsb, stridesb, boxb);
     if (rc) return rc;
-    if (ts) {
+    if (ts == 1) {
       rc = make_tensor_map(&maps.b_lo, W_lo, 2, dimsb, stridesb, boxb);
       if (rc) return rc;
     }
@@ -581,7 +683,7 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
   OBMAN_REQUIRE(in_step == 1 || in_step == 2, "obman_conv_nhwc: in_step must be 1 or 2");
   OBMAN_REQUIRE(w_slots >= 1, "obman_conv_nhwc: w_slots must be >= 1");
   OBMAN_REQUIRE(in_step == 1 || (h_in % 2 == 0 && w_in % 2 == 0), "obman_conv_nhwc: phase views need even h_in/w_in");
-  OBMAN_REQUIRE(passes == 1 || passes == 3, "obman_conv_nhwc: passes must be 1 or 3");
+  OBMAN_REQUIRE(passes == 1 || passes == 3 || passes == OBMAN_PREC_3XBF16, "obman_conv_nhwc: passes must be 1, 2 or 3");
   OBMAN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)w_lo & 15) == 0,
                 "obman_conv_nhwc: x/w must be 16-byte aligned");
   // output tile shape: TW = largest power of two <= min(w_out, 128) ... keep TN*TH*TW == 128
@@ -602,8 +704,11 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
   prog.n_img = n_img; prog.h_out = h_out; prog.w_out = w_out;
   const long long m_tiles = (long long)((n_img + TN - 1) / TN) * prog.tiles_h * prog.tiles_w;
   const int BN = pick_bn(c_out, m_tiles);
-  const int ts = (w_lo != nullptr) && passes == 3 && ts_enabled();
-  OBMAN_REQUIRE(w_lo == nullptr || passes == 1 || ts, "obman_conv_nhwc: pre-split weights need the TS path");
+  const bool bf = passes == OBMAN_PREC_3XBF16;
+  const int ts = bf ? 2 : ((w_lo != nullptr) && passes == 3 && ts_enabled());
+  OBMAN_REQUIRE(w_lo == nullptr || passes == 1 || ts == 1, "obman_conv_nhwc: pre-split weights need the TS path");
+  OBMAN_REQUIRE(!bf || c_in % 32 == 0, "obman_conv_nhwc: packed bf16 weights need c_in %% 32 == 0 (c_in=%d)", c_in);
+  if (bf) passes = 3;
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
   bool used[4] = {false, false, false, false};
@@ -630,10 +735,10 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
   {
     uint64_t dimsb[2] = {(uint64_t)w_slots * (uint64_t)c_in, (uint64_t)c_out};
     uint64_t stridesb[1] = {dimsb[0] * 4};
-    uint32_t boxb[2] = {BK, (uint32_t)BN};
+    uint32_t boxb[2] = {BK, (uint32_t)(ts ? BN / cluster_for(m_tiles) : BN)};
     int rc = make_tensor_map(&maps.b, w, 2, dimsb, stridesb, boxb);
     if (rc) return rc;
-    if (ts) {
+    if (ts == 1) {
       rc = make_tensor_map(&maps.b_lo, w_lo, 2, dimsb, stridesb, boxb);
       if (rc) return rc;
     }
@@ -759,6 +864,36 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   const float h = obman::sm100::to_tf32_rna(v);
   hi[i] = h;
   lo[i] = v - h;
+}
+
+// out (rows, ld_out) <- w (rows, K; row stride ldw) in the packed layout of the 3xBF16 path: per 32-element block
+// of a row, 32 bf16 hi values then 32 bf16 lo = bf16(w - hi) values (128 bytes, the bytes of 32 floats); columns
+// K .. ld_out-1 are zero.  ld_out = K rounded up to 32.
+__global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict__ w, long long ldw, int rows, int K,
+                                                        uint32_t* __restrict__ out, long long ld_out) {
+  // one thread per PAIR of consecutive elements
+  const long long pairs_per_row = ld_out / 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pairs_per_row * rows) return;
+  const long long r = i / pairs_per_row;
+  const int k = (int)(i - r * pairs_per_row) * 2;
+  const float v0 = k < K ? w[r * ldw + k] : 0.f;
+  const float v1 = k + 1 < K ? w[r * ldw + k + 1] : 0.f;
+  uint32_t hi, lo;
+  obman::sm100::split_bf16x2(v0, v1, hi, lo);
+  const int blk = k >> 5, in = (k & 31) >> 1;
+  out[r * ld_out + blk * 32 + in] = hi;
+  out[r * ld_out + blk * 32 + 16 + in] = lo;
+}
+
+extern "C" int obman_pack_bf16(const float* w, long long ldw, int rows, int K, float* out, long long ld_out,
+                               void* stream) {
+  OBMAN_REQUIRE(w && out && rows > 0 && K > 0, "obman_pack_bf16: bad arguments");
+  OBMAN_REQUIRE(ld_out % 32 == 0 && ld_out >= K && ldw >= K, "obman_pack_bf16: ld_out must be a multiple of 32 >= K");
+  const long long n = ld_out / 2 * rows;
+  pack_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w, ldw, rows, K, reinterpret_cast<uint32_t*>(out), ld_out);
+  return check_launch("pack_bf16_kernel");
 }
 
 extern "C" int obman_split_tf32(const float* w, long long n, float* hi, float* lo, void* stream) {

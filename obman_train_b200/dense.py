@@ -8,15 +8,24 @@ import torch
 
 from ._lib import call, ptr, stream_ptr
 
-PASSES = {"tf32": 1, "tf32x3": 3}
-_precision = {"fwd": "tf32x3", "bwd": "tf32x3"}
+PASSES = {"tf32": 1, "bf16x3": 2, "tf32x3": 3}
+BF16X3 = 2
+_precision = {"fwd": "bf16x3", "bwd": "bf16x3", "wgrad": "tf32x3"}
 
 
-def set_precision(fwd="tf32x3", bwd="tf32x3"):
-    """'tf32x3' (3xTF32 split, fp32-equivalent; default) or 'tf32' (single pass) per direction."""
+def set_precision(fwd="bf16x3", bwd="bf16x3", wgrad=None):
+    """Per direction (fwd = fprop, bwd = data gradients, wgrad = weight gradients): 'bf16x3' (fp32 operands
+    split into bf16 hi + lo, three products at the bf16 rate, ~2^-17 relative error per product), 'tf32x3'
+    (3xTF32 split) or 'tf32' (single pass).  fwd and bwd share one weight layout: both or neither 'bf16x3'."""
     assert fwd in PASSES and bwd in PASSES
+    if (fwd == "bf16x3") != (bwd == "bf16x3"):
+        raise ValueError("set_precision: 'bf16x3' must be chosen for both fwd and bwd or for neither")
+    if wgrad is None:
+        wgrad = "tf32" if bwd == "tf32" else "tf32x3"
+    assert wgrad in ("tf32", "tf32x3")
     _precision["fwd"] = fwd
     _precision["bwd"] = bwd
+    _precision["wgrad"] = wgrad
 
 
 def get_precision():
@@ -77,15 +86,32 @@ def split_tf32(w):
     return hi, lo
 
 
+def r32(n):
+    return (int(n) + 31) // 32 * 32
+
+
+def pack_bf16(w, k=None):
+    """(rows, r32(K)) buffer holding w[:, :K] in the packed bf16 hi|lo layout of the 3xBF16 kernels."""
+    _chk(w, "w")
+    rows = w.shape[0]
+    K = w.shape[1] if k is None else k
+    out = torch.empty((rows, r32(K)), device=w.device, dtype=torch.float32)
+    call("obman_pack_bf16", ptr(w), w.stride(0), rows, K, ptr(out), out.stride(0), stream_ptr())
+    return out
+
+
 def gemm(a, w, out=None, bias=None, addend=None, mask_src=None, alpha=1.0, relu=False,
-         accumulate=False, passes=3, n=None, k=None, w_lo=None):
+         accumulate=False, passes=3, n=None, k=None, w_lo=None, packed=False):
     """out[M,N] = epilogue(alpha * a[M,:K] @ w[:N,:K]^T).  ``a`` / ``w`` may have padded leading
     dimensions (row stride multiple of 4 floats); ``n`` / ``k`` give the logical sizes.  ``w_lo``: residual
-    of pre-split weights (``w`` is then the tf32-rounded part), selects the A-in-TMEM kernel."""
+    of pre-split weights (``w`` is then the tf32-rounded part), selects the A-in-TMEM kernel.  With
+    passes == BF16X3 ``w`` must be (or, unless ``packed``, is converted here to) the pack_bf16 layout."""
     _chk(a, "a"); _chk(w, "w")
     M = a.shape[0]
     K = k if k is not None else a.shape[1]
     N = n if n is not None else w.shape[0]
+    if passes == BF16X3 and not packed:
+        w = pack_bf16(w, K)
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32)
     _tc_call(2.0 * M * N * K, "obman_gemm", ptr(a), a.stride(0), ptr(w), ptr(w_lo) if passes == 3 else None,

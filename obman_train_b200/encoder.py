@@ -40,21 +40,25 @@ def _empty(*shape):
 class _Unit(object):
     """Per-step folded weights of one conv+BN unit."""
 
-    def __init__(self, w, gamma, beta, mean, var, ksize, stride, stem=False, need_dgrad=True):
+    def __init__(self, w, gamma, beta, mean, var, ksize, stride, stem=False, need_dgrad=True, packed=False):
         self.w, self.gamma, self.mean = w, gamma, mean
         self.O, self.I = w.shape[0], w.shape[1]
         self.k, self.stride, self.stem = ksize, stride, stem
         self.Ip = 64 if stem else self.I
         self.slots = 4 if stem else ksize * ksize
-        # weights are folded AND pre-split into tf32 hi / lo parts (3xTF32 with the A operand in tensor memory)
-        self.wf, self.wf_lo = _empty(self.O, self.slots * self.Ip), _empty(self.O, self.slots * self.Ip)
+        # weights are folded AND pre-split for the A-in-tensor-memory kernels: packed bf16 hi|lo (3xBF16) or
+        # tf32 hi / lo arrays (3xTF32)
+        self.packed = packed
+        self.wf = _empty(self.O, self.slots * self.Ip)
+        self.wf_lo = None if packed else _empty(self.O, self.slots * self.Ip)
         self.wft = self.wft_lo = None
         if need_dgrad and not stem:
-            self.wft, self.wft_lo = _empty(self.I, self.slots * self.O), _empty(self.I, self.slots * self.O)
+            self.wft = _empty(self.I, self.slots * self.O)
+            self.wft_lo = None if packed else _empty(self.I, self.slots * self.O)
         self.shift, self.scale, self.rstd = _empty(self.O), _empty(self.O), _empty(self.O)
         call("obman_fold_conv", ptr(w), None, ptr(gamma), ptr(beta), ptr(mean), ptr(var), BN_EPS, self.O, self.I,
-             ksize, ksize, self.Ip, int(stem), ptr(self.wf), ptr(self.wf_lo), ptr(self.wft), ptr(self.wft_lo),
-             ptr(self.shift), ptr(self.scale), ptr(self.rstd), stream_ptr())
+             ksize, ksize, self.Ip, int(stem), int(packed), ptr(self.wf), ptr(self.wf_lo), ptr(self.wft),
+             ptr(self.wft_lo), ptr(self.shift), ptr(self.scale), ptr(self.rstd), stream_ptr())
         if stem:
             self.taps = ([-2, -1, 0, 1], [0, 0, 0, 0], [0] * 4, list(range(4)))
             self.in_step = 1
@@ -131,7 +135,7 @@ class _EncoderFn(torch.autograd.Function):
         units = []
         for i, (_, _, O, I, k, s) in enumerate(specs):
             w, gamma, beta, mean, var = [p.detach().contiguous() for p in params[5 * i:5 * i + 5]]
-            units.append(_Unit(w, gamma, beta, mean, var, k, s, stem=(i == 0)))
+            units.append(_Unit(w, gamma, beta, mean, var, k, s, stem=(i == 0), packed=(pf == dense.BF16X3)))
         st = stream_ptr()
         xs = _empty(B, H // 2, W // 2, 64)
         call("obman_stem_pack", ptr(images), B, H, W, ptr(xs), st)
@@ -142,6 +146,8 @@ class _EncoderFn(torch.autograd.Function):
         p = _empty(B, hp, wp, 64)
         pidx = torch.empty((B, hp, wp, 64), device="cuda", dtype=torch.uint8)
         call("obman_maxpool_fwd", ptr(c1), B, H // 2, W // 2, 64, ptr(p), ptr(pidx), st)
+        if DEBUG is not None:
+            DEBUG["pool_idx"] = pidx
         x, h, w_ = p, hp, wp
         blocks = []
         ui = 1
@@ -173,7 +179,8 @@ class _EncoderFn(torch.autograd.Function):
     def backward(ctx, gfeat):
         units, blocks = ctx.units, ctx.blocks
         xs, pidx, p, H, W = ctx.saved
-        pb = dense.PASSES[dense.get_precision()["bwd"]]
+        pb = dense.PASSES[dense.get_precision()["bwd"]]      # data gradients
+        pw = dense.PASSES[dense.get_precision()["wgrad"]]    # weight gradients
         st = stream_ptr()
         gfeat = gfeat.contiguous()
         B = gfeat.shape[0]
@@ -188,13 +195,13 @@ class _EncoderFn(torch.autograd.Function):
                 DEBUG["g_out_%d" % bidx] = g2.clone()
             rows = B * ho * wo
             gb2 = colsum(rows, u2.O, g2)
-            grads[id(u2)] = u2.finish(u2.wgrad(g2, a, pb), gb2)
+            grads[id(u2)] = u2.finish(u2.wgrad(g2, a, pw), gb2)
             g1 = u2.dgrad(g2, ho, wo, mask_src=a, passes=pb)
             if DEBUG is not None:
                 DEBUG["g_a_%d" % bidx] = g1.clone()
-            grads[id(u1)] = u1.finish(u1.wgrad(g1, x, pb), colsum(rows, u1.O, g1))
+            grads[id(u1)] = u1.finish(u1.wgrad(g1, x, pw), colsum(rows, u1.O, g1))
             if ud is not None:
-                grads[id(ud)] = ud.finish(ud.wgrad(g2, x, pb), gb2)
+                grads[id(ud)] = ud.finish(ud.wgrad(g2, x, pw), gb2)
                 gres = ud.dgrad(g2, h, w_, passes=pb)
             else:
                 gres = g2
@@ -206,7 +213,7 @@ class _EncoderFn(torch.autograd.Function):
             DEBUG["g_p"] = g2.clone()
             DEBUG["g_c1"] = gc1.clone()
         u0 = units[0]
-        grads[id(u0)] = u0.finish(u0.wgrad(gc1, xs, pb), colsum(B * (H // 2) * (W // 2), 64, gc1))
+        grads[id(u0)] = u0.finish(u0.wgrad(gc1, xs, pw), colsum(B * (H // 2) * (W // 2), 64, gc1))
         outs = [None]
         for u in units:
             gw, gg, gbt = grads[id(u)]

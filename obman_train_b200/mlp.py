@@ -61,6 +61,7 @@ class _LinearFn(torch.autograd.Function):
     def backward(ctx, g):
         x, w, y = ctx.saved_tensors
         pb = dense.PASSES[dense.get_precision()["bwd"]]
+        pw = dense.PASSES[dense.get_precision()["wgrad"]]
         N, K = w.shape
         if ctx.relu:
             g = g * (y > 0)
@@ -72,7 +73,7 @@ class _LinearFn(torch.autograd.Function):
             gx = dense.gemm(gp, wt, passes=pb, n=K, k=N)
         if ctx.needs_input_grad[1]:
             xk = _pad_cols(x, _r32(K))
-            gw = dense.wgrad_matrix(gp, xk, passes=pb)[:N, :K].contiguous()
+            gw = dense.wgrad_matrix(gp, xk, passes=pw)[:N, :K].contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = colsum(gp, N)
         return gx, gw, gb, None
@@ -85,23 +86,37 @@ def linear(x, weight, bias=None, relu=False):
 class _Layer(object):
     """Folded 1x1-conv (+BN eval) layer of the point decoder: y = relu?(x Wf^T + shift)."""
 
-    def __init__(self, w, cbias, bn):
+    def __init__(self, w, cbias, bn, packed=False):
         self.w = w.detach().reshape(w.shape[0], w.shape[1]).contiguous()
         self.cbias = cbias.detach().contiguous()
         self.O, self.I = self.w.shape
         self.bn = None if bn is None else [t.detach().contiguous() for t in bn]
         gamma, beta, mean, var = self.bn if self.bn is not None else (None, None, None, None)
+        self.packed = packed
+        self.shift, self.scale, self.rstd = _empty(self.O), _empty(self.O), _empty(self.O)
+        if packed:
+            # folded weights in the packed bf16 hi|lo layout (3xBF16): wf (O, r32(I)), wft (I, r32(O))
+            self.ld = _r32(self.I)
+            self.wf, self.wf_lo = _empty(self.O, self.ld), None
+            self.wft, self.wft_lo = _zeros(self.I, _r32(self.O)), None
+            call("obman_fold_conv", ptr(self.w), ptr(self.cbias), ptr(gamma), ptr(beta), ptr(mean), ptr(var),
+                 BN_EPS, self.O, self.I, 1, 1, self.ld, 0, 1, ptr(self.wf), None, ptr(self.wft), None,
+                 ptr(self.shift), ptr(self.scale), ptr(self.rstd), stream_ptr())
+            self.fw = {"packed": True}
+            self.bw = {"packed": True}
+            return
         self.ld = (self.I + 3) // 4 * 4
         # folded weights, pre-split into tf32 hi / lo parts: wf + wf_lo = scale * w (fprop), wft + wft_lo (dgrad)
         self.wf, self.wf_lo = _empty(self.O, self.ld), _empty(self.O, self.ld)
         self.wft, self.wft_lo = _zeros(self.I, _r32(self.O)), _zeros(self.I, _r32(self.O))   # (I, O padded)
         wft_tmp, wft_tmp_lo = _empty(self.I, self.O), _empty(self.I, self.O)
-        self.shift, self.scale, self.rstd = _empty(self.O), _empty(self.O), _empty(self.O)
         call("obman_fold_conv", ptr(self.w), ptr(self.cbias), ptr(gamma), ptr(beta), ptr(mean), ptr(var),
-             BN_EPS, self.O, self.I, 1, 1, self.ld, 0, ptr(self.wf), ptr(self.wf_lo), ptr(wft_tmp),
+             BN_EPS, self.O, self.I, 1, 1, self.ld, 0, 0, ptr(self.wf), ptr(self.wf_lo), ptr(wft_tmp),
              ptr(wft_tmp_lo), ptr(self.shift), ptr(self.scale), ptr(self.rstd), stream_ptr())
         self.wft[:, :self.O] = wft_tmp
         self.wft_lo[:, :self.O] = wft_tmp_lo
+        self.fw = {"w_lo": self.wf_lo}
+        self.bw = {"w_lo": self.wft_lo}
 
     def finish(self, dwraw, gsum):
         """dwraw (>=O rows, row stride ld_raw, first I columns valid) -> (gw, gcbias, ggamma, gbeta)."""
@@ -134,10 +149,11 @@ class _PointDecoderFn(torch.autograd.Function):
         B, Fdim = feat.shape
         N = grid.shape[-2]
         per_sample = grid.dim() == 3
-        l1 = _Layer(p[0], p[1], p[8:12])
-        l2 = _Layer(p[2], p[3], p[12:16])
-        l3 = _Layer(p[4], p[5], p[16:20])
-        l4 = _Layer(p[6], p[7], None)
+        pk = pf == dense.BF16X3
+        l1 = _Layer(p[0], p[1], p[8:12])          # conv1 is split algebraically below: keep fp32 folded weights
+        l2 = _Layer(p[2], p[3], p[12:16], packed=pk)
+        l3 = _Layer(p[4], p[5], p[16:20], packed=pk)
+        l4 = _Layer(p[6], p[7], None, packed=pk)
         C1, C2, C3 = l1.O, l2.O, l3.O
         # layer 1: grid part (K = 3, batch independent) + feature part (B x F GEMM) -> relu(G + F)
         w1 = l1.wf + l1.wf_lo                                # full-precision folded conv1 weights
@@ -149,10 +165,9 @@ class _PointDecoderFn(torch.autograd.Function):
         h1 = _empty(B * N, ld1)
         call("obman_pointmlp_l1_fwd", ptr(G), N * C1 if per_sample else 0, ptr(Fb), B, N, C1, ld1, ptr(h1), st)
         h2 = _zeros(B * N, ld2)
-        dense.gemm(h1, l2.wf, out=h2, bias=l2.shift, relu=True, passes=pf, n=C2, k=C1, w_lo=l2.wf_lo)
-        h3 = dense.gemm(h2, l3.wf, bias=l3.shift, relu=True, passes=pf, n=C3, k=C2, w_lo=l3.wf_lo)
-        y = dense.gemm(h3, l4.wf, bias=l4.shift * out_factor, alpha=out_factor, passes=pf, n=3, k=C3,
-                       w_lo=l4.wf_lo)
+        dense.gemm(h1, l2.wf, out=h2, bias=l2.shift, relu=True, passes=pf, n=C2, k=C1, **l2.fw)
+        h3 = dense.gemm(h2, l3.wf, bias=l3.shift, relu=True, passes=pf, n=C3, k=C2, **l3.fw)
+        y = dense.gemm(h3, l4.wf, bias=l4.shift * out_factor, alpha=out_factor, passes=pf, n=3, k=C3, **l4.fw)
         ctx.layers = (l1, l2, l3, l4)
         ctx.param_shapes = [tuple(t.shape) for t in p]
         ctx.saved = (feat, grid, wfeat, h1, h2, h3, B, N, per_sample, out_factor)
@@ -161,6 +176,7 @@ class _PointDecoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         pb = dense.PASSES[dense.get_precision()["bwd"]]
+        pw = dense.PASSES[dense.get_precision()["wgrad"]]
         st = stream_ptr()
         l1, l2, l3, l4 = ctx.layers
         feat, grid, wfeat, h1, h2, h3, B, N, per_sample, out_factor = ctx.saved
@@ -168,14 +184,14 @@ class _PointDecoderFn(torch.autograd.Function):
         M = B * N
         g4 = _zeros(M, 32)
         g4[:, :3] = gy.reshape(M, 3) * out_factor
-        gw4, gb4, _, _ = l4.finish(dense.wgrad_matrix(g4, h3, passes=pb), colsum(g4, 3))
-        g3 = dense.gemm(g4, l4.wft, mask_src=h3, passes=pb, n=C3, k=3, w_lo=l4.wft_lo)       # (M,C3)
-        gw3, gb3, gg3, gbt3 = l3.finish(dense.wgrad_matrix(g3, h2, passes=pb), colsum(g3, C3))
+        gw4, gb4, _, _ = l4.finish(dense.wgrad_matrix(g4, h3, passes=pw), colsum(g4, 3))
+        g3 = dense.gemm(g4, l4.wft, mask_src=h3, passes=pb, n=C3, k=3, **l4.bw)       # (M,C3)
+        gw3, gb3, gg3, gbt3 = l3.finish(dense.wgrad_matrix(g3, h2, passes=pw), colsum(g3, C3))
         g2 = _zeros(M, h2.shape[1])
-        dense.gemm(g3, l3.wft, out=g2, mask_src=h2, passes=pb, n=C2, k=C3, w_lo=l3.wft_lo)
-        gw2, gb2, gg2, gbt2 = l2.finish(dense.wgrad_matrix(g2, h1, passes=pb), colsum(g2, C2))
+        dense.gemm(g3, l3.wft, out=g2, mask_src=h2, passes=pb, n=C2, k=C3, **l3.bw)
+        gw2, gb2, gg2, gbt2 = l2.finish(dense.wgrad_matrix(g2, h1, passes=pw), colsum(g2, C2))
         g1 = _zeros(M, h1.shape[1])
-        dense.gemm(g2, l2.wft, out=g1, mask_src=h1, passes=pb, n=C1, k=C2, w_lo=l2.wft_lo)
+        dense.gemm(g2, l2.wft, out=g1, mask_src=h1, passes=pb, n=C1, k=C2, **l2.bw)
         gF = _zeros(B, _r32(C1))
         gFc = _empty(B, C1)
         gG = None if per_sample else _empty(N, C1)
@@ -187,7 +203,7 @@ class _PointDecoderFn(torch.autograd.Function):
         else:
             gwg = torch.einsum("nc,nk->ck", gG, grid)
         Fdim = feat.shape[1]
-        gwf = dense.wgrad_matrix(gF, _pad_cols(feat, _r32(Fdim)), passes=pb)[:C1, :Fdim]
+        gwf = dense.wgrad_matrix(gF, _pad_cols(feat, _r32(Fdim)), passes=pw)[:C1, :Fdim]
         dw1 = torch.cat([gwg, gwf], dim=1).contiguous()                                      # (C1, 3+F)
         gw1, gb1, gg1, gbt1 = l1.finish(dw1, colsum(gF, C1))
         gfeat = None

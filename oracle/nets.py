@@ -49,13 +49,25 @@ def _relu(z, masks, name):
     return _ReluWithMask.apply(z, masks[name])
 
 
-def resnet18_features(state, images, prefix="base_net", bn_training=False, relu_masks=None):
+def _maxpool_with_idx(x, idx):
+    """3x3/2 pad-1 max pooling that takes the window slot (dy*3+dx, NCHW int64) chosen elsewhere (tests only)."""
+    xp = F.pad(x, (1, 1, 1, 1), value=float("-inf"))
+    win = xp.unfold(2, 3, 2).unfold(3, 3, 2)  # (B,C,Ho,Wo,3,3)
+    win = win.reshape(win.shape[:4] + (9,))
+    return torch.gather(win, 4, idx.unsqueeze(4)).squeeze(4)
+
+
+def resnet18_features(state, images, prefix="base_net", bn_training=False, relu_masks=None, pool_idx=None):
     """(B,3,H,W) -> (B,512); conv7x7/2, BN, ReLU, maxpool3/2, 4x2 BasicBlocks, spatial mean.
-    ``relu_masks`` (tests only): {"c1", "a0".."a7", "out0".."out7"} -> bool NCHW branch masks."""
+    ``relu_masks`` (tests only): {"c1", "a0".."a7", "out0".."out7"} -> bool NCHW branch masks;
+    ``pool_idx`` (tests only): arg-max window slots of the max pooling (near-ties resolved as the caller did)."""
     p = prefix + "."
     x = F.conv2d(images, state[p + "conv1.weight"], None, stride=2, padding=3)
     x = _relu(_bn(x, state, p + "bn1", bn_training), relu_masks, "c1")
-    x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    if pool_idx is None:
+        x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+    else:
+        x = _maxpool_with_idx(x, pool_idx)
     b = 0
     for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
         for bi in range(2):

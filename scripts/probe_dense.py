@@ -40,6 +40,8 @@ def case_gemm(M, N, K, passes, epilogue=False):
         kw = dict(bias=bias, addend=addend, mask_src=mask, alpha=0.5, relu=True)
     if os.environ.get("PROBE_PRESPLIT", "1") == "1" and passes == 3:
         w, kw["w_lo"] = dense.split_tf32(w)
+    if passes == 2:
+        w, kw["packed"] = dense.pack_bf16(w, K), True
     out = dense.gemm(a, w, passes=passes, n=N, k=K, **kw)
     torch.cuda.synchronize()
     return _stats(out, ref)
@@ -70,6 +72,8 @@ def case_conv(n, h, cin, cout, k, stride, passes, epilogue=False):
         kw = dict(bias=bias, addend=res, relu=True)
     if os.environ.get("PROBE_PRESPLIT", "1") == "1" and passes == 3:
         wk, kw["w_lo"] = dense.split_tf32(wk)
+    if passes == 2:
+        wk = dense.pack_bf16(wk)
     dense.conv_nhwc(_nhwc(x), wk, cout, (dh, dw, phase, slot), step, out, ho, ho, passes=passes, **kw)
     torch.cuda.synchronize()
     return _stats(out.permute(0, 3, 1, 2), ref)
@@ -93,6 +97,8 @@ def case_dgrad(n, h, cin, cout, k, stride, passes):
     wt_lo = None
     if os.environ.get("PROBE_PRESPLIT", "1") == "1" and passes == 3:
         wt, wt_lo = dense.split_tf32(wt)
+    if passes == 2:
+        wt = dense.pack_bf16(wt)
     dx = torch.zeros(n, h, h, cin, device="cuda")
     for ph in range(stride):
         for pw in range(stride):
@@ -197,6 +203,25 @@ def case_rounding_mode():
     return res
 
 
+# 3xBF16 (packed bf16 hi|lo weights, A split into tensor memory)
+CASES.update({
+    "gemm_128x128x32_b3": lambda: case_gemm(128, 128, 32, 2),
+    "gemm_256x256x512_b3": lambda: case_gemm(256, 256, 512, 2),
+    "gemm_64x33x256_b3": lambda: case_gemm(64, 33, 256, 2),
+    "gemm_1000x515x515_b3_epi": lambda: case_gemm(1000, 515, 515, 2, True),
+    "gemm_4096x512x2304_b3": lambda: case_gemm(4096, 512, 2304, 2),
+    "gemm_20000x3x128_b3": lambda: case_gemm(20000, 3, 128, 2),
+    "conv3x3_s1_16_64_64_b3_epi": lambda: case_conv(2, 16, 64, 64, 3, 1, 2, True),
+    "conv3x3_s1_64_64_128_b3": lambda: case_conv(3, 64, 64, 128, 3, 1, 2),
+    "conv3x3_s1_8_512_512_b3": lambda: case_conv(5, 8, 512, 512, 3, 1, 2),
+    "conv3x3_s2_32_64_128_b3": lambda: case_conv(2, 32, 64, 128, 3, 2, 2),
+    "conv1x1_s2_32_64_128_b3": lambda: case_conv(2, 32, 64, 128, 1, 2, 2),
+    "small_conv3x3_s1_2_512_512_b3": lambda: case_conv(2, 2, 512, 512, 3, 1, 2, True),
+    "small_dgrad3x3_s2_4_256_512_b3": lambda: case_dgrad(2, 4, 256, 512, 3, 2, 2),
+    "dgrad3x3_s1_16_64_64_b3": lambda: case_dgrad(2, 16, 64, 64, 3, 1, 2),
+    "dgrad3x3_s2_32_64_128_b3": lambda: case_dgrad(2, 32, 64, 128, 3, 2, 2),
+    "dgrad1x1_s2_32_64_128_b3": lambda: case_dgrad(2, 32, 64, 128, 1, 2, 2),
+})
 CASES["rounding_mode_p1"] = case_rounding_mode
 CASES["stemlike_wgrad_4x4_128_32_64_p3"] = lambda: case_wgrad(2, 64, 32, 64, 3, 1, 3)
 CASES["wgrad3x3_s1_32_128_128_p3"] = lambda: case_wgrad(3, 32, 128, 128, 3, 1, 3)

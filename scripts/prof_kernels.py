@@ -11,6 +11,7 @@ from obman_train_b200 import dense  # noqa: E402
 
 B = int(os.environ.get("PROF_B", "64"))
 PASSES = int(os.environ.get("PROF_PASSES", "3"))
+WG_PASSES = int(os.environ.get("PROF_WG_PASSES", "3"))
 REPS = int(os.environ.get("PROF_REPS", "1"))
 
 
@@ -25,6 +26,8 @@ def conv_case(h, cin, cout, k=3, stride=1):
     w_lo = None
     if PASSES == 3 and os.environ.get("PROF_PRESPLIT", "1") == "1":
         w, w_lo = dense.split_tf32(w)
+    if PASSES == 2:
+        w = dense.pack_bf16(w)
     return (lambda: dense.conv_nhwc(x, w, cout, (dh, dw, phase, slot), step, out, ho, ho, bias=bias, relu=True, passes=PASSES, w_lo=w_lo)), flops
 
 
@@ -35,7 +38,7 @@ def wgrad_case(h, cin, cout, k=3, stride=1):
     dh, dw, phase, slot, step = dense.fprop_taps(k, stride, k // 2)
     dwt = torch.empty(cout, k * k * cin, device="cuda")
     flops = 2.0 * B * ho * ho * cout * k * k * cin
-    return (lambda: dense.wgrad_nhwc(dy, x, (dh, dw, phase, slot), step, dwt, passes=PASSES)), flops
+    return (lambda: dense.wgrad_nhwc(dy, x, (dh, dw, phase, slot), step, dwt, passes=WG_PASSES)), flops
 
 
 def gemm_case(M, N, K):
@@ -44,7 +47,9 @@ def gemm_case(M, N, K):
     w_lo = None
     if PASSES == 3 and os.environ.get("PROF_PRESPLIT", "1") == "1":
         w, w_lo = dense.split_tf32(w)
-    return (lambda: dense.gemm(a, w, relu=True, passes=PASSES, n=N, k=K, w_lo=w_lo)), 2.0 * M * N * K
+    if PASSES == 2:
+        w = dense.pack_bf16(w, K)
+    return (lambda: dense.gemm(a, w, relu=True, passes=PASSES, n=N, k=K, w_lo=w_lo, packed=PASSES == 2)), 2.0 * M * N * K
 
 
 CASES = [

@@ -238,7 +238,7 @@ def run_b200(args):
         raise RuntimeError(lib.obman_get_last_error().decode())
     dense.set_precision(args.precision, args.precision)
     PRECISION_NOTE[0] = {
-        "bf16x3": "fprop/dgrad: fp32 operands split into bf16 hi+lo, 3 tensor-core products (fp32-equivalent to ~2^-17); wgrad: 3xTF32",
+        "bf16x3": "fp32 operands split into bf16 hi+lo, 3 tensor-core products per contraction (fp32-equivalent to ~2^-17), fwd+bwd",
         "tf32x3": "3xTF32 tensor-core passes (fp32-equivalent) fwd+bwd", "tf32": "single-pass TF32"}[args.precision]
 
     torch.manual_seed(0)  # identical replicas on every rank

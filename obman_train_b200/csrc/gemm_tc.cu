@@ -90,6 +90,122 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// Epilogue shared by the GEMM kernels: wait for the accumulator, then TMEM -> registers -> global.
+// Called by the four epilogue warps (q = TMEM lane quadrant, r = q * 32 + lane = tile row); `smem` is the tile
+// buffer base (its first 17 KB are reused for staging, every operand read has retired by then).
+template <int BN, int MODE>
+__device__ __forceinline__ void gemm_epilogue(uint8_t* smem, uint32_t tmem_base, uint64_t* accum,
+                                              const GemmProgram& prog, const GemmEpilogue& epi, int m0, int n0,
+                                              int n_img0, int h0, int w0, int q, int lane, int r) {
+    // ---- epilogue ----
+    // TMEM -> registers (lane = tile row) -> XOR-swizzled shared-memory transpose -> each store / addend / mask
+    // instruction touches 4 rows x 128 contiguous bytes (the row-per-lane layout would touch 32 rows x 16 bytes).
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    if (MODE == 2) {
+      // D[m, n] with m = stacked (tap, c_in) index and n = output channel; dw is (c_out, taps*c_in) row-major, so
+      // element (m, n) lives at n*ld + m: the 32 lanes of a warp (consecutive m) make every column one coalesced access.
+      const bool row_ok = (m0 + r) < prog.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= prog.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + c0 + j;
+          if (col >= prog.N) break;
+          float* dst = epi.out + (long long)col * epi.ld + (m0 + r);
+          const float y = epi.alpha * __uint_as_float(v[j]);
+          if (epi.accumulate) atomicAdd(dst, y);
+          else *dst = y;
+        }
+      }
+    } else {
+    // all MMAs (and therefore all TMA loads and operand reads) have retired: stage 0 is free for staging
+    uint8_t* wbase = smem + q * 4096;                                   // 32 rows x 128 B per warp
+    long long* rowinfo = reinterpret_cast<long long*>(smem + 16384);    // element offset of every tile row, -1 = none
+    {
+      bool row_ok;
+      long long row_off;
+      if (MODE == 0 && prog.spatial) {
+        const int tw = r % prog.TW;
+        const int th = (r / prog.TW) % prog.TH;
+        const int tn = r / (prog.TW * prog.TH);
+        const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
+        row_ok = n < prog.n_img && h < prog.h_out && w < prog.w_out;
+        row_off = n * epi.sN + h * epi.sH + w * epi.sW;
+      } else {
+        row_ok = (m0 + r) < prog.M;
+        row_off = (long long)(m0 + r) * epi.ld;
+      }
+      rowinfo[r] = row_ok ? row_off : -1;
+    }
+    __syncwarp();  // each warp only ever reads the rowinfo entries of its own 32 rows
+    const bool ptr_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
+                          reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0 && !epi.accumulate;
+    const int cc = lane & 7;     // 16-byte column chunk handled by this lane after the transpose
+    const int rsub = lane >> 3;  // row within each group of 4
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= prog.N) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(wbase + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+            make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      __syncwarp();
+      const int col = n0 + c0 + 4 * cc;
+      float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (epi.bias) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (col + e < prog.N) bias4[e] = __ldg(epi.bias + col + e);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + rsub;
+        const long long row_off = rowinfo[q * 32 + rr];
+        if (row_off < 0 || col >= prog.N) continue;
+        const float4 a = *reinterpret_cast<const float4*>(wbase + rr * 128 + ((cc ^ (rr & 7)) << 4));
+        float x[4] = {epi.alpha * a.x + bias4[0], epi.alpha * a.y + bias4[1], epi.alpha * a.z + bias4[2],
+                      epi.alpha * a.w + bias4[3]};
+        if ((col + 3 < prog.N) && ptr_ok && ((row_off & 3) == 0)) {
+          if (epi.addend) {
+            const float4 a4 = *reinterpret_cast<const float4*>(epi.addend + row_off + col);
+            x[0] += a4.x; x[1] += a4.y; x[2] += a4.z; x[3] += a4.w;
+          }
+          if (epi.relu) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+          }
+          if (epi.mask_src) {
+            const float4 m4 = *reinterpret_cast<const float4*>(epi.mask_src + row_off + col);
+            x[0] = m4.x > 0.f ? x[0] : 0.f; x[1] = m4.y > 0.f ? x[1] : 0.f;
+            x[2] = m4.z > 0.f ? x[2] : 0.f; x[3] = m4.w > 0.f ? x[3] : 0.f;
+          }
+          *reinterpret_cast<float4*>(epi.out + row_off + col) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (col + e >= prog.N) break;
+            float y = x[e];
+            if (epi.addend) y += epi.addend[row_off + col + e];
+            if (epi.relu) y = fmaxf(y, 0.f);
+            if (epi.mask_src) y = epi.mask_src[row_off + col + e] > 0.f ? y : 0.f;
+            if (epi.accumulate) atomicAdd(epi.out + row_off + col + e, y);
+            else epi.out[row_off + col + e] = y;
+          }
+        }
+      }
+      __syncwarp();  // staging is overwritten by the next chunk
+    }
+    }  // MODE != 2
+}
+
 // CL > 1 (TS path only): thread-block cluster of CL CTAs along the M-tile axis.  They share the weight tile, so
 // each CTA fetches 1/CL of it and TMA-multicasts it to all of them: the kernels were L2->SM bandwidth bound
 // (~9 TB/s measured against ~42 B/clk/SM), the weight tile being 2/3 of the bytes of every K block.
@@ -368,113 +484,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         mbar_arrive(&conv[s]);
       }
     }
-    // ---- epilogue ----
-    // TMEM -> registers (lane = tile row) -> XOR-swizzled shared-memory transpose -> each store / addend / mask
-    // instruction touches 4 rows x 128 contiguous bytes (the row-per-lane layout would touch 32 rows x 16 bytes).
-    mbar_wait(accum, 0);
-    tc_fence_after();
-    if (MODE == 2) {
-      // D[m, n] with m = stacked (tap, c_in) index and n = output channel; dw is (c_out, taps*c_in) row-major, so
-      // element (m, n) lives at n*ld + m: the 32 lanes of a warp (consecutive m) make every column one coalesced access.
-      const bool row_ok = (m0 + r) < prog.M;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= prog.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = n0 + c0 + j;
-          if (col >= prog.N) break;
-          float* dst = epi.out + (long long)col * epi.ld + (m0 + r);
-          const float y = epi.alpha * __uint_as_float(v[j]);
-          if (epi.accumulate) atomicAdd(dst, y);
-          else *dst = y;
-        }
-      }
-    } else {
-    // all MMAs (and therefore all TMA loads and operand reads) have retired: stage 0 is free for staging
-    uint8_t* wbase = smem + q * 4096;                                   // 32 rows x 128 B per warp
-    long long* rowinfo = reinterpret_cast<long long*>(smem + 16384);    // element offset of every tile row, -1 = none
-    {
-      bool row_ok;
-      long long row_off;
-      if (MODE == 0 && prog.spatial) {
-        const int tw = r % prog.TW;
-        const int th = (r / prog.TW) % prog.TH;
-        const int tn = r / (prog.TW * prog.TH);
-        const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
-        row_ok = n < prog.n_img && h < prog.h_out && w < prog.w_out;
-        row_off = n * epi.sN + h * epi.sH + w * epi.sW;
-      } else {
-        row_ok = (m0 + r) < prog.M;
-        row_off = (long long)(m0 + r) * epi.ld;
-      }
-      rowinfo[r] = row_ok ? row_off : -1;
-    }
-    __syncwarp();  // each warp only ever reads the rowinfo entries of its own 32 rows
-    const bool ptr_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
-                          reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0 && !epi.accumulate;
-    const int cc = lane & 7;     // 16-byte column chunk handled by this lane after the transpose
-    const int rsub = lane >> 3;  // row within each group of 4
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= prog.N) break;  // warp-uniform
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(wbase + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-            make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-      __syncwarp();
-      const int col = n0 + c0 + 4 * cc;
-      float bias4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (epi.bias) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) if (col + e < prog.N) bias4[e] = __ldg(epi.bias + col + e);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = 4 * i + rsub;
-        const long long row_off = rowinfo[q * 32 + rr];
-        if (row_off < 0 || col >= prog.N) continue;
-        const float4 a = *reinterpret_cast<const float4*>(wbase + rr * 128 + ((cc ^ (rr & 7)) << 4));
-        float x[4] = {epi.alpha * a.x + bias4[0], epi.alpha * a.y + bias4[1], epi.alpha * a.z + bias4[2],
-                      epi.alpha * a.w + bias4[3]};
-        if ((col + 3 < prog.N) && ptr_ok && ((row_off & 3) == 0)) {
-          if (epi.addend) {
-            const float4 a4 = *reinterpret_cast<const float4*>(epi.addend + row_off + col);
-            x[0] += a4.x; x[1] += a4.y; x[2] += a4.z; x[3] += a4.w;
-          }
-          if (epi.relu) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
-          }
-          if (epi.mask_src) {
-            const float4 m4 = *reinterpret_cast<const float4*>(epi.mask_src + row_off + col);
-            x[0] = m4.x > 0.f ? x[0] : 0.f; x[1] = m4.y > 0.f ? x[1] : 0.f;
-            x[2] = m4.z > 0.f ? x[2] : 0.f; x[3] = m4.w > 0.f ? x[3] : 0.f;
-          }
-          *reinterpret_cast<float4*>(epi.out + row_off + col) = make_float4(x[0], x[1], x[2], x[3]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (col + e >= prog.N) break;
-            float y = x[e];
-            if (epi.addend) y += epi.addend[row_off + col + e];
-            if (epi.relu) y = fmaxf(y, 0.f);
-            if (epi.mask_src) y = epi.mask_src[row_off + col + e] > 0.f ? y : 0.f;
-            if (epi.accumulate) atomicAdd(epi.out + row_off + col + e, y);
-            else epi.out[row_off + col + e] = y;
-          }
-        }
-      }
-      __syncwarp();  // staging is overwritten by the next chunk
-    }
-    }  // MODE != 2
+    gemm_epilogue<BN, MODE>(smem, tmem_base, accum, prog, epi, m0, n0, n_img0, h0, w0, q, lane, r);
   }
   tc_fence_before();
   __syncthreads();
@@ -521,6 +531,204 @@ static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const Gemm
   }
   gemm_tc_kernel<BN, PASSES, MODE, TS, OCC, CL><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
   return check_launch("gemm_tc_kernel");
+}
+
+// ---- weight gradient on the 3xBF16 path -----------------------------------------------------------------------
+// Both operands of a weight gradient are activations (dY and the shifted taps of x), channels contiguous and the
+// reduction (pixels) along rows, so neither can be pre-split.  The raw fp32 tiles land UNswizzled in a small
+// ring (TMA), the four splitter warps read them column-wise (one thread per channel: 32 pixels, conflict-free),
+// split every value into bf16 hi + lo and write
+//   * the A operand (128 channels x 32 pixels) into tensor memory, and
+//   * the B operand as K-major rows [32 hi | 32 lo] (the layout of the packed weights of the fprop kernels) into
+//     a second ring, hand-swizzled for the SW128 descriptor,
+// so the MMA stream is the one of the fprop kernels.  The raw ring is released as soon as it has been read, the
+// converted ring when its MMAs retire.  SWAP = 1: rows = stacked taps, columns = dY channels (c_out <= 64).
+template <int BN, int SWAP, int OCC>
+struct WgradCfg {
+  static constexpr int A_RAW = 128 * 128;              // 4 groups x 32 pixels x 32 channels fp32
+  static constexpr int B_RAW = BN * 128;
+  static constexpr int RAW_BYTES = A_RAW + B_RAW;
+  static constexpr int B_CONV = BN * 128;
+  static constexpr int BUDGET = (OCC == 2 ? 104 : 200) * 1024;
+  static constexpr int R = 2;                          // raw stages
+  static constexpr int C_SMEM = (BUDGET - R * RAW_BYTES) / B_CONV;
+  static constexpr int C_TMEM = ((OCC == 2 ? 256 : 512) - BN) / 32;
+  static constexpr int C0 = C_SMEM < C_TMEM ? C_SMEM : C_TMEM;
+  static constexpr int C = C0 > 6 ? 6 : C0;            // converted stages
+  static constexpr int TMEM_NEED = BN + C * 32;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
+  static constexpr int SMEM_BYTES = R * RAW_BYTES + C * B_CONV + 1024 + 256;
+};
+
+template <int BN, int SWAP, int OCC>
+__global__ void __launch_bounds__(GEMM_THREADS, OCC)
+wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, const GemmEpilogue epi) {
+  using Cfg = WgradCfg<BN, SWAP, OCC>;
+  static_assert(Cfg::C >= 2, "needs at least two converted stages");
+  constexpr int R = Cfg::R, C = Cfg::C;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* conv_base = smem + R * Cfg::RAW_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(conv_base + C * Cfg::B_CONV);
+  uint64_t* full = bars;                // [R] TMA bytes landed
+  uint64_t* rawfree = bars + R;         // [R] splitter has read the raw stage
+  uint64_t* conv = bars + 2 * R;        // [C] converted operands written
+  uint64_t* empty = bars + 2 * R + C;   // [C] MMAs reading the converted stage retired
+  uint64_t* accum = bars + 2 * R + 2 * C;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = (blockIdx.x / prog.n_tiles) * BM;
+  const int n0 = (blockIdx.x % prog.n_tiles) * BN;
+  const int total = prog.kblocks_n * prog.kblocks_h * prog.kblocks_w;
+  const int per = (total + gridDim.z - 1) / gridDim.z;
+  const int pb_begin = blockIdx.z * per;
+  const int n_iters = min(total, pb_begin + per) - pb_begin;
+  if (n_iters <= 0) return;  // uniform for the whole CTA, before any barrier / TMEM allocation
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&rawfree[i], 128); }
+    for (int i = 0; i < C; ++i) { mbar_init(&conv[i], 128); mbar_init(&empty[i], 1); }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto raw_a = [&](int i) { return smem + i * Cfg::RAW_BYTES; };
+  auto raw_b = [&](int i) { return smem + i * Cfg::RAW_BYTES + Cfg::A_RAW; };
+  auto conv_b = [&](int i) { return conv_base + i * Cfg::B_CONV; };
+  // groups of 32 channels of the stacked-tap operand that exist in this tile (B normally, A when swapped)
+  const int valid_groups = SWAP ? min(BM / 32, prog.total_groups - m0 / 32) : min(BN / 32, prog.total_groups - n0 / 32);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.a[0]);
+      for (int it = 0; it < n_iters; ++it) {
+        const int rs = it % R;
+        mbar_wait(&rawfree[rs], ((it / R) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[rs], 4096 * valid_groups + (SWAP ? Cfg::B_RAW : Cfg::A_RAW));
+        int pb = pb_begin + it;
+        const int bw = pb % prog.kblocks_w; pb /= prog.kblocks_w;
+        const int bh = pb % prog.kblocks_h; pb /= prog.kblocks_h;
+        const int pw = bw * prog.kTW, ph_ = bh * prog.kTH, pn = pb * prog.kTN;
+        uint8_t* taps_dst = SWAP ? raw_a(rs) : raw_b(rs);
+        const int g0 = (SWAP ? m0 : n0) / 32;
+        for (int j = 0; j < valid_groups; ++j) {
+          const int g = g0 + j;
+          const int tap = g / prog.cg_in, cg = g - tap * prog.cg_in;
+          tma_load_5d(taps_dst + j * 4096, &maps.a[1 + prog.tap_map[tap]], &full[rs], 0, pw + prog.tap_dw[tap],
+                      ph_ + prog.tap_dh[tap], pn, cg);
+        }
+        tma_load_5d(SWAP ? raw_b(rs) : raw_a(rs), &maps.a[0], &full[rs], 0, pw, ph_, pn, (SWAP ? n0 : m0) / 32);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(BM, BN);
+    for (int it = 0; it < n_iters; ++it) {
+      const int cs = it % C;
+      mbar_wait(&conv[cs], (it / C) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t b = smem_u32(conv_b(cs));
+        const uint32_t ta = tmem_base + (uint32_t)(BN + 32 * cs);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint64_t db = umma_desc(b + k * 32, 16, 1024, 2);
+          const uint64_t dbl = umma_desc(b + 64 + k * 32, 16, 1024, 2);
+          umma_f16_ts(tmem_base, ta + 16 + k * 8, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_f16_ts(tmem_base, ta + k * 8, dbl, idesc, 1u);
+          umma_f16_ts(tmem_base, ta + k * 8, db, idesc, 1u);
+        }
+        umma_commit(&empty[cs]);
+        if (it == n_iters - 1) umma_commit(accum);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int a_groups = SWAP ? valid_groups : BM / 32;
+    const int b_groups = SWAP ? BN / 32 : valid_groups;
+    for (int it = 0; it < n_iters; ++it) {
+      const int rs = it % R, cs = it % C;
+      mbar_wait(&full[rs], (it / R) & 1);
+      mbar_wait(&empty[cs], ((it / C) & 1) ^ 1);
+      tc_fence_after();
+      {
+        // A: channel r of the tile = column `lane` of group q, pixels along K
+        uint32_t hi[16], lo[16];
+        if (q < a_groups) {
+          const float* src = reinterpret_cast<const float*>(raw_a(rs)) + q * 1024 + lane;
+#pragma unroll
+          for (int p = 0; p < 16; ++p) split_bf16x2(src[(2 * p) * 32], src[(2 * p + 1) * 32], hi[p], lo[p]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < 16; ++p) hi[p] = lo[p] = 0u;
+        }
+        const uint32_t dst = lane_base + (uint32_t)(BN + 32 * cs);
+        tmem_st_32x16(dst, hi);
+        tmem_st_32x16(dst + 16, lo);
+      }
+#pragma unroll
+      for (int i = 0; i < (BN + 127) / 128; ++i) {
+        const int n = r + 128 * i;       // B row (channel of the tile)
+        if (n < BN) {
+          uint32_t hi[16], lo[16];
+          const int g = n >> 5;
+          if (g < b_groups) {
+            const float* src = reinterpret_cast<const float*>(raw_b(rs)) + g * 1024 + lane;
+#pragma unroll
+            for (int p = 0; p < 16; ++p) split_bf16x2(src[(2 * p) * 32], src[(2 * p + 1) * 32], hi[p], lo[p]);
+          } else {
+#pragma unroll
+            for (int p = 0; p < 16; ++p) hi[p] = lo[p] = 0u;
+          }
+          uint8_t* row = conv_b(cs) + n * 128;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<uint4*>(row + ((j ^ (n & 7)) << 4)) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            *reinterpret_cast<uint4*>(row + (((j + 4) ^ (n & 7)) << 4)) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+        }
+      }
+      mbar_arrive(&rawfree[rs]);
+      fence_proxy_async_smem();
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&conv[cs]);
+    }
+    gemm_epilogue<BN, SWAP ? 2 : 1>(smem, tmem_base, accum, prog, epi, m0, n0, 0, 0, 0, q, lane, r);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN, int SWAP, int OCC>
+static int launch_wgrad_bf16(const GemmMaps& maps, const GemmProgram& prog, const GemmEpilogue& epi, dim3 grid,
+                             cudaStream_t st) {
+  using Cfg = WgradCfg<BN, SWAP, OCC>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_bf16_kernel<BN, SWAP, OCC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("wgrad_bf16: cudaFuncSetAttribute(%d bytes) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return OBMAN_ERR_CUDA;
+    }
+    attr = true;
+  }
+  wgrad_bf16_kernel<BN, SWAP, OCC><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
+  return check_launch("wgrad_bf16_kernel");
 }
 
 // Cluster size the TS path will run with for a grid of grid_x row tiles (the weight tensor maps are built with a
@@ -768,7 +976,8 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
   OBMAN_REQUIRE(num_taps >= 1 && num_taps <= MAX_TAPS, "obman_wgrad_nhwc: bad tap count");
   OBMAN_REQUIRE(in_step == 1 || in_step == 2, "obman_wgrad_nhwc: in_step must be 1 or 2");
   OBMAN_REQUIRE(in_step == 1 || (h_in % 2 == 0 && w_in % 2 == 0), "obman_wgrad_nhwc: phase views need even h_in/w_in");
-  OBMAN_REQUIRE(passes == 1 || passes == 3, "obman_wgrad_nhwc: passes must be 1 or 3");
+  OBMAN_REQUIRE(passes == 1 || passes == 3 || passes == OBMAN_PREC_3XBF16, "obman_wgrad_nhwc: passes must be 1, 2 or 3");
+  const bool bf = passes == OBMAN_PREC_3XBF16;
   OBMAN_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0, "obman_wgrad_nhwc: dy/x must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   int kTW = 1;
@@ -786,7 +995,9 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
   prog.N = prog.total_groups * 32;
   prog.kTN = kTN; prog.kTH = kTH; prog.kTW = kTW;
   prog.mn_lbo = 4096; prog.mn_sbo = 512; prog.mn_layout = 1;
-  const CUtensorMapSwizzle mn_swizzle = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  // 3xBF16: the tiles are read by the splitter warps, not by the tensor core: no swizzle (column reads are
+  // conflict-free); 3xTF32: MN-major TF32 operands need the 128-byte swizzle with 32-byte atoms
+  const CUtensorMapSwizzle mn_swizzle = bf ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   prog.kblocks_n = (n_img + kTN - 1) / kTN;
   prog.kblocks_h = (h_out + kTH - 1) / kTH;
   prog.kblocks_w = (w_out + kTW - 1) / kTW;
@@ -851,6 +1062,12 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
   epi.accumulate = splits > 1;
   epi.ld = ld;
   dim3 grid((unsigned)(m_tiles * prog.n_tiles), 1, (unsigned)splits);
+  if (bf) {
+    if (swapped) return launch_wgrad_bf16<64, 1, 2>(maps, prog, epi, grid, st);
+    if (BN == 256) return launch_wgrad_bf16<256, 0, 1>(maps, prog, epi, grid, st);
+    if (BN == 128) return launch_wgrad_bf16<128, 0, 1>(maps, prog, epi, grid, st);
+    return launch_wgrad_bf16<64, 0, 1>(maps, prog, epi, grid, st);
+  }
   if (swapped) return dispatch_gemm<2>(BN, passes, 0, maps, prog, epi, grid, st);
   return dispatch_gemm<1>(BN, passes, 0, maps, prog, epi, grid, st);
 }

@@ -10,7 +10,7 @@ from ._lib import call, ptr, stream_ptr
 
 PASSES = {"tf32": 1, "bf16x3": 2, "tf32x3": 3}
 BF16X3 = 2
-_precision = {"fwd": "bf16x3", "bwd": "bf16x3", "wgrad": "tf32x3"}
+_precision = {"fwd": "bf16x3", "bwd": "bf16x3", "wgrad": "bf16x3"}
 
 
 def set_precision(fwd="bf16x3", bwd="bf16x3", wgrad=None):
@@ -21,8 +21,8 @@ def set_precision(fwd="bf16x3", bwd="bf16x3", wgrad=None):
     if (fwd == "bf16x3") != (bwd == "bf16x3"):
         raise ValueError("set_precision: 'bf16x3' must be chosen for both fwd and bwd or for neither")
     if wgrad is None:
-        wgrad = "tf32" if bwd == "tf32" else "tf32x3"
-    assert wgrad in ("tf32", "tf32x3")
+        wgrad = bwd
+    assert wgrad in PASSES
     _precision["fwd"] = fwd
     _precision["bwd"] = bwd
     _precision["wgrad"] = wgrad

@@ -222,6 +222,22 @@ CASES.update({
     "dgrad3x3_s2_32_64_128_b3": lambda: case_dgrad(2, 32, 64, 128, 3, 2, 2),
     "dgrad1x1_s2_32_64_128_b3": lambda: case_dgrad(2, 32, 64, 128, 1, 2, 2),
 })
+CASES.update({
+    "small_wgrad3x3_s1_4_512_512_b3": lambda: case_wgrad(4, 4, 512, 512, 3, 1, 2),
+    "small_wgrad3x3_s1_2_512_512_b3": lambda: case_wgrad(2, 2, 512, 512, 3, 1, 2),
+    "small_wgrad3x3_s2_4_256_512_b3": lambda: case_wgrad(2, 4, 256, 512, 3, 2, 2),
+    "wgrad_matrix_4096x128x256_b3": lambda: case_wgrad_matrix(4096, 128, 256, 2),
+    "wgrad_matrix_1000x64x544_b3": lambda: case_wgrad_matrix(1000, 64, 544, 2),
+    "wgrad_matrix_1000x32x128_b3": lambda: case_wgrad_matrix(1000, 32, 128, 2),
+    "wgrad_matrix_777x544x64_b3": lambda: case_wgrad_matrix(777, 544, 64, 2),
+    "wgrad3x3_s1_16_64_64_b3": lambda: case_wgrad(4, 16, 64, 64, 3, 1, 2),
+    "wgrad3x3_s1_8_512_512_b3": lambda: case_wgrad(4, 8, 512, 512, 3, 1, 2),
+    "wgrad3x3_s2_32_64_128_b3": lambda: case_wgrad(2, 32, 64, 128, 3, 2, 2),
+    "wgrad1x1_s2_32_64_128_b3": lambda: case_wgrad(2, 32, 64, 128, 1, 2, 2),
+    "stemlike_wgrad_4x4_128_32_64_b3": lambda: case_wgrad(2, 64, 32, 64, 3, 1, 2),
+    "wgrad3x3_s1_32_128_128_b3": lambda: case_wgrad(3, 32, 128, 128, 3, 1, 2),
+    "wgrad3x3_s1_20_96_160_b3": lambda: case_wgrad(2, 20, 96, 160, 3, 1, 2),
+})
 CASES["rounding_mode_p1"] = case_rounding_mode
 CASES["stemlike_wgrad_4x4_128_32_64_p3"] = lambda: case_wgrad(2, 64, 32, 64, 3, 1, 3)
 CASES["wgrad3x3_s1_32_128_128_p3"] = lambda: case_wgrad(3, 32, 128, 128, 3, 1, 3)

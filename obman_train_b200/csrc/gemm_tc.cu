@@ -68,7 +68,24 @@ struct GemmEpilogue {
   int accumulate;         // atomicAdd into out instead of store
   // row -> element offset: plain: row * ld ; spatial: n*sN + h*sH + w*sW  (+ column)
   long long ld, sN, sH, sW;
+  // diagnostics (obman_debug_trace): 8 clock64 stamps per CTA, NULL in normal operation
+  long long* trace;
+  long long trace_cap;
 };
+
+// stamp slot `k` of this CTA's trace record (slot 7 also gets the SM id in its upper bits)
+__device__ __forceinline__ void trace_stamp(const GemmEpilogue& epi, int k) {
+  if (epi.trace == nullptr) return;
+  const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
+  if ((cta + 1) * 8 > epi.trace_cap) return;
+  long long t = clock64();
+  if (k == 7) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    t = (t & 0x0000ffffffffffffLL) | ((long long)smid << 48);
+  }
+  epi.trace[cta * 8 + k] = t;
+}
 
 // OCC = CTAs per SM the configuration is sized for: with 2, one CTA's prologue / epilogue overlaps the other's
 // main loop (the kernel is not persistent), at the price of a shallower per-CTA pipeline.
@@ -102,6 +119,7 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, uint32_t tmem_base,
     // instruction touches 4 rows x 128 contiguous bytes (the row-per-lane layout would touch 32 rows x 16 bytes).
     mbar_wait(accum, 0);
     tc_fence_after();
+    if (r == 0) trace_stamp(epi, 6);
     if (MODE == 2) {
       // D[m, n] with m = stacked (tap, c_in) index and n = output channel; dw is (c_out, taps*c_in) row-major, so
       // element (m, n) lives at n*ld + m: the 32 lanes of a warp (consecutive m) make every column one coalesced access.
@@ -231,6 +249,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   int n_iters = prog.num_taps * prog.kblocks;
+  if (threadIdx.x == 0) trace_stamp(epi, 0);
 
   // tile coordinates
   int m0 = 0, n_img0 = 0, h0 = 0, w0 = 0;
@@ -273,6 +292,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   if (CL > 1) cluster_sync_all();   // peers' barriers must exist before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_stamp(epi, 1);
 
   // stage layout.  SS: A | B | A_lo | B_lo.   TS: A_raw | B_hi | B_lo.
   auto stage_a = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
@@ -349,6 +369,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
           tma_load_2d(stage_b(s), &maps.b, &full[s], prog.tap_bk[tap] + kb * BK, n0);
           if (TS == 1) tma_load_2d(stage_blo(s), &maps.b_lo, &full[s], prog.tap_bk[tap] + kb * BK, n0);
         }
+        if (it == 0) trace_stamp(epi, 2);
+        if (it == n_iters - 1) trace_stamp(epi, 3);
       }
     }
   } else if (warp == 1) {
@@ -368,6 +390,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
       if (PASSES == 3) mbar_wait(&conv[s], ph);
       tc_fence_after();
       if (lane == 0) {
+        if (it == 0) trace_stamp(epi, 4);
         const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_b(s));
         const uint32_t a_lo = smem_u32(stage_alo(s)), b_lo = smem_u32(stage_blo(s));
         if (TS == 2) {
@@ -407,7 +430,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         }
         if (CL > 1) umma_commit_mc(&empty[s], CL_MASK);
         else umma_commit(&empty[s]);
-        if (it == n_iters - 1) umma_commit(accum);
+        if (it == n_iters - 1) { umma_commit(accum); trace_stamp(epi, 5); }
       }
       __syncwarp();
     }
@@ -490,6 +513,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   __syncthreads();
   if (CL > 1) cluster_sync_all();   // no CTA may exit while peers can still multicast into it / arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (threadIdx.x == 0) trace_stamp(epi, 7);
 }
 
 template <int BN, int PASSES, int MODE, int TS, int OCC, int CL = 1>
@@ -586,6 +610,7 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
   const int pb_begin = blockIdx.z * per;
   const int n_iters = min(total, pb_begin + per) - pb_begin;
   if (n_iters <= 0) return;  // uniform for the whole CTA, before any barrier / TMEM allocation
+  if (threadIdx.x == 0) trace_stamp(epi, 0);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&rawfree[i], 128); }
@@ -602,6 +627,7 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (threadIdx.x == 0) trace_stamp(epi, 1);
   auto raw_a = [&](int i) { return smem + i * Cfg::RAW_BYTES; };
   auto raw_b = [&](int i) { return smem + i * Cfg::RAW_BYTES + Cfg::A_RAW; };
   auto conv_b = [&](int i) { return conv_base + i * Cfg::B_CONV; };
@@ -628,6 +654,8 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
                       ph_ + prog.tap_dh[tap], pn, cg);
         }
         tma_load_5d(SWAP ? raw_b(rs) : raw_a(rs), &maps.a[0], &full[rs], 0, pw, ph_, pn, (SWAP ? n0 : m0) / 32);
+        if (it == 0) trace_stamp(epi, 2);
+        if (it == n_iters - 1) trace_stamp(epi, 3);
       }
     }
   } else if (warp == 1) {
@@ -637,6 +665,7 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
       mbar_wait(&conv[cs], (it / C) & 1);
       tc_fence_after();
       if (lane == 0) {
+        if (it == 0) trace_stamp(epi, 4);
         const uint32_t b = smem_u32(conv_b(cs));
         const uint32_t ta = tmem_base + (uint32_t)(BN + 32 * cs);
 #pragma unroll
@@ -648,7 +677,7 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
           umma_f16_ts(tmem_base, ta + k * 8, db, idesc, 1u);
         }
         umma_commit(&empty[cs]);
-        if (it == n_iters - 1) umma_commit(accum);
+        if (it == n_iters - 1) { umma_commit(accum); trace_stamp(epi, 5); }
       }
       __syncwarp();
     }
@@ -711,6 +740,7 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (threadIdx.x == 0) trace_stamp(epi, 7);
 }
 
 template <int BN, int SWAP, int OCC>
@@ -801,6 +831,9 @@ static int pick_bn(int N, long long m_tiles) {
   return best;
 }
 
+static long long* g_trace = nullptr;
+static long long g_trace_cap = 0;
+
 static bool ts_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -866,6 +899,7 @@ extern "C" int obman_gemm(const float* A, long long lda, const float* W, const f
   memset(&epi, 0, sizeof(epi));
   epi.out = out; epi.bias = bias; epi.addend = addend; epi.mask_src = mask_src;
   epi.alpha = alpha; epi.relu = relu; epi.accumulate = accumulate; epi.ld = ldo;
+  epi.trace = g_trace; epi.trace_cap = g_trace_cap;
   dim3 grid((unsigned)m_tiles, (unsigned)((N + BN - 1) / BN), 1);
   return dispatch_gemm<0>(BN, passes, ts, maps, prog, epi, grid, (cudaStream_t)stream);
 }
@@ -956,6 +990,7 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
   epi.out = out; epi.bias = bias; epi.addend = addend; epi.mask_src = mask_src;
   epi.alpha = 1.f; epi.relu = relu; epi.accumulate = 0;
   epi.sN = o_sN; epi.sH = o_sH; epi.sW = o_sW;
+  epi.trace = g_trace; epi.trace_cap = g_trace_cap;
   dim3 grid((unsigned)m_tiles, (unsigned)((c_out + BN - 1) / BN), 1);
   return dispatch_gemm<0>(BN, passes, ts, maps, prog, epi, grid, (cudaStream_t)stream);
 }
@@ -1061,6 +1096,7 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
   epi.alpha = 1.f;
   epi.accumulate = splits > 1;
   epi.ld = ld;
+  epi.trace = g_trace; epi.trace_cap = g_trace_cap;
   dim3 grid((unsigned)(m_tiles * prog.n_tiles), 1, (unsigned)splits);
   if (bf) {
     if (swapped) return launch_wgrad_bf16<64, 1, 2>(maps, prog, epi, grid, st);
@@ -1111,6 +1147,15 @@ extern "C" int obman_pack_bf16(const float* w, long long ldw, int rows, int K, f
   pack_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       w, ldw, rows, K, reinterpret_cast<uint32_t*>(out), ld_out);
   return check_launch("pack_bf16_kernel");
+}
+
+// Diagnostics: while buf != NULL every tensor-core kernel launch writes 8 clock64 stamps per CTA into
+// buf[cta * 8 + k] (k = 0 entry, 1 setup done, 2 first / 3 last TMA issued, 4 first operands ready, 5 last MMA
+// issued, 6 accumulator complete, 7 exit | smid << 48).  cap = capacity in 8-byte entries.  NULL switches it off.
+extern "C" int obman_debug_trace(long long* buf, long long cap) {
+  g_trace = buf;
+  g_trace_cap = buf ? cap : 0;
+  return OBMAN_OK;
 }
 
 extern "C" int obman_split_tf32(const float* w, long long n, float* hi, float* lo, void* stream) {

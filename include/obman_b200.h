@@ -112,9 +112,10 @@ int obman_gemm(const float* A, long long lda, const float* W, const float* W_lo,
 /* hi = tf32-rounded w, lo = w - hi (n floats): weights pre-split for the 3xTF32 path whose A operand is
  * staged in tensor memory (pass them as W / W_lo, w / w_lo). */
 int obman_split_tf32(const float* w, long long n, float* hi, float* lo, void* stream);
-/* Diagnostics: while buf != NULL every tensor-core kernel launch writes 8 clock64 stamps per CTA into
- * buf[cta*8 + k] (entry, setup done, first / last TMA issued, first operands ready, last MMA issued, accumulator
- * complete, exit | smid << 48); cap = capacity in 8-byte entries.  NULL switches it off. */
+/* Diagnostics: while buf != NULL every tensor-core kernel launch writes 16 clock64 stamps per CTA into
+ * buf[cta*16 + k] (0 entry, 1 setup done, 2 first / 3 last TMA issued, 4 first operands ready, 5 last MMA issued,
+ * 6 accumulator complete, 7 exit | smid << 48; 8..15 inner phases of one main-loop iteration, see
+ * scripts/trace_kernels.py); cap = capacity in 8-byte entries.  NULL switches it off. */
 int obman_debug_trace(long long* buf, long long cap);
 /* Packed weights of the 3xBF16 path: out (rows, ld_out), ld_out = K rounded up to 32; every 32-element block of
  * a row holds 32 bf16 hi values then 32 bf16 lo = bf16(w - hi) values (the bytes of 32 floats); zero padded. */

@@ -56,6 +56,10 @@ struct GemmProgram {
   int cg_in;            // 32-channel groups per tap of the input (c_in / 32)
   int total_groups;     // num_taps * cg_in
   unsigned mn_lbo, mn_sbo, mn_layout;  // MN-major smem descriptor fields (bytes, bytes, layout type)
+  int grp_per_load;     // bf16 wgrad: consecutive channel groups of a tap fetched by one TMA (divides cg_in)
+  // halo kernel: bytes of one halo box and, per tap, its pixel offset inside the box (dh * (TW + 2) + dw)
+  int halo_bytes;
+  int tap_delta[MAX_TAPS];
 };
 
 struct GemmEpilogue {
@@ -68,7 +72,7 @@ struct GemmEpilogue {
   int accumulate;         // atomicAdd into out instead of store
   // row -> element offset: plain: row * ld ; spatial: n*sN + h*sH + w*sW  (+ column)
   long long ld, sN, sH, sW;
-  // diagnostics (obman_debug_trace): 8 clock64 stamps per CTA, NULL in normal operation
+  // diagnostics (obman_debug_trace): 16 clock64 stamps per CTA, NULL in normal operation
   long long* trace;
   long long trace_cap;
 };
@@ -77,14 +81,14 @@ struct GemmEpilogue {
 __device__ __forceinline__ void trace_stamp(const GemmEpilogue& epi, int k) {
   if (epi.trace == nullptr) return;
   const long long cta = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * blockIdx.z);
-  if ((cta + 1) * 8 > epi.trace_cap) return;
+  if ((cta + 1) * 16 > epi.trace_cap) return;
   long long t = clock64();
   if (k == 7) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     t = (t & 0x0000ffffffffffffLL) | ((long long)smid << 48);
   }
-  epi.trace[cta * 8 + k] = t;
+  epi.trace[cta * 16 + k] = t;
 }
 
 // OCC = CTAs per SM the configuration is sized for: with 2, one CTA's prologue / epilogue overlaps the other's
@@ -166,9 +170,31 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, uint32_t tmem_base,
                           reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0 && !epi.accumulate;
     const int cc = lane & 7;     // 16-byte column chunk handled by this lane after the transpose
     const int rsub = lane >> 3;  // row within each group of 4
+    long long ro[8];             // element offsets of the 8 rows this lane stores (row 4 i + rsub of the warp's 32)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ro[i] = rowinfo[q * 32 + 4 * i + rsub];
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= prog.N) break;  // warp-uniform
+      const int col = n0 + c0 + 4 * cc;
+      const bool colvec = (col + 3 < prog.N) && ptr_ok;
+      // issue every global read of this chunk (residual, ReLU-mask source, bias) before touching the accumulator:
+      // they are independent, so their latencies overlap instead of forming 8 serial round trips
+      float4 add4[8], msk4[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        add4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        msk4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (colvec && ro[i] >= 0 && (ro[i] & 3) == 0) {
+          if (epi.addend) add4[i] = __ldg(reinterpret_cast<const float4*>(epi.addend + ro[i] + col));
+          if (epi.mask_src) msk4[i] = __ldg(reinterpret_cast<const float4*>(epi.mask_src + ro[i] + col));
+        }
+      }
+      float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (epi.bias) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (col + e < prog.N) bias4[e] = __ldg(epi.bias + col + e);
+      }
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
@@ -177,34 +203,22 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, uint32_t tmem_base,
         *reinterpret_cast<uint4*>(wbase + lane * 128 + ((c ^ (lane & 7)) << 4)) =
             make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       __syncwarp();
-      const int col = n0 + c0 + 4 * cc;
-      float bias4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (epi.bias) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) if (col + e < prog.N) bias4[e] = __ldg(epi.bias + col + e);
-      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = 4 * i + rsub;
-        const long long row_off = rowinfo[q * 32 + rr];
+        const long long row_off = ro[i];
         if (row_off < 0 || col >= prog.N) continue;
         const float4 a = *reinterpret_cast<const float4*>(wbase + rr * 128 + ((cc ^ (rr & 7)) << 4));
         float x[4] = {epi.alpha * a.x + bias4[0], epi.alpha * a.y + bias4[1], epi.alpha * a.z + bias4[2],
                       epi.alpha * a.w + bias4[3]};
-        if ((col + 3 < prog.N) && ptr_ok && ((row_off & 3) == 0)) {
-          if (epi.addend) {
-            const float4 a4 = *reinterpret_cast<const float4*>(epi.addend + row_off + col);
-            x[0] += a4.x; x[1] += a4.y; x[2] += a4.z; x[3] += a4.w;
-          }
+        if (colvec && ((row_off & 3) == 0)) {
+          x[0] += add4[i].x; x[1] += add4[i].y; x[2] += add4[i].z; x[3] += add4[i].w;
           if (epi.relu) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
           }
-          if (epi.mask_src) {
-            const float4 m4 = *reinterpret_cast<const float4*>(epi.mask_src + row_off + col);
-            x[0] = m4.x > 0.f ? x[0] : 0.f; x[1] = m4.y > 0.f ? x[1] : 0.f;
-            x[2] = m4.z > 0.f ? x[2] : 0.f; x[3] = m4.w > 0.f ? x[3] : 0.f;
-          }
+          x[0] = msk4[i].x > 0.f ? x[0] : 0.f; x[1] = msk4[i].y > 0.f ? x[1] : 0.f;
+          x[2] = msk4[i].z > 0.f ? x[2] : 0.f; x[3] = msk4[i].w > 0.f ? x[3] : 0.f;
           *reinterpret_cast<float4*>(epi.out + row_off + col) = make_float4(x[0], x[1], x[2], x[3]);
         } else {
 #pragma unroll
@@ -246,7 +260,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   uint64_t* accum = bars + 3 * S;   // accumulator complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
   int n_iters = prog.num_taps * prog.kblocks;
   if (threadIdx.x == 0) trace_stamp(epi, 0);
@@ -291,7 +305,9 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   __syncthreads();
   if (CL > 1) cluster_sync_all();   // peers' barriers must exist before any multicast / remote arrive
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // read through a shuffle: tells the compiler the value is warp-uniform, so the tcgen05 operands derived
+  // from it live in uniform registers (otherwise every MMA is wrapped in an elect / broadcast loop)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (threadIdx.x == 0) trace_stamp(epi, 1);
 
   // stage layout.  SS: A | B | A_lo | B_lo.   TS: A_raw | B_hi | B_lo.
@@ -446,12 +462,12 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(&full[s], ph);
-        const uint8_t* row = stage_a(s) + r * 128;
+        const uint32_t row = smem_u32(stage_a(s)) + r * 128;
         if (TS == 2) {
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
+            const float4 v = lds_v4(row + ((j ^ (r & 7)) << 4));
             split_bf16x2(v.x, v.y, hi[2 * j], lo[2 * j]);
             split_bf16x2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
           }
@@ -465,7 +481,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         uint32_t hi[32], lo[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 v = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 4));
+          const float4 v = lds_v4(row + ((j ^ (r & 7)) << 4));
           const float h0f = to_tf32_rna(v.x), h1f = to_tf32_rna(v.y), h2f = to_tf32_rna(v.z), h3f = to_tf32_rna(v.w);
           hi[4 * j + 0] = __float_as_uint(h0f); lo[4 * j + 0] = __float_as_uint(v.x - h0f);
           hi[4 * j + 1] = __float_as_uint(h1f); lo[4 * j + 1] = __float_as_uint(v.y - h1f);
@@ -567,6 +583,8 @@ static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const Gemm
 //     a second ring, hand-swizzled for the SW128 descriptor,
 // so the MMA stream is the one of the fprop kernels.  The raw ring is released as soon as it has been read, the
 // converted ring when its MMAs retire.  SWAP = 1: rows = stacked taps, columns = dY channels (c_out <= 64).
+constexpr int TRACE_IT = 12;   // main-loop iteration whose inner phases obman_debug_trace records (slots 8..15)
+
 template <int BN, int SWAP, int OCC>
 struct WgradCfg {
   static constexpr int A_RAW = 128 * 128;              // 4 groups x 32 pixels x 32 channels fp32
@@ -582,14 +600,26 @@ struct WgradCfg {
   static constexpr int TMEM_NEED = BN + C * 32;
   static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
   static constexpr int SMEM_BYTES = R * RAW_BYTES + C * B_CONV + 1024 + 256;
+  // one splitter thread per operand row: 4 warps for the 128 A rows (also the epilogue warps), BN / 32 for B
+  static constexpr int SPLIT_WARPS = 4 + BN / 32;
+  static constexpr int SPLIT_THREADS = SPLIT_WARPS * 32;
+  static constexpr int THREADS = 64 + SPLIT_THREADS;
 };
 
+// 32 pixels of one channel (column `lane` of a 32 x 32 fp32 group at shared address `grp`) -> 16 packed bf16x2 hi / lo
+__device__ __forceinline__ void split_column(uint32_t grp, int lane, uint32_t* hi, uint32_t* lo) {
+  const uint32_t a = grp + (uint32_t)lane * 4u;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) split_bf16x2(lds_f32(a + (2 * p) * 128), lds_f32(a + (2 * p + 1) * 128), hi[p], lo[p]);
+}
+
 template <int BN, int SWAP, int OCC>
-__global__ void __launch_bounds__(GEMM_THREADS, OCC)
+__global__ void __launch_bounds__(WgradCfg<BN, SWAP, OCC>::THREADS, OCC)
 wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, const GemmEpilogue epi) {
   using Cfg = WgradCfg<BN, SWAP, OCC>;
   static_assert(Cfg::C >= 2, "needs at least two converted stages");
   constexpr int R = Cfg::R, C = Cfg::C;
+  constexpr int TAP_GROUPS = SWAP ? BM / 32 : BN / 32;   // 32-channel groups of the stacked-tap operand per tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* conv_base = smem + R * Cfg::RAW_BYTES;
@@ -601,7 +631,7 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
   uint64_t* accum = bars + 2 * R + 2 * C;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
   const int m0 = (blockIdx.x / prog.n_tiles) * BM;
   const int n0 = (blockIdx.x % prog.n_tiles) * BN;
@@ -613,8 +643,8 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
   if (threadIdx.x == 0) trace_stamp(epi, 0);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&rawfree[i], 128); }
-    for (int i = 0; i < C; ++i) { mbar_init(&conv[i], 128); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < R; ++i) { mbar_init(&full[i], 1); mbar_init(&rawfree[i], Cfg::SPLIT_THREADS); }
+    for (int i = 0; i < C; ++i) { mbar_init(&conv[i], Cfg::SPLIT_THREADS); mbar_init(&empty[i], 1); }
     mbar_init(accum, 1);
     fence_barrier_init();
   }
@@ -625,37 +655,54 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   if (threadIdx.x == 0) trace_stamp(epi, 1);
   auto raw_a = [&](int i) { return smem + i * Cfg::RAW_BYTES; };
   auto raw_b = [&](int i) { return smem + i * Cfg::RAW_BYTES + Cfg::A_RAW; };
   auto conv_b = [&](int i) { return conv_base + i * Cfg::B_CONV; };
   // groups of 32 channels of the stacked-tap operand that exist in this tile (B normally, A when swapped)
-  const int valid_groups = SWAP ? min(BM / 32, prog.total_groups - m0 / 32) : min(BN / 32, prog.total_groups - n0 / 32);
+  const int valid_groups = min(TAP_GROUPS, prog.total_groups - (SWAP ? m0 : n0) / 32);
 
   if (warp == 0) {
     if (lane == 0) {
       tma_prefetch_desc(&maps.a[0]);
+      // one TMA per `gl` consecutive channel groups of a tap (gl = prog.grp_per_load divides cg_in and the tile)
+      const int gl = prog.grp_per_load;
+      const int nl = valid_groups / gl;
+      const CUtensorMap* lmap[TAP_GROUPS];
+      int ldw[TAP_GROUPS], ldh[TAP_GROUPS], lcg[TAP_GROUPS];
+#pragma unroll
+      for (int j = 0; j < TAP_GROUPS; ++j) {
+        const int g = (SWAP ? m0 : n0) / 32 + j * gl;
+        const int tap = (j < nl) ? g / prog.cg_in : 0;
+        lmap[j] = &maps.a[1 + prog.tap_map[tap]];
+        ldw[j] = prog.tap_dw[tap];
+        ldh[j] = prog.tap_dh[tap];
+        lcg[j] = g - tap * prog.cg_in;
+      }
+      int pb = pb_begin;
+      int bw = pb % prog.kblocks_w; pb /= prog.kblocks_w;
+      int bh = pb % prog.kblocks_h;
+      int bn = pb / prog.kblocks_h;
       for (int it = 0; it < n_iters; ++it) {
         const int rs = it % R;
         mbar_wait(&rawfree[rs], ((it / R) & 1) ^ 1);
+        if (it == TRACE_IT) trace_stamp(epi, 8);
         mbar_arrive_expect_tx(&full[rs], 4096 * valid_groups + (SWAP ? Cfg::B_RAW : Cfg::A_RAW));
-        int pb = pb_begin + it;
-        const int bw = pb % prog.kblocks_w; pb /= prog.kblocks_w;
-        const int bh = pb % prog.kblocks_h; pb /= prog.kblocks_h;
-        const int pw = bw * prog.kTW, ph_ = bh * prog.kTH, pn = pb * prog.kTN;
+        const int pw = bw * prog.kTW, ph_ = bh * prog.kTH, pn = bn * prog.kTN;
         uint8_t* taps_dst = SWAP ? raw_a(rs) : raw_b(rs);
-        const int g0 = (SWAP ? m0 : n0) / 32;
-        for (int j = 0; j < valid_groups; ++j) {
-          const int g = g0 + j;
-          const int tap = g / prog.cg_in, cg = g - tap * prog.cg_in;
-          tma_load_5d(taps_dst + j * 4096, &maps.a[1 + prog.tap_map[tap]], &full[rs], 0, pw + prog.tap_dw[tap],
-                      ph_ + prog.tap_dh[tap], pn, cg);
+#pragma unroll
+        for (int j = 0; j < TAP_GROUPS; ++j) {
+          if (j < nl) tma_load_5d(taps_dst + j * gl * 4096, lmap[j], &full[rs], 0, pw + ldw[j], ph_ + ldh[j], pn, lcg[j]);
         }
         tma_load_5d(SWAP ? raw_b(rs) : raw_a(rs), &maps.a[0], &full[rs], 0, pw, ph_, pn, (SWAP ? n0 : m0) / 32);
         if (it == 0) trace_stamp(epi, 2);
+        if (it == TRACE_IT) trace_stamp(epi, 9);
         if (it == n_iters - 1) trace_stamp(epi, 3);
+        if (++bw == prog.kblocks_w) {
+          bw = 0;
+          if (++bh == prog.kblocks_h) { bh = 0; ++bn; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -666,6 +713,7 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
       tc_fence_after();
       if (lane == 0) {
         if (it == 0) trace_stamp(epi, 4);
+        if (it == TRACE_IT) trace_stamp(epi, 13);
         const uint32_t b = smem_u32(conv_b(cs));
         const uint32_t ta = tmem_base + (uint32_t)(BN + 32 * cs);
 #pragma unroll
@@ -677,65 +725,68 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
           umma_f16_ts(tmem_base, ta + k * 8, db, idesc, 1u);
         }
         umma_commit(&empty[cs]);
+        if (it == TRACE_IT) trace_stamp(epi, 14);
         if (it == n_iters - 1) { umma_commit(accum); trace_stamp(epi, 5); }
       }
       __syncwarp();
     }
-  } else {
+  } else if (warp < 6) {
+    // ---- A rows: warps 2..5, TMEM lane quadrant = warp % 4; afterwards the epilogue ----
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const int a_groups = SWAP ? valid_groups : BM / 32;
+    for (int it = 0; it < n_iters; ++it) {
+      const int rs = it % R, cs = it % C;
+      mbar_wait(&full[rs], (it / R) & 1);
+      if (r == 0 && it == TRACE_IT) trace_stamp(epi, 10);
+      if (r == 0 && it == TRACE_IT + 1) trace_stamp(epi, 15);
+      mbar_wait(&empty[cs], ((it / C) & 1) ^ 1);
+      tc_fence_after();
+      if (r == 0 && it == TRACE_IT) trace_stamp(epi, 11);
+      uint32_t hi[16], lo[16];
+      if (q < a_groups) {
+        split_column(smem_u32(raw_a(rs)) + q * 4096, lane, hi, lo);
+      } else {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) hi[p] = lo[p] = 0u;
+      }
+      mbar_arrive(&rawfree[rs]);
+      const uint32_t dst = lane_base + (uint32_t)(BN + 32 * cs);
+      tmem_st_32x16(dst, hi);
+      tmem_st_32x16(dst + 16, lo);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&conv[cs]);
+      if (r == 0 && it == TRACE_IT) trace_stamp(epi, 12);
+    }
+    gemm_epilogue<BN, SWAP ? 2 : 1>(smem, tmem_base, accum, prog, epi, m0, n0, 0, 0, 0, q, lane, r);
+  } else {
+    // ---- B rows: one warp per 32-channel group; K-major rows [32 hi | 32 lo], hand-swizzled for SW128 ----
+    const int g = warp - 6;
+    const int n = g * 32 + lane;
     const int b_groups = SWAP ? BN / 32 : valid_groups;
     for (int it = 0; it < n_iters; ++it) {
       const int rs = it % R, cs = it % C;
       mbar_wait(&full[rs], (it / R) & 1);
       mbar_wait(&empty[cs], ((it / C) & 1) ^ 1);
-      tc_fence_after();
-      {
-        // A: channel r of the tile = column `lane` of group q, pixels along K
-        uint32_t hi[16], lo[16];
-        if (q < a_groups) {
-          const float* src = reinterpret_cast<const float*>(raw_a(rs)) + q * 1024 + lane;
+      uint32_t hi[16], lo[16];
+      if (g < b_groups) {
+        split_column(smem_u32(raw_b(rs)) + g * 4096, lane, hi, lo);
+      } else {
 #pragma unroll
-          for (int p = 0; p < 16; ++p) split_bf16x2(src[(2 * p) * 32], src[(2 * p + 1) * 32], hi[p], lo[p]);
-        } else {
-#pragma unroll
-          for (int p = 0; p < 16; ++p) hi[p] = lo[p] = 0u;
-        }
-        const uint32_t dst = lane_base + (uint32_t)(BN + 32 * cs);
-        tmem_st_32x16(dst, hi);
-        tmem_st_32x16(dst + 16, lo);
-      }
-#pragma unroll
-      for (int i = 0; i < (BN + 127) / 128; ++i) {
-        const int n = r + 128 * i;       // B row (channel of the tile)
-        if (n < BN) {
-          uint32_t hi[16], lo[16];
-          const int g = n >> 5;
-          if (g < b_groups) {
-            const float* src = reinterpret_cast<const float*>(raw_b(rs)) + g * 1024 + lane;
-#pragma unroll
-            for (int p = 0; p < 16; ++p) split_bf16x2(src[(2 * p) * 32], src[(2 * p + 1) * 32], hi[p], lo[p]);
-          } else {
-#pragma unroll
-            for (int p = 0; p < 16; ++p) hi[p] = lo[p] = 0u;
-          }
-          uint8_t* row = conv_b(cs) + n * 128;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            *reinterpret_cast<uint4*>(row + ((j ^ (n & 7)) << 4)) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            *reinterpret_cast<uint4*>(row + (((j + 4) ^ (n & 7)) << 4)) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-          }
-        }
+        for (int p = 0; p < 16; ++p) hi[p] = lo[p] = 0u;
       }
       mbar_arrive(&rawfree[rs]);
+      const uint32_t row = smem_u32(conv_b(cs)) + n * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sts_v4(row + ((j ^ (n & 7)) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+        sts_v4(row + (((j + 4) ^ (n & 7)) << 4), lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+      }
       fence_proxy_async_smem();
-      tmem_st_wait();
-      tc_fence_before();
       mbar_arrive(&conv[cs]);
     }
-    gemm_epilogue<BN, SWAP ? 2 : 1>(smem, tmem_base, accum, prog, epi, m0, n0, 0, 0, 0, q, lane, r);
   }
   tc_fence_before();
   __syncthreads();
@@ -757,9 +808,205 @@ static int launch_wgrad_bf16(const GemmMaps& maps, const GemmProgram& prog, cons
     }
     attr = true;
   }
-  wgrad_bf16_kernel<BN, SWAP, OCC><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
+  wgrad_bf16_kernel<BN, SWAP, OCC><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
   return check_launch("wgrad_bf16_kernel");
 }
+
+// ---- 3x3-neighbourhood convolution with the input tile shared by all taps ("halo" kernel) -------------------------
+// The shifted-box kernel above fetches the A tile once per tap: 9 x 16 KB per 32 input channels, which (with the
+// weight tile) runs into the L2->SM fabric limit (~60 B/clk/SM measured, profiles/cta_phases_r1_bf16.txt) long
+// before the tensor pipe is busy.  Here ONE (TN, TH+2, TW+2, 32ch) box with a one-pixel halo is fetched per 32
+// input channels and every tap is a different row offset into it: A traffic drops 6.4x, total L2->SM bytes 1.7x
+// (C_out = 128) to 2.2x (C_out = 64).  Rings: halo boxes (RA slots, released by the splitter warps), weight tiles
+// + A operands in tensor memory (C slots, released by tcgen05.commit).  Stride-1 taps with |dh|, |dw| <= 1 only
+// (3x3 forward and its data gradient); everything else takes the shifted-box kernel.
+template <int BN, int OCC>
+struct HaloCfg {
+  static constexpr int HALO_BYTES = 25600;   // up to 200 halo pixels x 32 channels fp32 (multiple of 1024: swizzle phase)
+  static constexpr int RA = 2;
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int BUDGET = (OCC == 2 ? 104 : 200) * 1024;
+  static constexpr int C_SMEM = (BUDGET - RA * HALO_BYTES) / B_TILE;
+  static constexpr int C_TMEM = ((OCC == 2 ? 256 : 512) - BN) / 32;
+  static constexpr int C0 = C_SMEM < C_TMEM ? C_SMEM : C_TMEM;
+  static constexpr int C = C0 > 8 ? 8 : C0;
+  static constexpr int TMEM_NEED = BN + C * 32;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
+  static constexpr int SMEM_BYTES = RA * HALO_BYTES + C * B_TILE + 1024 + 256;
+};
+
+template <int BN, int OCC>
+__global__ void __launch_bounds__(GEMM_THREADS, OCC)
+conv_halo_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, const GemmEpilogue epi) {
+  using Cfg = HaloCfg<BN, OCC>;
+  static_assert(Cfg::C >= 2, "needs at least two weight / operand slots");
+  constexpr int RA = Cfg::RA, C = Cfg::C;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* bring = smem + RA * Cfg::HALO_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bring + C * Cfg::B_TILE);
+  uint64_t* afull = bars;                  // [RA] halo box landed
+  uint64_t* afree = bars + RA;             // [RA] splitter warps are done with the halo box
+  uint64_t* bfull = bars + 2 * RA;         // [C] weight tile landed
+  uint64_t* conv = bars + 2 * RA + C;      // [C] A operand (bf16 hi | lo) written to tensor memory
+  uint64_t* empty = bars + 2 * RA + 2 * C; // [C] MMAs reading slot c retired
+  uint64_t* accum = bars + 2 * RA + 3 * C;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
+  const int lane = threadIdx.x & 31;
+  const int T = prog.num_taps, KB = prog.kblocks;
+  const int n_iters = T * KB;
+  if (threadIdx.x == 0) trace_stamp(epi, 0);
+  int t_ = blockIdx.x;
+  const int tw_i = t_ % prog.tiles_w; t_ /= prog.tiles_w;
+  const int th_i = t_ % prog.tiles_h; t_ /= prog.tiles_h;
+  const int n_img0 = t_ * prog.TN, h0 = th_i * prog.TH, w0 = tw_i * prog.TW;
+  const int n0 = blockIdx.y * BN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RA; ++i) { mbar_init(&afull[i], 1); mbar_init(&afree[i], 128); }
+    for (int i = 0; i < C; ++i) { mbar_init(&bfull[i], 1); mbar_init(&conv[i], 128); mbar_init(&empty[i], 1); }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // read through a shuffle: tells the compiler the value is warp-uniform, so the tcgen05 operands derived
+  // from it live in uniform registers (otherwise every MMA is wrapped in an elect / broadcast loop)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  if (threadIdx.x == 0) trace_stamp(epi, 1);
+  auto halo = [&](int i) { return smem + i * Cfg::HALO_BYTES; };
+  auto bslot = [&](int i) { return bring + i * Cfg::B_TILE; };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.a[0]);
+      tma_prefetch_desc(&maps.b);
+      // the halo box of K block kb + 1 is requested while the taps of kb are still being fed (at tap `pre`): by
+      // then the splitter warps have long released the slot (they run C taps behind this thread)
+      const int pre = (C < T - 1) ? C : T - 1;
+      mbar_arrive_expect_tx(&afull[0], prog.halo_bytes);
+      tma_load_4d(halo(0), &maps.a[0], &afull[0], 0, w0 - 1, h0 - 1, n_img0);
+      int it = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        for (int tap = 0; tap < T; ++tap, ++it) {
+          const int c = it % C;
+          mbar_wait(&empty[c], ((it / C) & 1) ^ 1);
+          mbar_arrive_expect_tx(&bfull[c], Cfg::B_TILE);
+          tma_load_2d(bslot(c), &maps.b, &bfull[c], prog.tap_bk[tap] + kb * BK, n0);
+          if (it == 0) trace_stamp(epi, 2);
+          if (tap == pre && kb + 1 < KB) {
+            const int a = (kb + 1) % RA;
+            mbar_wait(&afree[a], (((kb + 1) / RA) & 1) ^ 1);
+            mbar_arrive_expect_tx(&afull[a], prog.halo_bytes);
+            tma_load_4d(halo(a), &maps.a[0], &afull[a], (kb + 1) * BK, w0 - 1, h0 - 1, n_img0);
+          }
+        }
+      }
+      trace_stamp(epi, 3);
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(BM, BN);
+    for (int it = 0; it < n_iters; ++it) {
+      const int c = it % C;
+      const uint32_t ph = (it / C) & 1;
+      mbar_wait(&bfull[c], ph);
+      if (lane == 0 && it == TRACE_IT) trace_stamp(epi, 11);
+      mbar_wait(&conv[c], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        if (it == 0) trace_stamp(epi, 4);
+        if (it == TRACE_IT) trace_stamp(epi, 12);
+        if (it == TRACE_IT + 1) trace_stamp(epi, 15);
+        const uint32_t b = smem_u32(bslot(c));
+        const uint32_t ta = tmem_base + (uint32_t)(BN + 32 * c);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint64_t db = umma_desc(b + k * 32, 16, 1024, 2);
+          const uint64_t dbl = umma_desc(b + 64 + k * 32, 16, 1024, 2);
+          umma_f16_ts(tmem_base, ta + 16 + k * 8, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_f16_ts(tmem_base, ta + k * 8, dbl, idesc, 1u);
+          umma_f16_ts(tmem_base, ta + k * 8, db, idesc, 1u);
+        }
+        umma_commit(&empty[c]);
+        if (it == TRACE_IT) trace_stamp(epi, 13);
+        if (it == n_iters - 1) { umma_commit(accum); trace_stamp(epi, 5); }
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    // pixel of this row inside the halo box (box = TN x (TH+2) x (TW+2) pixels, 128 bytes each, SW128)
+    const int tw = r % prog.TW, th = (r / prog.TW) % prog.TH, tn = r / (prog.TW * prog.TH);
+    const int hp0 = (tn * (prog.TH + 2) + th + 1) * (prog.TW + 2) + tw + 1;
+    int it = 0;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int a = kb % RA;
+      mbar_wait(&afull[a], (kb / RA) & 1);
+      const uint32_t box = smem_u32(halo(a));
+      for (int tap = 0; tap < T; ++tap, ++it) {
+        const int c = it % C;
+        mbar_wait(&empty[c], ((it / C) & 1) ^ 1);
+        tc_fence_after();
+        if (r == 0 && it == TRACE_IT) trace_stamp(epi, 8);
+        if (r == 0 && it == TRACE_IT + 1) trace_stamp(epi, 14);
+        const int hp = hp0 + prog.tap_delta[tap];
+        const uint32_t row = box + hp * 128;
+        const int sw = hp & 7;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 v = lds_v4(row + ((j ^ sw) << 4));
+          split_bf16x2(v.x, v.y, hi[2 * j], lo[2 * j]);
+          split_bf16x2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        const uint32_t dst = lane_base + (uint32_t)(BN + 32 * c);
+        if (r == 0 && it == TRACE_IT) trace_stamp(epi, 9);
+        tmem_st_32x16(dst, hi);
+        tmem_st_32x16(dst + 16, lo);
+        tmem_st_wait();
+        if (r == 0 && it == TRACE_IT) trace_stamp(epi, 10);
+        tc_fence_before();
+        mbar_arrive(&conv[c]);
+      }
+      mbar_arrive(&afree[a]);
+    }
+    gemm_epilogue<BN, 0>(smem, tmem_base, accum, prog, epi, 0, n0, n_img0, h0, w0, q, lane, r);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (threadIdx.x == 0) trace_stamp(epi, 7);
+}
+
+template <int BN, int OCC>
+static int launch_conv_halo(const GemmMaps& maps, const GemmProgram& prog, const GemmEpilogue& epi, dim3 grid,
+                            cudaStream_t st) {
+  using Cfg = HaloCfg<BN, OCC>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("conv_halo: cudaFuncSetAttribute(%d bytes) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      return OBMAN_ERR_CUDA;
+    }
+    attr = true;
+  }
+  conv_halo_kernel<BN, OCC><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
+  return check_launch("conv_halo_kernel");
+}
+
+static long long* g_trace = nullptr;
+static long long g_trace_cap = 0;
 
 // Cluster size the TS path will run with for a grid of grid_x row tiles (the weight tensor maps are built with a
 // box of BN / cluster rows, so the host code asks before encoding them).
@@ -830,9 +1077,6 @@ static int pick_bn(int N, long long m_tiles) {
   }
   return best;
 }
-
-static long long* g_trace = nullptr;
-static long long g_trace_cap = 0;
 
 static bool ts_enabled() {
   static int v = -1;
@@ -928,6 +1172,63 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
   OBMAN_REQUIRE(passes == 1 || passes == 3 || passes == OBMAN_PREC_3XBF16, "obman_conv_nhwc: passes must be 1, 2 or 3");
   OBMAN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)w_lo & 15) == 0,
                 "obman_conv_nhwc: x/w must be 16-byte aligned");
+  {
+    // halo kernel: stride-1 taps inside the 3x3 neighbourhood, packed bf16 weights
+    static int halo_on = -1;
+    if (halo_on < 0) {
+      const char* e = getenv("OBMAN_CONV_HALO");
+      halo_on = (e && e[0] == '1') ? 1 : 0;   // off by default: measured no faster (the loop is MMA-issue bound)
+    }
+    bool ok = halo_on && passes == OBMAN_PREC_3XBF16 && in_step == 1 && num_taps >= 2 && c_in % 32 == 0;
+    for (int t = 0; ok && t < num_taps; ++t) ok = tap_dh[t] >= -1 && tap_dh[t] <= 1 && tap_dw[t] >= -1 && tap_dw[t] <= 1;
+    int hTW = 1;
+    while (hTW * 2 <= w_out && hTW * 2 <= 16) hTW *= 2;
+    int hTH = 1;
+    while (hTH * 2 <= h_out && hTW * hTH * 2 <= 128) hTH *= 2;
+    const int hTN = 128 / (hTW * hTH);
+    const int halo_pix = (hTW + 2) * (hTH + 2) * hTN;
+    ok = ok && hTW >= 8 && halo_pix * 128 <= HaloCfg<64, 2>::HALO_BYTES;
+    if (ok) {
+      GemmProgram prog;
+      memset(&prog, 0, sizeof(prog));
+      prog.spatial = 1;
+      prog.num_taps = num_taps;
+      prog.kblocks = c_in / BK;
+      prog.N = c_out;
+      prog.TN = hTN; prog.TH = hTH; prog.TW = hTW;
+      prog.tiles_h = (h_out + hTH - 1) / hTH;
+      prog.tiles_w = (w_out + hTW - 1) / hTW;
+      prog.n_img = n_img; prog.h_out = h_out; prog.w_out = w_out;
+      prog.halo_bytes = halo_pix * 128;
+      for (int t = 0; t < num_taps; ++t) {
+        prog.tap_bk[t] = (tap_wslot ? tap_wslot[t] : t) * c_in;
+        prog.tap_delta[t] = tap_dh[t] * (hTW + 2) + tap_dw[t];
+      }
+      const long long m_tiles = (long long)((n_img + hTN - 1) / hTN) * prog.tiles_h * prog.tiles_w;
+      const int BN = c_out <= 64 ? 64 : 128;
+      GemmMaps maps;
+      memset(&maps, 0, sizeof(maps));
+      uint64_t dims[4] = {(uint64_t)c_in, (uint64_t)w_in, (uint64_t)h_in, (uint64_t)n_img};
+      uint64_t strides[3] = {(uint64_t)c_in * 4, (uint64_t)w_in * c_in * 4, (uint64_t)h_in * w_in * c_in * 4};
+      uint32_t box[4] = {BK, (uint32_t)(hTW + 2), (uint32_t)(hTH + 2), (uint32_t)hTN};
+      int rc = make_tensor_map(&maps.a[0], x, 4, dims, strides, box);
+      if (rc) return rc;
+      uint64_t dimsb[2] = {(uint64_t)w_slots * (uint64_t)c_in, (uint64_t)c_out};
+      uint64_t stridesb[1] = {dimsb[0] * 4};
+      uint32_t boxb[2] = {BK, (uint32_t)BN};
+      rc = make_tensor_map(&maps.b, w, 2, dimsb, stridesb, boxb);
+      if (rc) return rc;
+      GemmEpilogue epi;
+      memset(&epi, 0, sizeof(epi));
+      epi.out = out; epi.bias = bias; epi.addend = addend; epi.mask_src = mask_src;
+      epi.alpha = 1.f; epi.relu = relu; epi.accumulate = 0;
+      epi.sN = o_sN; epi.sH = o_sH; epi.sW = o_sW;
+      epi.trace = g_trace; epi.trace_cap = g_trace_cap;
+      dim3 grid((unsigned)m_tiles, (unsigned)((c_out + BN - 1) / BN), 1);
+      if (BN == 64) return launch_conv_halo<64, 2>(maps, prog, epi, grid, (cudaStream_t)stream);
+      return launch_conv_halo<128, 2>(maps, prog, epi, grid, (cudaStream_t)stream);
+    }
+  }
   // output tile shape: TW = largest power of two <= min(w_out, 128) ... keep TN*TH*TW == 128
   int TW = 1;
   while (TW * 2 <= w_out && TW * 2 <= 128) TW *= 2;
@@ -1050,6 +1351,13 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
     BN = 64;
     prog.n_tiles = 1;
   }
+  // 3xBF16: one TMA fetches `grp_per_load` consecutive 32-channel groups of a tap (largest power of two that
+  // divides c_in / 32 and the tile's group count); the 3xTF32 kernels load group by group
+  prog.grp_per_load = 1;
+  if (bf) {
+    const int cap = swapped ? BM / 32 : 8;
+    while (prog.grp_per_load * 2 <= cap && prog.cg_in % (prog.grp_per_load * 2) == 0) prog.grp_per_load *= 2;
+  }
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
   {
@@ -1074,7 +1382,7 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
     uint64_t dims[5] = {32, (uint64_t)(w_in / in_step), (uint64_t)(h_in / in_step), (uint64_t)n_img, (uint64_t)(c_in / 32)};
     uint64_t strides[4] = {(uint64_t)c_in * 4 * in_step, (uint64_t)w_in * c_in * 4 * in_step,
                            (uint64_t)h_in * w_in * c_in * 4, 128};
-    uint32_t box[5] = {32, (uint32_t)kTW, (uint32_t)kTH, (uint32_t)kTN, 1};
+    uint32_t box[5] = {32, (uint32_t)kTW, (uint32_t)kTH, (uint32_t)kTN, (uint32_t)prog.grp_per_load};
     const float* base = x + ((long long)py * w_in + px) * c_in;
     int rc = make_tensor_map(&maps.a[1 + ph], base, 5, dims, strides, box, mn_swizzle);
     if (rc) return rc;
@@ -1150,7 +1458,7 @@ extern "C" int obman_pack_bf16(const float* w, long long ldw, int rows, int K, f
 }
 
 // Diagnostics: while buf != NULL every tensor-core kernel launch writes 8 clock64 stamps per CTA into
-// buf[cta * 8 + k] (k = 0 entry, 1 setup done, 2 first / 3 last TMA issued, 4 first operands ready, 5 last MMA
+// buf[cta * 16 + k] (k = 0 entry, 1 setup done, 2 first / 3 last TMA issued, 4 first operands ready, 5 last MMA
 // issued, 6 accumulator complete, 7 exit | smid << 48).  cap = capacity in 8-byte entries.  NULL switches it off.
 extern "C" int obman_debug_trace(long long* buf, long long cap) {
   g_trace = buf;

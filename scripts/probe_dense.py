@@ -217,6 +217,11 @@ CASES.update({
     "conv3x3_s2_32_64_128_b3": lambda: case_conv(2, 32, 64, 128, 3, 2, 2),
     "conv1x1_s2_32_64_128_b3": lambda: case_conv(2, 32, 64, 128, 1, 2, 2),
     "small_conv3x3_s1_2_512_512_b3": lambda: case_conv(2, 2, 512, 512, 3, 1, 2, True),
+    "conv3x3_s1_20_96_160_b3_epi": lambda: case_conv(2, 20, 96, 160, 3, 1, 2, True),
+    "conv3x3_s1_16_256_256_b3": lambda: case_conv(3, 16, 256, 256, 3, 1, 2),
+    "conv3x3_s1_12_64_64_b3": lambda: case_conv(5, 12, 64, 64, 3, 1, 2),
+    "dgrad3x3_s1_20_96_160_b3": lambda: case_dgrad(2, 20, 96, 160, 3, 1, 2),
+    "dgrad3x3_s1_8_512_512_b3": lambda: case_dgrad(3, 8, 512, 512, 3, 1, 2),
     "small_dgrad3x3_s2_4_256_512_b3": lambda: case_dgrad(2, 4, 256, 512, 3, 2, 2),
     "dgrad3x3_s1_16_64_64_b3": lambda: case_dgrad(2, 16, 64, 64, 3, 1, 2),
     "dgrad3x3_s2_32_64_128_b3": lambda: case_dgrad(2, 32, 64, 128, 3, 2, 2),

@@ -75,7 +75,10 @@ NAMES = ["setup", "first TMA issued", "all TMA issued", "first operands ready", 
 def main():
     cap = 1 << 22
     buf = torch.zeros(cap, dtype=torch.int64, device="cuda")
+    only = os.environ.get("TRACE_ONLY")
     for name, fn in CASES:
+        if only and only not in name:
+            continue
         fn()  # warm (tensor maps, attributes, L2)
         torch.cuda.synchronize()
         buf.zero_()
@@ -86,8 +89,11 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         call("obman_debug_trace", None, 0)
-        t = buf.view(-1, 8).cpu()
-        t = t[t[:, 0] != 0]
+        t = buf.view(-1, 16).cpu()
+        fine = (t[:, 8:16] & 0x0000ffffffffffff).double()
+        keep = t[:, 0] != 0
+        t = t[keep]
+        fine = fine[keep]
         smid = (t[:, 7] >> 48) & 0xffff
         t7 = t[:, 7] & 0x0000ffffffffffff
         t = torch.cat([t[:, :7] & 0x0000ffffffffffff, t7[:, None]], 1).double()
@@ -101,7 +107,19 @@ def main():
         for k in order:
             d = t[:, k] - t[:, 0]
             print("      %-34s +%8.0f clk (median %8.0f)" % (labels[k], d.mean(), d.median()))
-        kernel_span = (t[:, 7].max() - t[:, 0].min())
+        if (fine[:, 0] > 0).any():
+            ok = fine[:, 0] > 0
+            f = fine[ok]
+            wg = name.startswith("wgrad")
+            names = ["producer: raw slot free (it=12)", "producer: loads issued", "splitter: raw tile landed",
+                     "splitter: converted slot free", "splitter: conversion done", "MMA warp: operands ready",
+                     "MMA warp: 6 MMAs + commit issued", "splitter: raw tile landed (it=13)"] if wg else [
+                     "splitter: slot free (it=12)", "splitter: row read + split done", "splitter: TMEM store complete",
+                     "MMA warp: weight tile landed", "MMA warp: A operand ready", "MMA warp: 6 MMAs + commit issued",
+                     "splitter: slot free (it=13)", "MMA warp: A operand ready (it=13)"]
+            for k in range(8):
+                d = f[:, k] - f[:, 0]
+                print("      [it 12] %-38s %+8.0f clk (median %+8.0f)" % (names[k], d.mean(), d.median()))
         per_sm = {}
         for s, a, b in zip(smid.tolist(), t[:, 0].tolist(), t[:, 7].tolist()):
             lo, hi, n = per_sm.get(s, (a, b, 0))

@@ -183,10 +183,27 @@ int obman_pointmlp_l1_fwd(const float* G, long long g_bstride, const float* F, i
 /* g (B,N, ld) -> gF[b,c] = sum_n g, gG[n,c] = sum_b g (gG may be NULL). */
 int obman_pointmlp_l1_bwd(const float* g, int B, int N, int C, int ld, float* gF, float* gG,
                           void* stream);
-/* Fused torch.optim.Adam step (traineval.py:113-116) on flat fp32 buffers; g is multiplied by grad_scale.
- * step_dev: device float holding the 1-based step number (device memory so that CUDA graphs can replay it). */
+/* Cotangent-Laplacian regulariser (laplacianloss.py:24-41: loss = mean_{b,i} ||(L V_b)_i||_2; L built once from the
+ * unit icosphere, laplacianloss.py:100-131).  L is passed in ELL form: nbr (N,K) int32 neighbour ids, w (N,K) the
+ * off-diagonal entries L_ij (rows padded with w = 0); the diagonal is -sum_j L_ij by construction.
+ * V (B,N,3) -> Lx (B,N,3), loss (1); partial: workspace of ceil(B*N/256) floats.  Deterministic (no atomics). */
+int obman_laplacian_fwd(const float* V, const int* nbr, const float* w, int B, int N, int K, float* Lx,
+                        float* partial, float* loss, void* stream);
+/* Backward (laplacianloss.py:137-150: L^T g = L g) fused with the gradient of the row norms: gloss (1) -> gV (B,N,3). */
+int obman_laplacian_bwd(const float* Lx, const float* gloss, const int* nbr, const float* w, int B, int N,
+                        int K, float* gV, void* stream);
+/* edge_loss (atlasbranch.py:153-167): loss (1) = mean |e - mean_b(e)| over the 3F squared edge lengths of every
+ * sample.  faces (F,3) int32; stats (B,3) = {mean, sum |dev|, sum sign(dev)} is kept for the backward. */
+int obman_edge_loss_fwd(const float* V, const int* faces, int B, int N, int F, float* stats, float* loss,
+                        void* stream);
+/* vf (N,Kf) int32: ids of the faces incident to each vertex, -1 padded (vertex-centric gather, no atomics). */
+int obman_edge_loss_bwd(const float* V, const int* faces, const int* vf, const float* stats,
+                        const float* gloss, int B, int N, int F, int Kf, float* gV, void* stream);
+/* Fused torch.optim.Adam step (traineval.py:113-116) on flat fp32 buffers (16-byte aligned); g is multiplied by
+ * grad_scale.  hyper_dev: device float[2] = {1-based step number, learning-rate multiplier} - device memory so that a
+ * captured CUDA graph keeps exact bias corrections and follows StepLR (traineval.py:179-182): lr_eff = lr * hyper_dev[1]. */
 int obman_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                    float beta2, float eps, float weight_decay, const float* step_dev, float grad_scale,
+                    float beta2, float eps, float weight_decay, const float* hyper_dev, float grad_scale,
                     void* stream);
 
 #ifdef __cplusplus

@@ -232,3 +232,68 @@ def mano_layer(pose, betas, trans, tables, side_left, root_palm, center_idx):
 
 def launches():
     return _lib.launch_count
+
+
+# ---------------------------------------------------------------------------------------------------
+# mesh regularisers (fixed icosphere topology)
+# ---------------------------------------------------------------------------------------------------
+class _LaplacianFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, nbr, w):
+        verts = _prep(verts, "verts")
+        B, N, _ = verts.shape
+        K = nbr.shape[1]
+        if nbr.shape[0] != N or tuple(w.shape) != tuple(nbr.shape):
+            raise RuntimeError("laplacian_loss: the Laplacian was built for {} vertices, got {}".format(
+                nbr.shape[0], N))
+        lx = torch.empty_like(verts)
+        partial = torch.empty((B * N + 255) // 256, device=verts.device)
+        loss = torch.empty(1, device=verts.device)
+        call("obman_laplacian_fwd", ptr(verts), ptr(nbr), ptr(w), B, N, K, ptr(lx), ptr(partial), ptr(loss),
+             stream_ptr())
+        ctx.save_for_backward(lx, nbr, w)
+        ctx.mark_non_differentiable(lx)
+        return loss, lx
+
+    @staticmethod
+    def backward(ctx, gloss, _glx):
+        lx, nbr, w = ctx.saved_tensors
+        B, N, _ = lx.shape
+        gv = torch.empty_like(lx)
+        call("obman_laplacian_bwd", ptr(lx), ptr(_prep(gloss, "gloss")), ptr(nbr), ptr(w), B, N, nbr.shape[1],
+             ptr(gv), stream_ptr())
+        return gv, None, None
+
+
+def laplacian_loss(verts, nbr, w):
+    """verts (B,N,3); nbr (N,K) int32 / w (N,K) fp32: ELL form of the constant cotangent Laplacian.
+    Returns (loss (1,), Lx (B,N,3)); laplacianloss.py:36-41."""
+    return _LaplacianFn.apply(verts, nbr, w)
+
+
+class _EdgeLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, faces_i32, vert_faces):
+        verts = _prep(verts, "verts")
+        B, N, _ = verts.shape
+        F = faces_i32.shape[0]
+        stats = torch.empty((B, 3), device=verts.device)
+        loss = torch.empty(1, device=verts.device)
+        call("obman_edge_loss_fwd", ptr(verts), ptr(faces_i32), B, N, F, ptr(stats), ptr(loss), stream_ptr())
+        ctx.save_for_backward(verts, faces_i32, vert_faces, stats)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        verts, faces_i32, vert_faces, stats = ctx.saved_tensors
+        B, N, _ = verts.shape
+        gv = torch.empty_like(verts)
+        call("obman_edge_loss_bwd", ptr(verts), ptr(faces_i32), ptr(vert_faces), ptr(stats),
+             ptr(_prep(gloss, "gloss")), B, N, faces_i32.shape[0], vert_faces.shape[1], ptr(gv), stream_ptr())
+        return gv, None, None
+
+
+def edge_loss(verts, faces_i32, vert_faces):
+    """verts (B,N,3); faces_i32 (F,3) int32; vert_faces (N,Kf) int32 (-1 padded incident-face table).
+    Returns the (1,) edge regulariser of atlasbranch.py:153-167."""
+    return _EdgeLossFn.apply(verts, faces_i32, vert_faces)

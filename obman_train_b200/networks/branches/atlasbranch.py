@@ -4,14 +4,16 @@ Same constructor / forward / forward_inference signatures and result keys as the
 (/root/reference/mano_train/networks/branches/atlasbranch.py:14-150) and the same AtlasLoss.compute_loss
 contract (:170-287).  The decoder and the two small MLP heads run on the tcgen05 GEMM kernels, the
 Chamfer terms on the fused nearest-neighbour kernel.  The residual decoder (``use_residual``) is out of
-scope: ``atlas_residual`` is never set from the CLI; the Laplacian regulariser is
-broken upstream on torch >= 1.5 (Appendix A.17) and therefore rejected when its lambda is non-zero.
+scope: ``atlas_residual`` is never set from the CLI.  The mesh regularisers (edge lengths,
+cotangent Laplacian) run as fused CUDA kernels (csrc/mesh_regul.cu); the reference's own Laplacian class is a legacy
+autograd Function that fails on torch >= 1.5 (Appendix A.17), the one here computes the same loss on the device.
 """
 import numpy as np
 import torch
 from torch import nn
 import torch.nn.functional as torch_f
 
+from ... import functional as Fb
 from ... import mlp
 from ...icosphere import icosphere
 from ...queries import TransQueries
@@ -112,28 +114,35 @@ class AtlasBranch(nn.Module):
 _faces_cache = {}
 
 
-def _faces_on(faces, device):
-    """(F,3) int64 face tensor on ``device``, cached (no host->device copy per step, CUDA-graph safe)."""
+def _faces_on(faces, device, dtype=np.int64):
+    """(F,3) face tensor on ``device``, cached (no host->device copy per step, CUDA-graph safe)."""
     if torch.is_tensor(faces):
-        return faces.to(device)
-    arr = np.ascontiguousarray(np.asarray(faces).astype(np.int64))
-    key = (arr.shape, hash(arr.tobytes()), str(device))
+        faces = faces.detach().cpu().numpy()
+    arr = np.ascontiguousarray(np.asarray(faces).astype(dtype))
+    key = (arr.shape, arr.dtype.str, hash(arr.tobytes()), str(device))
     if key not in _faces_cache:
         _faces_cache[key] = torch.from_numpy(arr).to(device)
     return _faces_cache[key]
 
 
+_vert_faces_cache = {}
+
+
+def _vert_faces_on(faces, n_verts, device):
+    arr = np.ascontiguousarray(np.asarray(faces).astype(np.int32))
+    key = (arr.shape, hash(arr.tobytes()), n_verts, str(device))
+    if key not in _vert_faces_cache:
+        from .laplacianloss import vertex_face_table
+        _vert_faces_cache[key] = torch.from_numpy(vertex_face_table(n_verts, arr)).to(device)
+    return _vert_faces_cache[key]
+
+
 def edge_loss(edges, faces):
-    """atlasbranch.py:153-167: mean absolute deviation of the squared edge lengths from their per-sample mean."""
-    faces = _faces_on(faces, edges.device)
-    edges_A = edges[:, faces[:, 0]]
-    edges_B = edges[:, faces[:, 1]]
-    edges_C = edges[:, faces[:, 2]]
-    edge_lengths_A = torch.sum((edges_B - edges_A) ** 2, dim=2)
-    edge_lengths_B = torch.sum((edges_C - edges_B) ** 2, dim=2)
-    edge_lengths_C = torch.sum((edges_A - edges_C) ** 2, dim=2)
-    all_edges = torch.cat([edge_lengths_C, edge_lengths_B, edge_lengths_A], dim=1)
-    return torch.mean(torch.abs(all_edges - all_edges.mean(1, keepdim=True)))
+    """atlasbranch.py:153-167: mean absolute deviation of the squared edge lengths from their per-sample mean.
+    One fused CUDA kernel pair per direction (csrc/mesh_regul.cu) instead of ~15 gather / reduce launches."""
+    faces_i32 = _faces_on(faces, edges.device, np.int32)
+    vert_faces = _vert_faces_on(faces, edges.shape[1], edges.device)
+    return Fb.edge_loss(edges, faces_i32, vert_faces).squeeze(0)
 
 
 class AtlasLoss:
@@ -147,8 +156,10 @@ class AtlasLoss:
         self.edge_regul_lambda = edge_regul_lambda
         self.lambda_laplacian = lambda_laplacian
         if lambda_laplacian:
-            raise NotImplementedError("the Laplacian regulariser of the reference is a legacy autograd "
-                                      "Function that fails on torch >= 1.5 (SURVEY.md Appendix A.17)")
+            # atlasbranch.py:189-192; the reference's own class is a legacy autograd Function that fails on
+            # torch >= 1.5 - this one computes the same loss on the device
+            from .laplacianloss import LaplacianLoss
+            self.laplacian_loss = LaplacianLoss(laplacian_faces, laplacian_verts)
         self.atlas_loss = atlas_loss
         if self.atlas_loss == "chamfer":
             self.chamfer_loss = atlasutils.ChamferLoss()
@@ -189,6 +200,10 @@ class AtlasLoss:
                 edge_regul_loss = edge_loss(obj_mesh, preds["objfaces"])
                 atlas_losses["atlas_edge_regul"] = edge_regul_loss
                 final_loss = final_loss + self.edge_regul_lambda * edge_regul_loss
+            if self.lambda_laplacian:  # atlasbranch.py:275-280
+                laplacian_loss = self.laplacian_loss(obj_mesh)
+                atlas_losses["atlas_laplac"] = laplacian_loss
+                final_loss = final_loss + self.lambda_laplacian * laplacian_loss
         else:
             sym_loss = None
             final_loss = torch.zeros(1, device="cuda")

@@ -49,8 +49,17 @@ class FlatAdamTrainer(object):
         self.numel = total
         self.param_numel = sum(p.numel() for _, p in params)
         self.step_count = 0
-        self._step_dev = torch.zeros(1, device=dev, dtype=torch.float32)  # step number for captured graphs
+        # {step number, lr multiplier} in device memory: a captured graph reads both at replay time
+        self._hyper_dev = torch.tensor([0.0, 1.0], device=dev, dtype=torch.float32)
+        self._step_view, self._scale_view = self._hyper_dev[0:1], self._hyper_dev[1:2]
+        self.lr_scale = 1.0
         self._graph = None
+        # index of every optimised parameter in the reference's optimizer (traineval.py:105-116: Adam over
+        # filter(requires_grad, model.parameters()), which still counts the never-used ``fc`` parameters)
+        order = {id(p): i for i, p in enumerate(q for q in model.parameters() if q.requires_grad)}
+        self.optim_index = [order[id(p)] for p in self.params]
+        self.optim_len = len(order)
+        self.offsets = offsets
 
     def zero_grad(self):
         self.flat_g.zero_()
@@ -91,10 +100,24 @@ class FlatAdamTrainer(object):
         capturing = torch.cuda.is_current_stream_capturing()
         if not capturing:
             self.step_count += 1
-            self._step_dev.fill_(float(self.step_count))
+            self._push_hyper()
         call("obman_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.exp_avg), ptr(self.exp_avg_sq),
              self.numel, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-             float(self.weight_decay), ptr(self._step_dev), 1.0 / float(self.world_size), stream_ptr())
+             float(self.weight_decay), ptr(self._hyper_dev), 1.0 / float(self.world_size), stream_ptr())
+
+    def _push_hyper(self):
+        # fill kernels carry the value as a launch argument: safe with many steps in flight (a pinned staging
+        # buffer would be overwritten by the host before the queued copies ran)
+        self._step_view.fill_(float(self.step_count))
+
+    def set_lr_scale(self, scale):
+        """Multiplier on ``lr`` read from device memory by the Adam kernel (works under graph replay).
+        ``StepLR(step_size, gamma)`` of traineval.py:179-182 is ``set_lr_scale(gamma ** (epoch // step_size))``."""
+        self.lr_scale = float(scale)
+        self._scale_view.fill_(self.lr_scale)
+
+    def step_lr(self, epoch, step_size, gamma):
+        self.set_lr_scale(gamma ** (epoch // step_size))
 
     # ---- CUDA-graph mode: the whole step (forward, backward, all-reduce, Adam) replayed as one graph ----------
     def capture(self, sample, warmup=3):
@@ -127,11 +150,129 @@ class FlatAdamTrainer(object):
                 if torch.is_tensor(v):
                     self._static_sample[k].copy_(v, non_blocking=True)
         self.step_count += 1
-        self._step_dev.fill_(float(self.step_count))
+        self._push_hyper()
         self._graph.replay()
         return self._static_loss
+
+    # ---- checkpoint interchange with torch.optim.Adam (modelio.load_checkpoint / save_checkpoint) ---------------
+    def state_dict(self):
+        """Optimizer state in ``torch.optim.Adam.state_dict()`` format, indexed like the reference's optimizer, so a
+        checkpoint written here resumes under the reference's traineval.py and vice versa."""
+        state = {}
+        if self.step_count > 0:
+            for p, off, idx in zip(self.params, self.offsets, self.optim_index):
+                n = p.numel()
+                state[idx] = {"step": torch.tensor(float(self.step_count)),
+                              "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
+                              "exp_avg_sq": self.exp_avg_sq[off:off + n].view_as(p).clone()}
+        group = {"lr": self.lr * self.lr_scale, "betas": tuple(self.betas), "eps": self.eps,
+                 "weight_decay": self.weight_decay, "amsgrad": False, "maximize": False, "foreach": None,
+                 "capturable": False, "differentiable": False, "fused": None, "initial_lr": self.lr,
+                 "params": list(range(self.optim_len))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        """Accepts ``torch.optim.Adam.state_dict()`` of the reference's optimizer (or this class's own).  Raises
+        ``ValueError`` on a parameter-count / shape mismatch like torch does (modelio.load_checkpoint catches it)."""
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != self.optim_len:
+            raise ValueError("loaded state dict contains a parameter group that doesn't match the size of "
+                             "optimizer's group")
+        g = groups[0]
+        self.lr = float(g.get("initial_lr", g["lr"]))
+        self.lr_scale = float(g["lr"]) / self.lr if self.lr != 0 else 1.0
+        self.betas, self.eps = tuple(g["betas"]), float(g["eps"])
+        self.weight_decay = float(g.get("weight_decay", 0.0))
+        if g.get("amsgrad", False):
+            raise ValueError("FlatAdamTrainer: amsgrad checkpoints are not supported")
+        ids = g["params"]  # torch re-maps by position, not by id value
+        pos = {pid: i for i, pid in enumerate(ids)}
+        state = {pos[k]: v for k, v in sd["state"].items()}
+        steps = set()
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for p, off, idx in zip(self.params, self.offsets, self.optim_index):
+            st = state.get(idx)
+            if st is None:
+                continue
+            n = p.numel()
+            if st["exp_avg"].numel() != n:
+                raise ValueError("FlatAdamTrainer: optimizer state %d has %d elements, parameter has %d" % (
+                    idx, st["exp_avg"].numel(), n))
+            self.exp_avg[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            steps.add(int(float(st["step"])))
+        # the fused kernel keeps ONE step counter; the reference's per-parameter counters are all equal except for
+        # parameters that never received a gradient (no state at all)
+        if len(steps) > 1:
+            raise ValueError("FlatAdamTrainer: per-parameter step counts differ (%s)" % sorted(steps))
+        self.step_count = steps.pop() if steps else 0
+        self._scale_view.fill_(self.lr_scale)
 
     def grads_are_views(self):
         """Autograd must have accumulated in place into the flat buffer (sanity check for tests)."""
         base = self.flat_g.untyped_storage().data_ptr()
         return all(p.grad is not None and p.grad.untyped_storage().data_ptr() == base for p in self.params)
+
+
+class PinnedFeeder(object):
+    """Host -> device input pipeline for the captured step (the replacement for the reference's
+    ``DataParallel.scatter`` of the collated batch, /root/reference/mano_train/netscripts/epochpass3d.py:80).
+
+    The next batch travels from PINNED host memory into a staging set on a copy stream while the current step
+    runs; at the start of a step the staging set is moved into the graph's static input buffers (a device-to-device
+    copy, ~20 us for a 51 MB batch) and the staging set is handed back to the copy stream.  Every step still pays
+    one full host->device copy of its own inputs; it is just not serialised with the compute.
+
+        feeder = PinnedFeeder(trainer)          # after trainer.capture(static_sample)
+        feeder.prefetch(batch0)
+        for batch in batches[1:] + [None]:
+            loss = feeder.step(next_host_sample=batch)
+    """
+
+    def __init__(self, trainer):
+        if trainer._graph is None:
+            raise RuntimeError("PinnedFeeder: call trainer.capture(sample) first")
+        self.trainer = trainer
+        self.static = trainer._static_sample
+        self.keys = [k for k, v in self.static.items() if torch.is_tensor(v)]
+        self.staging = {k: torch.empty_like(self.static[k]) for k in self.keys}
+        self.copy_stream = torch.cuda.Stream()
+        self.ready = torch.cuda.Event()
+        self.free = torch.cuda.Event()
+        self._staged = False
+        self._consumed_once = False
+        self.h2d_bytes = sum(self.static[k].numel() * self.static[k].element_size() for k in self.keys)
+
+    def prefetch(self, host_sample):
+        """Enqueue the host->device copy of ``host_sample`` (pinned tensors under the static sample's keys)."""
+        if self._staged:
+            raise RuntimeError("PinnedFeeder.prefetch: the staged batch has not been consumed by step() yet")
+        for k in self.keys:
+            v = host_sample[k]
+            if v.is_cuda or not v.is_pinned():
+                raise RuntimeError("PinnedFeeder: input %r must be a pinned host tensor" % (k,))
+            if v.shape != self.static[k].shape or v.dtype != self.static[k].dtype:
+                raise RuntimeError("PinnedFeeder: input %r has shape %s, the captured step was built for %s" % (
+                    k, tuple(v.shape), tuple(self.static[k].shape)))
+        if self._consumed_once:
+            self.copy_stream.wait_event(self.free)
+        with torch.cuda.stream(self.copy_stream):
+            for k in self.keys:
+                self.staging[k].copy_(host_sample[k], non_blocking=True)
+            self.ready.record(self.copy_stream)
+        self._staged = True
+
+    def step(self, next_host_sample=None):
+        """Run one captured step on the staged batch; start copying ``next_host_sample`` behind it."""
+        if not self._staged:
+            raise RuntimeError("PinnedFeeder.step: nothing staged, call prefetch(host_sample) first")
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ready)
+        for k in self.keys:
+            self.static[k].copy_(self.staging[k], non_blocking=True)
+        self.free.record(cur)
+        self._staged, self._consumed_once = False, True
+        if next_host_sample is not None:
+            self.prefetch(next_host_sample)
+        return self.trainer.replay()

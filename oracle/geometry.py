@@ -167,15 +167,45 @@ def edge_loss(verts, faces):
     return (e - e.mean(1, keepdim=True)).abs().mean()
 
 
+def laplacian_matrix(sphere_verts, faces):
+    """Dense (N,N) float64 cotangent Laplacian of the unit sphere mesh, as laplacianloss.py builds it:
+    cotangent (:153-185) -> C (F,3) = [l2^2+l3^2-l1^2, l1^2+l3^2-l2^2, l1^2+l2^2-l3^2] / (2*Heron area) / 4;
+    entries at (rows, cols) = (f[:, [1,2,0]], f[:, [2,0,1]]) (:117-123); L = L + L^T; L = L - diag(rowsum) (:124-127)."""
+    v = np.asarray(sphere_verts, dtype=np.float64)
+    f = np.asarray(faces).astype(np.int64)
+    v1, v2, v3 = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    l1 = np.sqrt(((v2 - v3) ** 2).sum(1))
+    l2 = np.sqrt(((v3 - v1) ** 2).sum(1))
+    l3 = np.sqrt(((v1 - v2) ** 2).sum(1))
+    sp = (l1 + l2 + l3) * 0.5
+    A = 2 * np.sqrt(sp * (sp - l1) * (sp - l2) * (sp - l3))
+    C = np.stack([l2 ** 2 + l3 ** 2 - l1 ** 2, l1 ** 2 + l3 ** 2 - l2 ** 2, l1 ** 2 + l2 ** 2 - l3 ** 2], 1)
+    C = C / A[:, None] / 4
+    n = v.shape[0]
+    L = np.zeros((n, n))
+    np.add.at(L, (f[:, [1, 2, 0]].reshape(-1), f[:, [2, 0, 1]].reshape(-1)), C.reshape(-1))
+    L = L + L.T
+    return L - np.diag(L.sum(1))
+
+
+def laplacian_loss(verts, L):
+    """LaplacianLoss.__call__ (laplacianloss.py:36-41): mean over all B*N rows of ||(L V_b)_i||_2.
+    ``L`` from laplacian_matrix (numpy or tensor); differentiable in ``verts`` (the reference's backward is
+    L^T g = L g, :137-150, which is what autograd gives here)."""
+    Lt = torch.as_tensor(L, dtype=verts.dtype)
+    lx = torch.einsum("ij,bjc->bic", Lt, verts)
+    return torch.sqrt((lx ** 2).sum(2)).mean(), lx
+
+
 def mse(a, b):
     return ((a - b) ** 2).mean()
 
 
 def atlas_loss(preds, gt_points, lambda_atlas, final_lambda_atlas, trans_weight, scale_weight,
-               edge_regul_lambda=None):
+               edge_regul_lambda=None, lambda_laplacian=0, laplacian=None):
     """AtlasLoss.compute_loss (atlasbranch.py:199-287), translation-predicted branch
-    (:206-253) and the plain branch (:255-264); Laplacian term excluded (laplacianloss.py is
-    broken on torch>=1.5)."""
+    (:206-253) and the plain branch (:255-264); ``laplacian`` = laplacian_matrix(sphere verts, faces) when
+    ``lambda_laplacian`` is set (:275-280)."""
     losses = {}
     if "objtrans" in preds and "objpointscentered3d" in preds:
         centroid = gt_points.mean(1)
@@ -205,6 +235,10 @@ def atlas_loss(preds, gt_points, lambda_atlas, final_lambda_atlas, trans_weight,
         el = edge_loss(mesh, preds["objfaces"])
         losses["atlas_edge_regul"] = el
         total = total + edge_regul_lambda * el
+    if lambda_laplacian:
+        ll, _ = laplacian_loss(mesh, laplacian)
+        losses["atlas_laplac"] = ll
+        total = total + lambda_laplacian * ll
     losses["atlas_objpoints3d"] = sym
     return total, losses
 

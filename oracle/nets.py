@@ -224,7 +224,9 @@ def handnet_forward(state, cfg, sample, mano_tables, grid, faces, zones=None, bn
             atotal, al = geometry.atlas_loss(
                 ares, sample["objpoints3d"], g("atlas_lambda") or 0, g("atlas_final_lambda") or 0,
                 g("atlas_trans_weight", 1), g("atlas_scale_weight", 1),
-                g("atlas_lambda_regul_edges", 0))
+                g("atlas_lambda_regul_edges", 0), g("atlas_lambda_laplacian", 0),
+                geometry.laplacian_matrix(grid.detach().cpu().numpy(), faces) if g("atlas_lambda_laplacian", 0)
+                else None)
             total = atotal if total is None else total + atotal
             losses.update(al)
     losses["total_loss"] = total

@@ -81,6 +81,18 @@ def test_handnet_shared_encoder_ico3_no_contact():
     _check(*_run(cfg, B=2, H=64, seed=10, sides=["right", "right"]))
 
 
+def test_handnet_with_laplacian_regulariser():
+    """atlas_lambda_laplacian > 0 (atlasbranch.py:275-280): the reference's own class no longer runs on torch >= 1.5;
+    the oracle restatement is pinned against its numerical body (tests/test_mesh_regul.py)."""
+    cfg = dict(FULL_CFG)
+    cfg.update(atlas_lambda_laplacian=0.05, contact_lambda=0, collision_lambda=0)
+    model, state, got, ref = _run(cfg, B=2, H=64, seed=20)
+    assert "atlas_laplac" in got[2] and float(got[2]["atlas_laplac"]) > 0
+    _check(model, state, got, ref)
+    model.decay_regul(0.5)
+    assert model.atlas_loss.lambda_laplacian == pytest.approx(0.025)
+
+
 def test_handnet_no_loss_inference_hand_only():
     from obman_train_b200.networks.handnet import HandNet
     from obman_train_b200.queries import TransQueries, BaseQueries

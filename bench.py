@@ -181,7 +181,8 @@ def workload_config(n_gpus):
             "per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * n_gpus,
             "parallelism": "dp%d" % n_gpus, "precision": PRECISION_NOTE[0],
             "l2_policy": "activations per step (~3 GB) exceed the 126 MB L2; no explicit flush",
-            "launch": "whole step replayed as one CUDA graph (--no-graph for eager launches)"}
+            "launch": "whole step replayed as one CUDA graph (--no-graph for eager launches); weight-gradient / "
+                      "BN-gradient / weight-folding kernels on a second captured stream (OBMAN_OVERLAP=0 disables)"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -322,12 +323,15 @@ def run_b200(args):
     ms_e2e = timed(args.steps, step_e2e)
 
     # roofline of the dominant kernel (gemm_tc_kernel): per-launch CUDA events + algorithmic FLOPs
+    from obman_train_b200 import streams
+    overlap = streams.set_enabled(False)  # per-launch timing needs every launch alone on the GPU: one stream
     dense.profile_begin()
     nprof = min(args.steps, 3)
     for _ in range(nprof):
         trainer.step(resident)  # eager (not the graph): per-launch events need individual launches
     dense.profile_end.steps = nprof
     prof = dense.profile_end()
+    streams.set_enabled(overlap)
     if rank == 0 and args.dump_launches:
         per = len(dense.last_profile) // nprof
         with open(args.dump_launches, "w") as f:
@@ -348,6 +352,15 @@ def run_b200(args):
     # measured cuBLAS bf16 rate, kind::tf32 at half of it
     tc_peak = bf16 if args.precision == "bf16x3" else bf16 / 2.0
     passes = 1 if args.precision == "tf32" else 3
+    # DRAM traffic of the dominant kernel family per launch, from the committed ncu capture of this command
+    # (profiles/gemm_traffic_r1d.json <- profiles/launches_r1d_bench_step.csv); only valid for the default workload
+    traffic, traffic_src = None, None
+    if args.config == 2 and args.precision == "bf16x3":
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic_r1d.json")))
+            traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
+        except Exception:  # noqa: BLE001
+            pass
     value = B * world * args.steps / (ms / 1e3)
     e2e = B * world * args.steps / (ms_e2e / 1e3)
     line = {
@@ -369,7 +382,12 @@ def run_b200(args):
                      "tensor_pipe_tflops_incl_passes": prof["tflops"] * passes,
                      "tensor_pipe_frac": prof["tflops"] * passes / tc_peak,
                      "gemm_ms_per_step": prof["ms_per_step"], "gemm_launches_per_step": prof["launches_per_step"],
-                     "share_of_step": prof["ms_per_step"] / (ms / args.steps), "traffic": None},
+                     "share_of_step": prof["ms_per_step"] / (ms / args.steps),
+                     "share_note": "per-launch times are measured with every launch alone on one stream (eager); in "
+                                   "the timed graph the weight-gradient launches overlap the data-gradient chain",
+                     "flops_per_launch": prof["flops"] / max(1, prof["launches"]),
+                     "traffic": traffic, "traffic_unit": "bytes/launch (dram read+write, ncu)",
+                     "traffic_source": traffic_src},
     }
     line["chamfer"] = chamfer_report(peaks)
     if not args.no_cpu_baseline:

@@ -11,7 +11,7 @@ Forward and backward of mano_train/networks/bases/resnet.py:154-188 (conv7x7/2 -
 """
 import torch
 
-from . import dense
+from . import dense, streams
 from ._lib import call, ptr, stream_ptr
 
 BN_EPS = 1e-5
@@ -132,11 +132,21 @@ class _EncoderFn(torch.autograd.Function):
             raise RuntimeError("encoder: image height/width must be multiples of 32")
         pf = dense.PASSES[dense.get_precision()["fwd"]]
         specs = resnet18_units()
-        units = []
-        for i, (_, _, O, I, k, s) in enumerate(specs):
-            w, gamma, beta, mean, var = [p.detach().contiguous() for p in params[5 * i:5 * i + 5]]
-            units.append(_Unit(w, gamma, beta, mean, var, k, s, stem=(i == 0), packed=(pf == dense.BF16X3)))
+        packed = pf == dense.BF16X3
+        unit_params = [[p.detach().contiguous() for p in params[5 * i:5 * i + 5]] for i in range(len(specs))]
+
+        def make_unit(i):
+            _, _, O, I, k, s = specs[i]
+            w, gamma, beta, mean, var = unit_params[i]
+            return _Unit(w, gamma, beta, mean, var, k, s, stem=(i == 0), packed=packed)
+
         st = stream_ptr()
+        units = [make_unit(0)]
+        # the BN folding / weight packing of the 19 remaining units runs on the auxiliary stream underneath the
+        # HBM-bound front of the network (stem pack, stem convolution, max-pool)
+        streams.fork()
+        with streams.on_aux():
+            units.extend(make_unit(i) for i in range(1, len(specs)))
         xs = _empty(B, H // 2, W // 2, 64)
         call("obman_stem_pack", ptr(images), B, H, W, ptr(xs), st)
         c1 = units[0].fprop(xs, H // 2, W // 2, relu=True, passes=pf)
@@ -146,6 +156,7 @@ class _EncoderFn(torch.autograd.Function):
         p = _empty(B, hp, wp, 64)
         pidx = torch.empty((B, hp, wp, 64), device="cuda", dtype=torch.uint8)
         call("obman_maxpool_fwd", ptr(c1), B, H // 2, W // 2, 64, ptr(p), ptr(pidx), st)
+        streams.join()
         if DEBUG is not None:
             DEBUG["pool_idx"] = pidx
         x, h, w_ = p, hp, wp
@@ -189,19 +200,33 @@ class _EncoderFn(torch.autograd.Function):
         g2 = torch.empty_like(last)
         call("obman_meanpool_bwd", ptr(gfeat), ptr(last), B, hl * wl, 512, ptr(g2), st)
         grads = {}
+        # Critical path (current stream): the chain of data gradients.  Off the path (auxiliary stream): per unit the
+        # column sum of the incoming gradient (d beta), the weight-gradient GEMM and its BatchNorm finish.  ``keep``
+        # pins every tensor that crosses the two streams until they are joined (see streams.py).
+        keep = []
+
+        def side_unit(u, g, x, rows, gb=None):
+            keep.extend((g, x))
+            streams.fork()  # g was produced on the current stream
+            with streams.on_aux():
+                if gb is None:
+                    gb = colsum(rows, u.O, g)
+                grads[id(u)] = u.finish(u.wgrad(g, x, pw), gb)
+            return gb
+
         for bidx, (u1, u2, ud, x, a, out, h, w_) in reversed(list(enumerate(blocks))):
             ho, wo = out.shape[1], out.shape[2]
             if DEBUG is not None:
                 DEBUG["g_out_%d" % bidx] = g2.clone()
             rows = B * ho * wo
-            gb2 = colsum(rows, u2.O, g2)
-            grads[id(u2)] = u2.finish(u2.wgrad(g2, a, pw), gb2)
+            gb2 = side_unit(u2, g2, a, rows)
+            if ud is not None:
+                side_unit(ud, g2, x, rows, gb=gb2)
             g1 = u2.dgrad(g2, ho, wo, mask_src=a, passes=pb)
             if DEBUG is not None:
                 DEBUG["g_a_%d" % bidx] = g1.clone()
-            grads[id(u1)] = u1.finish(u1.wgrad(g1, x, pw), colsum(rows, u1.O, g1))
+            side_unit(u1, g1, x, rows)
             if ud is not None:
-                grads[id(ud)] = ud.finish(ud.wgrad(g2, x, pw), gb2)
                 gres = ud.dgrad(g2, h, w_, passes=pb)
             else:
                 gres = g2
@@ -214,6 +239,8 @@ class _EncoderFn(torch.autograd.Function):
             DEBUG["g_c1"] = gc1.clone()
         u0 = units[0]
         grads[id(u0)] = u0.finish(u0.wgrad(gc1, xs, pw), colsum(B * (H // 2) * (W // 2), 64, gc1))
+        streams.join()
+        del keep
         outs = [None]
         for u in units:
             gw, gg, gbt = grads[id(u)]

@@ -9,7 +9,7 @@
 """
 import torch
 
-from . import dense
+from . import dense, streams
 from ._lib import call, ptr, stream_ptr
 
 BN_EPS = 1e-5
@@ -182,14 +182,23 @@ class _PointDecoderFn(torch.autograd.Function):
         feat, grid, wfeat, h1, h2, h3, B, N, per_sample, out_factor = ctx.saved
         C1, C2, C3 = l1.O, l2.O, l3.O
         M = B * N
+        # data-gradient chain on the current stream, weight gradients / BN finishes on the auxiliary stream
+        keep = []
+
+        def side_layer(layer, g, h, C):
+            keep.extend((g, h))
+            streams.fork()
+            with streams.on_aux():
+                return layer.finish(dense.wgrad_matrix(g, h, passes=pw), colsum(g, C))
+
         g4 = _zeros(M, 32)
         g4[:, :3] = gy.reshape(M, 3) * out_factor
-        gw4, gb4, _, _ = l4.finish(dense.wgrad_matrix(g4, h3, passes=pw), colsum(g4, 3))
+        gw4, gb4, _, _ = side_layer(l4, g4, h3, 3)
         g3 = dense.gemm(g4, l4.wft, mask_src=h3, passes=pb, n=C3, k=3, **l4.bw)       # (M,C3)
-        gw3, gb3, gg3, gbt3 = l3.finish(dense.wgrad_matrix(g3, h2, passes=pw), colsum(g3, C3))
+        gw3, gb3, gg3, gbt3 = side_layer(l3, g3, h2, C3)
         g2 = _zeros(M, h2.shape[1])
         dense.gemm(g3, l3.wft, out=g2, mask_src=h2, passes=pb, n=C2, k=C3, **l3.bw)
-        gw2, gb2, gg2, gbt2 = l2.finish(dense.wgrad_matrix(g2, h1, passes=pw), colsum(g2, C2))
+        gw2, gb2, gg2, gbt2 = side_layer(l2, g2, h1, C2)
         g1 = _zeros(M, h1.shape[1])
         dense.gemm(g2, l2.wft, out=g1, mask_src=h1, passes=pb, n=C1, k=C2, **l2.bw)
         gF = _zeros(B, _r32(C1))
@@ -211,6 +220,8 @@ class _PointDecoderFn(torch.autograd.Function):
             wft = _zeros(Fdim, _r32(C1))
             wft[:, :C1] = wfeat.t()
             gfeat = dense.gemm(gF, wft, passes=pb, n=Fdim, k=C1)
+        streams.join()
+        del keep
         p = ctx.param_shapes
         return (gfeat, None, None,
                 gw1.view(p[0]), gb1, gw2.view(p[2]), gb2, gw3.view(p[4]), gb3, gw4.view(p[6]), gb4,

@@ -104,3 +104,63 @@ def test_handnet_no_loss_inference_hand_only():
     assert total is None and losses["total_loss"] is None
     assert results["verts"].shape == (1, 778, 3) and results["joints"].shape == (1, 21, 3)
     assert torch.isfinite(results["verts"]).all()
+
+
+def test_aux_stream_overlap_graph_replay_and_pinned_feeder_match_serial_eager_step():
+    """One training step from identical weights, four ways: (1) eager on one stream, (2) eager with the weight-gradient
+    work on the auxiliary stream (streams.py), (3) the captured CUDA graph replayed, (4) the graph fed from pinned host
+    memory through PinnedFeeder.  Gradients and updated parameters must agree (tolerance = re-ordering of the split-K
+    float atomics in the weight-gradient kernels; the first Adam update is ~lr*sign(g), which amplifies that noise on
+    near-zero gradient entries, hence the looser bound on the parameter change)."""
+    from obman_train_b200 import streams
+    from obman_train_b200.networks.handnet import HandNet
+    from obman_train_b200.trainer import FlatAdamTrainer, PinnedFeeder
+    host = make_sample(4, 64, 77)
+    sample = enum_sample(host)
+    torch.manual_seed(5)
+    model = HandNet(**FULL_CFG).eval().cuda()
+    trainer = FlatAdamTrainer(model, lr=1e-3)
+    p0 = trainer.flat_p.clone()
+
+    def restore():
+        trainer.flat_p.copy_(p0)
+        trainer.exp_avg.zero_()
+        trainer.exp_avg_sq.zero_()
+        trainer.step_count = 0
+
+    def close(a, b, tol):
+        return ((a - b).norm() / b.norm()).item() < tol
+
+    prev = streams.set_enabled(False)
+    try:
+        loss_s = trainer.step(sample).item()
+        g_s, p_s = trainer.flat_g.clone(), trainer.flat_p.clone()
+        assert torch.isfinite(g_s).all() and (p_s != p0).any()
+        streams.set_enabled(True)
+        restore()
+        loss_o = trainer.step(sample).item()
+        assert abs(loss_o - loss_s) <= 1e-6 * abs(loss_s)
+        assert close(trainer.flat_g, g_s, 1e-5) and close(trainer.flat_p - p0, p_s - p0, 2e-2)
+        trainer.capture(sample, warmup=1)
+        restore()
+        loss_g = trainer.replay().item()
+        torch.cuda.synchronize()
+        assert abs(loss_g - loss_s) <= 1e-6 * abs(loss_s)
+        assert close(trainer.flat_g, g_s, 1e-5) and close(trainer.flat_p - p0, p_s - p0, 2e-2)
+        # pinned host feed: a different batch first (so the static buffers really get overwritten), then this one
+        feeder = PinnedFeeder(trainer)
+        other = enum_sample(make_sample(4, 64, 78), device="cpu")
+        pin = lambda smp: {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in smp.items()}  # noqa: E731
+        feeder.prefetch(pin(other))
+        feeder.step(next_host_sample=pin(enum_sample(host, device="cpu")))
+        restore()
+        loss_f = feeder.step().item()
+        torch.cuda.synchronize()
+        assert abs(loss_f - loss_s) <= 1e-6 * abs(loss_s)
+        assert close(trainer.flat_g, g_s, 1e-5) and close(trainer.flat_p - p0, p_s - p0, 2e-2)
+        with pytest.raises(RuntimeError, match="nothing staged"):
+            feeder.step()
+        with pytest.raises(RuntimeError, match="pinned"):
+            feeder.prefetch(enum_sample(host, device="cpu"))
+    finally:
+        streams.set_enabled(prev)

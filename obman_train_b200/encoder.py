@@ -37,6 +37,14 @@ def _empty(*shape):
     return torch.empty(shape, device="cuda", dtype=torch.float32)
 
 
+class _NullCtx(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 class _Unit(object):
     """Per-step folded weights of one conv+BN unit."""
 
@@ -75,10 +83,16 @@ class _Unit(object):
         return out
 
     def dgrad(self, g, h_in, w_in, addend=None, mask_src=None, passes=3):
-        """g (B,Ho,Wo,O) -> gx (B,h_in,w_in,I) = conv^T(g) [+ addend] [masked by mask_src > 0]."""
+        """g (B,Ho,Wo,O) -> gx (B,h_in,w_in,I) = conv^T(g) [+ addend] [masked by mask_src > 0].
+        A stride-2 convolution is four launches that write the four interleaved output phases; each is a small
+        GEMM (a quarter of the pixels, 1-4 taps) that cannot fill 148 SMs on its own, so two of them are issued on
+        the CHAIN auxiliary stream (disjoint outputs, same inputs)."""
         B = g.shape[0]
         s, k = self.stride, self.k
         gx = _empty(B, h_in, w_in, self.I)
+        two_lanes = s > 1 and k > 1 and streams.enabled()
+        if two_lanes:
+            streams.fork(streams.CHAIN)
         for ph in range(s):
             for pw in range(s):
                 dh, dw, slot = dense.dgrad_taps(k, s, k // 2, (ph, pw))
@@ -92,9 +106,13 @@ class _Unit(object):
                     else:
                         view.zero_()
                     continue
-                dense.conv_nhwc(g, self.wft, self.I, (dh, dw, None, slot), 1, gx, h_in // s, w_in // s,
-                                out_strides=strides, out_offset=off, addend=addend, mask_src=mask_src,
-                                passes=passes, w_slots=k * k, w_lo=self.wft_lo)
+                lane = streams.on_aux(streams.CHAIN) if (two_lanes and ph == 1) else _NullCtx()
+                with lane:
+                    dense.conv_nhwc(g, self.wft, self.I, (dh, dw, None, slot), 1, gx, h_in // s, w_in // s,
+                                    out_strides=strides, out_offset=off, addend=addend, mask_src=mask_src,
+                                    passes=passes, w_slots=k * k, w_lo=self.wft_lo)
+        if two_lanes:
+            streams.join(streams.CHAIN)
         return gx
 
     def wgrad(self, g, x, passes=3):
@@ -222,14 +240,21 @@ class _EncoderFn(torch.autograd.Function):
             gb2 = side_unit(u2, g2, a, rows)
             if ud is not None:
                 side_unit(ud, g2, x, rows, gb=gb2)
+            if ud is not None:
+                # the downsample branch's data gradient only needs g2: second lane, next to conv2's dgrad
+                keep.append(g2)
+                streams.fork(streams.CHAIN)
+                with streams.on_aux(streams.CHAIN):
+                    gres = ud.dgrad(g2, h, w_, passes=pb)
+            else:
+                gres = g2
             g1 = u2.dgrad(g2, ho, wo, mask_src=a, passes=pb)
             if DEBUG is not None:
                 DEBUG["g_a_%d" % bidx] = g1.clone()
             side_unit(u1, g1, x, rows)
             if ud is not None:
-                gres = ud.dgrad(g2, h, w_, passes=pb)
-            else:
-                gres = g2
+                streams.join(streams.CHAIN)
+            keep.append(gres)
             g2 = u1.dgrad(g1, h, w_, addend=gres, mask_src=x, passes=pb)
         # g2 is now the gradient w.r.t. the max-pool output (already masked by p > 0)
         gc1 = _empty(B, H // 2, W // 2, 64)

@@ -16,7 +16,7 @@ from copy import deepcopy
 import torch
 from torch import nn
 
-from .. import mlp
+from .. import mlp, streams
 from ..queries import TransQueries, BaseQueries
 from .bases import resnet
 from .branches.manobranch import ManoBranch, ManoLoss
@@ -122,19 +122,31 @@ class HandNet(nn.Module):
              or (TransQueries.joints2d in sample.keys() and TransQueries.camintrs in sample.keys()))
                 and BaseQueries.sides in sample.keys() and self.mano_lambdas):
             root_palm = sample["root"] == "palm"
-            mano_results = self.mano_branch(features, sides=sample[BaseQueries.sides], root_palm=root_palm,
-                                            use_stereoshape=False)
-            if not no_loss:
-                mano_total_loss, mano_losses = self.mano_loss.compute_loss(mano_results, sample)
-                if total_loss is None:
-                    total_loss = mano_total_loss
-                else:
-                    total_loss += mano_total_loss
-                for key, val in mano_losses.items():
-                    losses[key] = val
+            # The hand branch (3 small GEMMs, the MANO layer, 4 scalar losses: ~50 launch-latency-bound kernels) and the
+            # object branch (the AtlasNet decoder GEMMs) only share the image features: the hand branch is issued on
+            # the BRANCH auxiliary stream and joined before the first consumer of its vertices (contact loss / total);
+            # autograd replays the same two lanes in the backward pass.
+            streams.fork(streams.BRANCH)
+            with streams.on_aux(streams.BRANCH):
+                mano_results = self.mano_branch(features, sides=sample[BaseQueries.sides], root_palm=root_palm,
+                                                use_stereoshape=False)
+                if not no_loss:
+                    mano_total_loss, mano_losses = self.mano_loss.compute_loss(mano_results, sample)
+                    if total_loss is None:
+                        total_loss = mano_total_loss
+                    else:
+                        total_loss += mano_total_loss
+                    for key, val in mano_losses.items():
+                        losses[key] = val
             for key, result in mano_results.items():
                 results[key] = result
+            hand_lane_open = True
+        else:
+            hand_lane_open = False
         predict_atlas = TransQueries.objpoints3d in sample.keys() and (self.atlas_lambda or self.atlas_final_lambda)
+        if not predict_atlas and hand_lane_open:
+            streams.join(streams.BRANCH)
+            hand_lane_open = False
         if predict_atlas:
             if self.atlas_mesh:
                 if self.adapt_atlas_decoder:
@@ -148,6 +160,8 @@ class HandNet(nn.Module):
                     atlas_results = self.atlas_branch.forward_inference(atlas_features)
             else:
                 atlas_results = self.atlas_branch(features)
+            if hand_lane_open:
+                streams.join(streams.BRANCH)
             if self.need_collisions:
                 attr_loss, penetr_loss, contact_infos, contact_metrics = compute_contact_loss(
                     mano_results["verts"], self.mano_branch.faces, atlas_results["objpoints3d"],

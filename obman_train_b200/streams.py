@@ -31,30 +31,34 @@ def enabled():
     return _enabled
 
 
-def aux_stream():
-    dev = torch.cuda.current_device()
-    if dev not in _streams:
-        _streams[dev] = torch.cuda.Stream(device=dev)
-    return _streams[dev]
+WGRAD, CHAIN, BRANCH = 0, 1, 2   # auxiliary streams: weight-gradient work | second lane of the data-gradient chain
+                                  # (phases of a strided dgrad, downsample branch) | AtlasNet branch next to MANO
 
 
-def fork():
+def aux_stream(which=WGRAD):
+    key = (torch.cuda.current_device(), which)
+    if key not in _streams:
+        _streams[key] = torch.cuda.Stream(device=key[0])
+    return _streams[key]
+
+
+def fork(which=WGRAD):
     """Order the auxiliary stream after everything issued so far on the current stream."""
     if _enabled:
-        aux_stream().wait_stream(torch.cuda.current_stream())
+        aux_stream(which).wait_stream(torch.cuda.current_stream())
 
 
-def join():
+def join(which=WGRAD):
     """Order the current stream after everything issued so far on the auxiliary stream."""
     if _enabled:
-        torch.cuda.current_stream().wait_stream(aux_stream())
+        torch.cuda.current_stream().wait_stream(aux_stream(which))
 
 
 @contextlib.contextmanager
-def on_aux():
+def on_aux(which=WGRAD):
     """Issue the enclosed launches on the auxiliary stream (no-op when overlap is disabled)."""
     if not _enabled:
         yield
         return
-    with torch.cuda.stream(aux_stream()):
+    with torch.cuda.stream(aux_stream(which)):
         yield

@@ -198,6 +198,12 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, uint32_t tmem_base,
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
+      // Keep the mask words opaque until here.  Without this the compiler folds every mask load into predicate bits
+      // right behind the load (FSETP on the freshly loaded registers), which turns the 8 independent loads into 8
+      // serial memory round trips per chunk: +42 % on the 64-channel data-gradient kernels (scripts/ab_conv.py).
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("" : "+f"(msk4[i].x), "+f"(msk4[i].y), "+f"(msk4[i].z), "+f"(msk4[i].w));
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(wbase + lane * 128 + ((c ^ (lane & 7)) << 4)) =

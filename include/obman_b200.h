@@ -126,10 +126,13 @@ int obman_pack_bf16(const float* w, long long ldw, int rows, int K, float* out, 
  * (mano_train/networks/bases/resnet.py:19-23,38-54,110-152) share it.  x (n_img,h_in,w_in,c_in),
  * c_in % 4 == 0; w (c_out, w_slots*c_in), tap t uses weight slot tap_wslot[t] (NULL: t) and reads input
  * pixel (h + tap_dh[t], w + tap_dw[t]) of view tap_phase[t] = ph*2+pw of x[:, ph::in_step, pw::in_step]
- * (zero outside the view).  out is written at n*o_sN + h*o_sH + w*o_sW + c (elements) for h < h_out,
+ * (zero outside the view).  x_sN / x_sH / x_sW: element strides of x (all 0 = dense NHWC; multiples of 4); the
+ * pixel stride may be smaller than c_in, consecutive pixels then overlap (sliding window over a narrower tensor:
+ * the stem reads 4 neighbouring 16-channel pixels of obman_stem_pack's output as one 64-channel pixel).
+ * out is written at n*o_sN + h*o_sH + w*o_sW + c (elements) for h < h_out,
  * w < w_out; bias[c_out], addend / mask_src indexed like out (NULL to disable), relu flag. */
 int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, int c_in, int in_step,
-                    const float* w, const float* w_lo, int c_out, int w_slots, int num_taps,
+                    long long x_sN, long long x_sH, long long x_sW, const float* w, const float* w_lo, int c_out, int w_slots, int num_taps,
                     const int* tap_dh, const int* tap_dw, const int* tap_phase, const int* tap_wslot,
                     float* out, int h_out, int w_out, long long o_sN, long long o_sH, long long o_sW,
                     const float* bias, const float* addend, const float* mask_src, int relu,
@@ -137,15 +140,18 @@ int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, int c_in, int
 
 /* obman_wgrad_nhwc: dw[co, t*c_in + ci] = sum_{n,h,w} dy[n,h,w,co] * xview_t[n, h+dh[t], w+dw[t], ci];
  * weight gradient of the convolution above and (h = 1) of obman_gemm, as ONE GEMM with the taps stacked
- * along N.  c_out, c_in multiples of 32.  dw (c_out, num_taps*c_in) is overwritten. */
+ * along N.  c_out, c_in multiples of 32.  dw (c_out, num_taps*c_in) is overwritten.  x_sN / x_sH / x_sW as above. */
 int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out, int c_out, const float* x,
-                     int h_in, int w_in, int c_in, int in_step, int num_taps, const int* tap_dh,
+                     int h_in, int w_in, int c_in, int in_step, long long x_sN, long long x_sH,
+                     long long x_sW, int num_taps, const int* tap_dh,
                      const int* tap_dw, const int* tap_phase, float* dw, int passes, void* stream);
 
 /* ---- Encoder helpers (bandwidth-bound; mano_train/networks/bases/resnet.py:154-188) -----------------------
- * obman_stem_pack: x (B,3,H,W) NCHW -> out (B,H/2,W/2,64) NHWC: 2x2 space-to-depth (12 channels) with the four
- * horizontal taps of the 7x7/2 stem packed along channels (q*12 + (ph*2+pw)*3 + c, 16 zero channels), so that the
- * stem runs as a 4-tap (vertical), 64-channel obman_conv_nhwc (K = 256). */
+ * obman_stem_pack: x (B,3,H,W) NCHW -> out (B, H/2, W/2 + 4, 16) NHWC: 2x2 space-to-depth, channel
+ * (ph*2+pw)*3 + c (12 real + 4 zero channels), two zero pixels of padding on either side of every row.  Read through
+ * an overlapping view (pixel stride 16, 64 channels: obman_conv_nhwc's x_sW) the four horizontal taps of the 7x7/2
+ * stem sit side by side, so the stem runs as a 4-tap (vertical), 64-channel convolution (K = 256) without ever
+ * materialising the 4x replicated tensor. */
 int obman_stem_pack(const float* x, int B, int H, int W, float* out, void* stream);
 /* BatchNorm(eval) folding + weight re-layout, once per step.  w (O,I,KH,KW); gamma/beta/mean/var (O) or NULL
  * (no BN), cbias (O) conv bias or NULL: shift = beta + (cbias - mean)*scale (no BN: shift = cbias).
@@ -153,7 +159,7 @@ int obman_stem_pack(const float* x, int B, int H, int W, float* out, void* strea
  * packed = 1: wf / wft in the obman_pack_bf16 layout instead (Ip % 32 == 0, *_lo NULL; wft rows are
  * KH*KW*Op long, Op = O rounded up to 32, padding zeroed by the caller).
  * wf (O, KH*KW*Ip) fprop operand, wft (I, KH*KW*O) dgrad operand
- * (NULL to skip), shift/scale/rstd (O).  stem=1: (O,3,7,7) filter -> (O, 4*64) layout of obman_stem_pack. */
+ * (NULL to skip), shift/scale/rstd (O).  stem=1: (O,3,7,7) filter -> (O, 4*64): slot = vertical tap, channel q*16 + (ph*2+pw)*3 + c. */
 int obman_fold_conv(const float* w, const float* cbias, const float* gamma, const float* beta, const float* mean,
                     const float* var, float eps, int O, int I, int KH, int KW, int Ip, int stem,
                     int packed, float* wf, float* wf_lo, float* wft, float* wft_lo, float* shift,

@@ -1,7 +1,7 @@
 // Bandwidth-bound helpers around the tensor-core convolutions of the ResNet-18 encoder
 // (mano_train/networks/bases/resnet.py:154-188) and the parameter update:
-//   stem_pack        NCHW image -> space-to-depth NHWC with the 4 horizontal taps packed along channels (48 real + 16
-//                    zero channels) so that the 7x7/2 stem becomes a 4-tap shifted-box convolution (K = 256) on the same
+//   stem_pack        NCHW image -> space-to-depth NHWC (16 channels, row padding) whose overlapping 64-channel view
+//                    turns the 7x7/2 stem into a 4-tap shifted-box convolution (K = 256) on the same
 //                    TMA path as every other conv
 //   fold_conv        BatchNorm(eval) folding + OIHW -> (O, KH*KW*I) / (I, KH*KW*O) re-layout, once per step
 //   maxpool 3x3/2    forward (with arg-max) and backward
@@ -21,33 +21,39 @@ __device__ __forceinline__ float to_tf32_rna_dev(float x) {
   return __uint_as_float(r);
 }
 
-// x (B,3,H,W) NCHW -> out (B, H/2, W/2, 64): space-to-depth (2x2 blocks -> 12 channels) with the FOUR horizontal
-// taps of the 7x7/2 stem packed along the channel axis:
-//   out[b,i,j, q*12 + (ph*2+pw)*3 + c] = x[b, c, 2i+ph, 2(j+q-2)+pw]   (0 outside the image), q = 0..3; channels 48..63 = 0
-// so that the stem becomes a 4-tap (vertical) x 64-channel shifted-box convolution: K = 256 instead of 16 x 32 = 512.
+// x (B,3,H,W) NCHW -> out (B, H/2, W/2 + 4, 16): 2x2 space-to-depth with two zero pixels on either side of a row,
+//   out[b, i, j + 2, (ph*2+pw)*3 + c] = x[b, c, 2i+ph, 2j+pw],  channels 12..15 = 0.
+// The 7x7/2 stem reads it through an overlapping view (pixel stride 16 floats, 64 channels = pixels j-2 .. j+1 of
+// the unpadded row): 4 vertical taps x 64 channels, K = 256, without materialising the 4x replicated tensor.
+// One thread per output pixel: 12 image reads (consecutive threads = consecutive j: 8-byte stride per (c, ph) row
+// segment, both pw of a segment are consumed by the same thread) and four float4 stores.
 __global__ void __launch_bounds__(256)
 stem_pack_kernel(const float* __restrict__ x, int B, int H, int W, float* __restrict__ out) {
-  const int Ho = H / 2, Wo = W / 2;
-  const size_t total = (size_t)B * Ho * Wo * 16;  // one float4 (4 channels) per thread
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int q4 = (int)(t & 15);
-  size_t p = t >> 4;
-  const int j = (int)(p % Wo); p /= Wo;
-  const int i = (int)(p % Ho);
-  const int b = (int)(p / Ho);
-  float v[4] = {0.f, 0.f, 0.f, 0.f};
-  if (q4 < 12) {
+  const int Ho = H / 2, Wo = W / 2, Wp = Wo + 4;
+  const int jp = blockIdx.x * blockDim.x + threadIdx.x;   // padded column
+  const int i = blockIdx.y, b = blockIdx.z;
+  if (jp >= Wp) return;
+  float4 v[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int chn = q4 * 4 + e;  // 0..47
-      const int q = chn / 12, ch = chn - q * 12;
-      const int ph = ch / 6, pw = (ch / 3) & 1, c = ch % 3;
-      const int jj = j + q - 2;
-      if (jj >= 0 && jj < Wo) v[e] = __ldg(x + (((size_t)b * 3 + c) * H + (2 * i + ph)) * W + (2 * jj + pw));
-    }
+  for (int e = 0; e < 4; ++e) v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int j = jp - 2;
+  if (j >= 0 && j < Wo) {
+    float ch[12];
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float2 p2 = __ldg(reinterpret_cast<const float2*>(x + (((size_t)b * 3 + c) * H + (2 * i + ph)) * W) + j);
+        ch[(ph * 2 + 0) * 3 + c] = p2.x;
+        ch[(ph * 2 + 1) * 3 + c] = p2.y;
+      }
+    v[0] = make_float4(ch[0], ch[1], ch[2], ch[3]);
+    v[1] = make_float4(ch[4], ch[5], ch[6], ch[7]);
+    v[2] = make_float4(ch[8], ch[9], ch[10], ch[11]);
   }
-  reinterpret_cast<float4*>(out)[t] = make_float4(v[0], v[1], v[2], v[3]);
+  float4* dst = reinterpret_cast<float4*>(out + (((size_t)b * Ho + i) * Wp + jp) * 16);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) dst[e] = v[e];
 }
 
 // Folded weights for one convolution.  w (O,I,KH,KW); scale s[o] = gamma*rsqrt(var+eps) (or 1 without BN).
@@ -90,12 +96,12 @@ fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
     shift[o] = gamma ? beta[o] + (cb - mean[o]) * s : cb;
   }
   if (stem) {
-    // vertical tap a in [-2,1] -> slot a+2; channel q*12 + (ph*2+pw)*3 + c <-> kh = 2a+ph+3, kw = 2(q-2)+pw+3
+    // vertical tap a in [-2,1] -> slot a+2; channel q*16 + (ph*2+pw)*3 + c <-> kh = 2a+ph+3, kw = 2(q-2)+pw+3
     for (int k = threadIdx.x; k < 4 * 64; k += blockDim.x) {
       const int slot = k >> 6, chn = k & 63;
       float v = 0.f;
-      if (chn < 48) {
-        const int a = slot - 2, q = chn / 12, ch = chn - q * 12;
+      if ((chn & 15) < 12) {
+        const int a = slot - 2, q = chn >> 4, ch = chn & 15;
         const int ph = ch / 6, pw = (ch / 3) & 1, c = ch % 3;
         const int kh = 2 * a + ph + 3, kw = 2 * (q - 2) + pw + 3;
         if (kh >= 0 && kh < 7 && kw >= 0 && kw < 7) v = s * w[((o * 3 + c) * 7 + kh) * 7 + kw];
@@ -133,15 +139,14 @@ fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, float* __restrict__ out,
                    unsigned char* __restrict__ idx) {
+  // grid (ceil(Wo*C/4 / 256), Ho, B): 32-bit index arithmetic only (the flat 64-bit div/mod version was
+  // instruction bound at ~1/3 of the HBM rate)
   const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
-  const size_t total = (size_t)B * Ho * Wo * C4;
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int c4 = (int)(t % C4);
-  size_t p = t / C4;
-  const int j = (int)(p % Wo); p /= Wo;
-  const int i = (int)(p % Ho);
-  const int b = (int)(p / Ho);
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= Wo * C4) return;
+  const int c4 = u % C4, j = u / C4;
+  const int i = blockIdx.y, b = blockIdx.z;
+  const size_t t = ((size_t)b * Ho + i) * (size_t)(Wo * C4) + u;
   float best[4] = {-3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
   int bi[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -167,15 +172,13 @@ maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C, floa
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const float* __restrict__ gout, const unsigned char* __restrict__ idx, int B, int H,
                    int W, int C, float* __restrict__ gx) {
+  // grid (ceil(W*C/4 / 256), H, B), see maxpool_fwd_kernel
   const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
-  const size_t total = (size_t)B * H * W * C4;
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int c4 = (int)(t % C4);
-  size_t p = t / C4;
-  const int w = (int)(p % W); p /= W;
-  const int h = (int)(p % H);
-  const int b = (int)(p / H);
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= W * C4) return;
+  const int c4 = u % C4, w = u / C4;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const size_t t = ((size_t)b * H + h) * (size_t)(W * C4) + u;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int i = (h + 1) / 2 - 1; i <= (h + 1) / 2; ++i) {
     if (i < 0 || i >= Ho) continue;
@@ -263,7 +266,7 @@ bn_wgrad_finish_kernel(const float* __restrict__ dwraw, long long dw_ld, const f
     if (stem) {
       const int kh = t / 7, kw = t % 7;
       const int a = (kh - 3) >> 1, ph = (kh - 3) & 1, q = ((kw - 3) >> 1) + 2, pw = (kw - 3) & 1;
-      raw = dwraw[(size_t)o * dw_ld + (a + 2) * 64 + q * 12 + (ph * 2 + pw) * 3 + i];
+      raw = dwraw[(size_t)o * dw_ld + (a + 2) * 64 + q * 16 + (ph * 2 + pw) * 3 + i];
     } else {
       raw = dwraw[(size_t)o * dw_ld + (size_t)t * Ip + i];
     }
@@ -406,8 +409,11 @@ extern "C" int obman_pointmlp_l1_bwd(const float* g, int B, int N, int C, int ld
 
 extern "C" int obman_stem_pack(const float* x, int B, int H, int W, float* out, void* stream) {
   OBMAN_REQUIRE(x && out && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "obman_stem_pack: bad arguments");
-  const size_t total = (size_t)B * (H / 2) * (W / 2) * 16;
-  stem_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, out);
+  OBMAN_REQUIRE(((uintptr_t)x & 7) == 0 && ((uintptr_t)out & 15) == 0, "obman_stem_pack: misaligned pointers");
+  OBMAN_REQUIRE(B <= 65535 && H / 2 <= 65535, "obman_stem_pack: batch / height too large for the grid");
+  const int Wp = W / 2 + 4;
+  dim3 grid((unsigned)((Wp + 127) / 128), (unsigned)(H / 2), (unsigned)B);
+  stem_pack_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, B, H, W, out);
   return check_launch("stem_pack_kernel");
 }
 
@@ -429,16 +435,18 @@ extern "C" int obman_fold_conv(const float* w, const float* cbias, const float* 
 extern "C" int obman_maxpool_fwd(const float* x, int B, int H, int W, int C, float* out,
                                  unsigned char* idx, void* stream) {
   OBMAN_REQUIRE(x && out && idx && B > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "obman_maxpool_fwd: bad arguments");
-  const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 4);
-  maxpool_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, out, idx);
+  OBMAN_REQUIRE(B <= 65535 && H / 2 <= 65535, "obman_maxpool_fwd: batch / height too large for the grid");
+  dim3 grid((unsigned)(((W / 2) * (C / 4) + 255) / 256), (unsigned)(H / 2), (unsigned)B);
+  maxpool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, B, H, W, C, out, idx);
   return check_launch("maxpool_fwd_kernel");
 }
 
 extern "C" int obman_maxpool_bwd(const float* gout, const unsigned char* idx, int B, int H, int W, int C,
                                  float* gx, void* stream) {
   OBMAN_REQUIRE(gout && idx && gx && B > 0 && H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "obman_maxpool_bwd: bad arguments");
-  const size_t total = (size_t)B * H * W * (C / 4);
-  maxpool_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(gout, idx, B, H, W, C, gx);
+  OBMAN_REQUIRE(B <= 65535 && H <= 65535, "obman_maxpool_bwd: batch / height too large for the grid");
+  dim3 grid((unsigned)((W * (C / 4) + 255) / 256), (unsigned)H, (unsigned)B);
+  maxpool_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout, idx, B, H, W, C, gx);
   return check_launch("maxpool_bwd_kernel");
 }
 

@@ -1162,7 +1162,7 @@ extern "C" int obman_gemm(const float* A, long long lda, const float* W, const f
 //          (ph*2+pw) when in_step == 2, i.e. of x[:, ph::2, pw::2, :]; with in_step == 1 there is a single view.
 //   out  : written at element offset n*o_sN + h*o_sH + w*o_sW + c   (lets dgrad write strided phases)
 extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, int c_in, int in_step,
-                               const float* w, const float* w_lo, int c_out, int w_slots, int num_taps,
+                               long long x_sN, long long x_sH, long long x_sW, const float* w, const float* w_lo, int c_out, int w_slots, int num_taps,
                                const int* tap_dh, const int* tap_dw, const int* tap_phase, const int* tap_wslot,
                                float* out, int h_out, int w_out, long long o_sN, long long o_sH, long long o_sW,
                                const float* bias, const float* addend, const float* mask_src, int relu,
@@ -1178,6 +1178,12 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
   OBMAN_REQUIRE(passes == 1 || passes == 3 || passes == OBMAN_PREC_3XBF16, "obman_conv_nhwc: passes must be 1, 2 or 3");
   OBMAN_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)w & 15) == 0 && ((uintptr_t)w_lo & 15) == 0,
                 "obman_conv_nhwc: x/w must be 16-byte aligned");
+  // x strides in elements (0 = dense NHWC).  The pixel stride may be SMALLER than c_in: consecutive pixels then
+  // overlap (a sliding window over a narrower tensor; the stem reads 4 neighbouring 16-channel pixels as 64 channels).
+  const bool x_dense = x_sN == 0 && x_sH == 0 && x_sW == 0;
+  if (x_dense) { x_sW = c_in; x_sH = (long long)w_in * c_in; x_sN = (long long)h_in * w_in * c_in; }
+  OBMAN_REQUIRE(x_sW > 0 && x_sH > 0 && x_sN > 0 && x_sW % 4 == 0 && x_sH % 4 == 0 && x_sN % 4 == 0,
+                "obman_conv_nhwc: x strides must be positive multiples of 4 elements (or all 0)");
   {
     // halo kernel: stride-1 taps inside the 3x3 neighbourhood, packed bf16 weights
     static int halo_on = -1;
@@ -1185,7 +1191,7 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
       const char* e = getenv("OBMAN_CONV_HALO");
       halo_on = (e && e[0] == '1') ? 1 : 0;   // off by default: measured no faster (the loop is MMA-issue bound)
     }
-    bool ok = halo_on && passes == OBMAN_PREC_3XBF16 && in_step == 1 && num_taps >= 2 && c_in % 32 == 0;
+    bool ok = halo_on && x_dense && passes == OBMAN_PREC_3XBF16 && in_step == 1 && num_taps >= 2 && c_in % 32 == 0;
     for (int t = 0; ok && t < num_taps; ++t) ok = tap_dh[t] >= -1 && tap_dh[t] <= 1 && tap_dw[t] >= -1 && tap_dw[t] <= 1;
     int hTW = 1;
     while (hTW * 2 <= w_out && hTW * 2 <= 16) hTW *= 2;
@@ -1274,10 +1280,9 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
     if (!used[ph]) continue;
     const int py = ph >> 1, px = ph & 1;
     uint64_t dims[4] = {(uint64_t)c_in, (uint64_t)(w_in / in_step), (uint64_t)(h_in / in_step), (uint64_t)n_img};
-    uint64_t strides[3] = {(uint64_t)c_in * 4 * in_step, (uint64_t)w_in * c_in * 4 * in_step,
-                           (uint64_t)h_in * w_in * c_in * 4};
+    uint64_t strides[3] = {(uint64_t)x_sW * 4 * in_step, (uint64_t)x_sH * 4 * in_step, (uint64_t)x_sN * 4};
     uint32_t box[4] = {BK, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
-    const float* base = x + ((long long)py * w_in + px) * c_in;
+    const float* base = x + (long long)py * x_sH + (long long)px * x_sW;
     int rc = make_tensor_map(&maps.a[ph], base, 4, dims, strides, box);
     if (rc) return rc;
   }
@@ -1308,7 +1313,8 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
 // read MN-major (channels contiguous, pixels along K) straight from NHWC; the pixel reduction is split over
 // gridDim.z (a whole number of waves) and combined with fp32 atomics.  c_out, c_in multiples of 32.
 extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out, int c_out,
-                                const float* x, int h_in, int w_in, int c_in, int in_step, int num_taps,
+                                const float* x, int h_in, int w_in, int c_in, int in_step, long long x_sN,
+                                long long x_sH, long long x_sW, int num_taps,
                                 const int* tap_dh, const int* tap_dw, const int* tap_phase, float* dw,
                                 int passes, void* stream) {
   OBMAN_REQUIRE(dy && x && dw && tap_dh && tap_dw, "obman_wgrad_nhwc: null argument");
@@ -1321,6 +1327,9 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
   OBMAN_REQUIRE(passes == 1 || passes == 3 || passes == OBMAN_PREC_3XBF16, "obman_wgrad_nhwc: passes must be 1, 2 or 3");
   const bool bf = passes == OBMAN_PREC_3XBF16;
   OBMAN_REQUIRE(((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0, "obman_wgrad_nhwc: dy/x must be 16-byte aligned");
+  if (x_sN == 0 && x_sH == 0 && x_sW == 0) { x_sW = c_in; x_sH = (long long)w_in * c_in; x_sN = (long long)h_in * w_in * c_in; }
+  OBMAN_REQUIRE(x_sW > 0 && x_sH > 0 && x_sN > 0 && x_sW % 4 == 0 && x_sH % 4 == 0 && x_sN % 4 == 0,
+                "obman_wgrad_nhwc: x strides must be positive multiples of 4 elements (or all 0)");
   cudaStream_t st = (cudaStream_t)stream;
   int kTW = 1;
   while (kTW * 2 <= w_out && kTW * 2 <= 32) kTW *= 2;
@@ -1386,10 +1395,9 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
     if (!used[ph]) continue;
     const int py = ph >> 1, px = ph & 1;
     uint64_t dims[5] = {32, (uint64_t)(w_in / in_step), (uint64_t)(h_in / in_step), (uint64_t)n_img, (uint64_t)(c_in / 32)};
-    uint64_t strides[4] = {(uint64_t)c_in * 4 * in_step, (uint64_t)w_in * c_in * 4 * in_step,
-                           (uint64_t)h_in * w_in * c_in * 4, 128};
+    uint64_t strides[4] = {(uint64_t)x_sW * 4 * in_step, (uint64_t)x_sH * 4 * in_step, (uint64_t)x_sN * 4, 128};
     uint32_t box[5] = {32, (uint32_t)kTW, (uint32_t)kTH, (uint32_t)kTN, (uint32_t)prog.grp_per_load};
-    const float* base = x + ((long long)py * w_in + px) * c_in;
+    const float* base = x + (long long)py * x_sH + (long long)px * x_sW;
     int rc = make_tensor_map(&maps.a[1 + ph], base, 5, dims, strides, box, mn_swizzle);
     if (rc) return rc;
   }

@@ -153,11 +153,17 @@ def dgrad_taps(ksize, stride, pad, out_phase=(0, 0)):
 
 def conv_nhwc(x, w, c_out, taps, in_step, out, h_out, w_out, out_strides=None, out_offset=0,
               bias=None, addend=None, mask_src=None, relu=False, passes=3, w_slots=None, algo_k=None,
-              w_lo=None):
+              w_lo=None, x_geom=None):
     """Raw obman_conv_nhwc call.  x (N,H,W,C) contiguous; w (c_out, slots*C); taps = (dh, dw, phase, slot).
-    ``out`` is any tensor whose storage receives element (n,h,w,c) at out_offset + n*sN + h*sH + w*sW + c."""
+    ``out`` is any tensor whose storage receives element (n,h,w,c) at out_offset + n*sN + h*sH + w*sW + c.
+    ``x_geom`` = (N, H, W, C, sN, sH, sW): read ``x``'s storage as that strided (possibly overlapping) NHWC view."""
     _chk(x, "x"); _chk(w, "w")
-    n_img, h_in, w_in, c_in = x.shape
+    if x_geom is None:
+        n_img, h_in, w_in, c_in = x.shape
+        xs = (0, 0, 0)
+    else:
+        n_img, h_in, w_in, c_in = x_geom[:4]
+        xs = tuple(int(v) for v in x_geom[4:7])
     dh, dw, phase, slot = taps
     if w_slots is None:
         w_slots = w.shape[1] // c_in
@@ -170,7 +176,7 @@ def conv_nhwc(x, w, c_out, taps, in_step, out, h_out, w_out, out_strides=None, o
 
     k_eff = algo_k if algo_k is not None else len(dh) * c_in
     _tc_call(2.0 * n_img * h_out * w_out * c_out * k_eff,
-             "obman_conv_nhwc", ptr(x), n_img, h_in, w_in, c_in, int(in_step), ptr(w),
+             "obman_conv_nhwc", ptr(x), n_img, h_in, w_in, c_in, int(in_step), xs[0], xs[1], xs[2], ptr(w),
              ptr(w_lo) if passes == 3 else None, int(c_out),
          int(w_slots), len(dh), _ints(dh), _ints(dw), _ints(phase) if phase is not None else None,
          _ints(slot), off(out), int(h_out), int(w_out), int(out_strides[0]), int(out_strides[1]),
@@ -179,20 +185,25 @@ def conv_nhwc(x, w, c_out, taps, in_step, out, h_out, w_out, out_strides=None, o
     return out
 
 
-def wgrad_nhwc(dy, x, taps, in_step, dw_out, passes=3, algo_k=None):
+def wgrad_nhwc(dy, x, taps, in_step, dw_out, passes=3, algo_k=None, x_geom=None):
     """dw_out (c_out, num_taps*c_in) = sum over pixels dy (N,Ho,Wo,c_out) x shifted x (N,H,W,c_in); the tap
-    order is the weight-slot order (taps = (dh, dw, phase, slot) with slot == position)."""
+    order is the weight-slot order (taps = (dh, dw, phase, slot) with slot == position).  ``x_geom`` as in conv_nhwc."""
     _chk(dy, "dy"); _chk(x, "x"); _chk(dw_out, "dw")
     n_img, h_out, w_out, c_out = dy.shape
-    _, h_in, w_in, c_in = x.shape
+    if x_geom is None:
+        _, h_in, w_in, c_in = x.shape
+        xs = (0, 0, 0)
+    else:
+        _, h_in, w_in, c_in = x_geom[:4]
+        xs = tuple(int(v) for v in x_geom[4:7])
     dh, dw, phase, slot = taps
     if list(slot) != list(range(len(dh))):
         raise RuntimeError("wgrad_nhwc: taps must be listed in weight-slot order")
     k_eff = algo_k if algo_k is not None else len(dh) * c_in
     _tc_call(2.0 * n_img * h_out * w_out * c_out * k_eff,
              "obman_wgrad_nhwc", ptr(dy), n_img, h_out, w_out, c_out, ptr(x), h_in, w_in, c_in,
-             int(in_step), len(dh), _ints(dh), _ints(dw), _ints(phase) if phase is not None else None,
-             ptr(dw_out), int(passes), stream_ptr(),
+             int(in_step), xs[0], xs[1], xs[2], len(dh), _ints(dh), _ints(dw),
+             _ints(phase) if phase is not None else None, ptr(dw_out), int(passes), stream_ptr(),
              tag="n%d %dx%d c%d->%d taps%d" % (n_img, h_out, w_out, c_in, c_out, len(dh)))
     return dw_out
 

@@ -37,6 +37,13 @@ def _empty(*shape):
     return torch.empty(shape, device="cuda", dtype=torch.float32)
 
 
+def stem_view(xs):
+    """xs (B, Ho, Wo + 4, 16) from obman_stem_pack -> geometry of the overlapping (B, Ho, Wo, 64) view the stem
+    convolution reads: pixel stride 16 floats, so pixel j of the view covers unpadded pixels j-2 .. j+1."""
+    B, Ho, Wp, C = xs.shape
+    return (B, Ho, Wp - 4, 64, Ho * Wp * C, Wp * C, C)
+
+
 class _NullCtx(object):
     def __enter__(self):
         return self
@@ -79,7 +86,8 @@ class _Unit(object):
         out = _empty(x.shape[0], h_out, w_out, self.O)
         dense.conv_nhwc(x, self.wf, self.O, self.taps, self.in_step, out, h_out, w_out, bias=self.shift,
                         addend=addend, relu=relu, passes=passes, w_slots=self.slots,
-                        algo_k=147 if self.stem else None, w_lo=self.wf_lo)
+                        algo_k=147 if self.stem else None, w_lo=self.wf_lo,
+                        x_geom=stem_view(x) if self.stem else None)
         return out
 
     def dgrad(self, g, h_in, w_in, addend=None, mask_src=None, passes=3):
@@ -118,7 +126,7 @@ class _Unit(object):
     def wgrad(self, g, x, passes=3):
         dwraw = _empty(self.O, self.slots * self.Ip)
         dense.wgrad_nhwc(g, x, self.taps, self.in_step, dwraw, passes=passes,
-                         algo_k=147 if self.stem else None)
+                         algo_k=147 if self.stem else None, x_geom=stem_view(x) if self.stem else None)
         return dwraw
 
     def finish(self, dwraw, gbeta_sum):
@@ -165,7 +173,7 @@ class _EncoderFn(torch.autograd.Function):
         streams.fork()
         with streams.on_aux():
             units.extend(make_unit(i) for i in range(1, len(specs)))
-        xs = _empty(B, H // 2, W // 2, 64)
+        xs = _empty(B, H // 2, W // 2 + 4, 16)
         call("obman_stem_pack", ptr(images), B, H, W, ptr(xs), st)
         c1 = units[0].fprop(xs, H // 2, W // 2, relu=True, passes=pf)
         if DEBUG is not None:

@@ -40,7 +40,8 @@ def _run(cfg, B, H, seed, n_gt=600, sides=None):
     return model, state, (total, results, losses), (ototal, oresults, olosses)
 
 
-def _check(model, state, got, ref, rtol=1e-4, grad_rtol=5e-2):
+def _check(model, state, got, ref, rtol=1e-4, grad_rtol=5e-2, key_rtol=None):
+    key_rtol = key_rtol or {}
     total, results, losses = got
     ototal, oresults, olosses = ref
     assert abs(total.item() - ototal.item()) < rtol * abs(ototal.item()), (total.item(), ototal.item())
@@ -48,7 +49,8 @@ def _check(model, state, got, ref, rtol=1e-4, grad_rtol=5e-2):
         if oval is None or key in ("total_loss", "mano_total_loss", "contact_loss"):
             continue
         print("  %-22s %.7g  oracle %.7g" % (key, float(losses[key]), float(oval)))
-        assert abs(float(losses[key]) - float(oval)) <= rtol * abs(float(oval)) + 1e-6, (key, float(losses[key]), float(oval))
+        tol = key_rtol.get(key, rtol)
+        assert abs(float(losses[key]) - float(oval)) <= tol * abs(float(oval)) + 1e-6, (key, float(losses[key]), float(oval))
     for key in ("verts", "joints", "objpoints3d"):
         if key in oresults:
             o = oresults[key].detach().numpy()
@@ -88,7 +90,11 @@ def test_handnet_with_laplacian_regulariser():
     cfg.update(atlas_lambda_laplacian=0.05, contact_lambda=0, collision_lambda=0)
     model, state, got, ref = _run(cfg, B=2, H=64, seed=20)
     assert "atlas_laplac" in got[2] and float(got[2]["atlas_laplac"]) > 0
-    _check(model, state, got, ref)
+    # The Laplacian of the (smooth, random-init) predicted mesh is a difference of neighbouring vertices: |L V| ~ 0.1
+    # for |V| ~ 40 mm, so the 1e-5 relative error of the vertex coordinates (within the 1e-4 bound checked below on
+    # "objpoints3d") is amplified ~100x in this one scalar.  The kernel itself is held to 1e-4 on identical vertices
+    # in tests/test_mesh_regul.py; here the end-to-end value gets the amplified bound.
+    _check(model, state, got, ref, key_rtol={"atlas_laplac": 2e-3})
     model.decay_regul(0.5)
     assert model.atlas_loss.lambda_laplacian == pytest.approx(0.025)
 

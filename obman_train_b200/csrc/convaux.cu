@@ -224,6 +224,46 @@ meanpool_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x,
   gx[t] = x[t] > 0.f ? gout[(size_t)b * C + c] / (float)P : 0.f;
 }
 
+// Vector variant (C % 4 == 0, ld % 4 == 0, 16-byte aligned x): every thread owns one float4 column group and walks
+// rows with stride (256 / groups); four independent loads in flight per thread.  grid (1, row chunks).
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+colsum_v4_kernel(const float* __restrict__ x, long long rows, int C, long long ld, long long rows_per_block,
+                 float* __restrict__ out) {
+  extern __shared__ float4 red4[];            // [rows_in_flight][groups]
+  const int groups = C >> 2;                  // float4 column groups, <= 256
+  const int rpb = 256 / groups;               // rows handled per block iteration
+  const int g = threadIdx.x % groups, rr = threadIdx.x / groups;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rr < rpb) {
+    long long r = r0 + rr;
+    for (; r + (long long)(UNROLL - 1) * rpb < r1; r += (long long)UNROLL * rpb) {
+      float4 v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(x + (r + (long long)u * rpb) * ld) + g);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; r < r1; r += rpb) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld) + g);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    red4[rr * groups + g] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < rpb; ++k) {
+      const float4 v = red4[k * groups + threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    float* o = out + 4 * threadIdx.x;
+    atomicAdd(o, t.x); atomicAdd(o + 1, t.y); atomicAdd(o + 2, t.z); atomicAdd(o + 3, t.w);
+  }
+}
+
 // out[c] (+)= sum_r x[r, c] ; x has row stride ld. grid (col tiles of 32, row chunks); out zero-initialised.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const float* __restrict__ x, long long rows, int C, long long ld, long long rows_per_block,
@@ -468,6 +508,17 @@ extern "C" int obman_colsum(const float* x, long long rows, int C, long long ld,
   OBMAN_REQUIRE(x && out && rows > 0 && C > 0 && ld >= C, "obman_colsum: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(out, 0, sizeof(float) * C, st);
+  if (C % 4 == 0 && ld % 4 == 0 && C <= 1024 && (((uintptr_t)x) & 15) == 0) {
+    const int groups = C / 4, rpb = 256 / groups;
+    long long chunks = 4LL * num_sms();
+    const long long min_rows = (long long)rpb * 8;   // at least 8 block iterations per chunk
+    if (chunks > (rows + min_rows - 1) / min_rows) chunks = (rows + min_rows - 1) / min_rows;
+    if (chunks < 1) chunks = 1;
+    const long long per = (rows + chunks - 1) / chunks;
+    colsum_v4_kernel<4><<<dim3(1, (unsigned)((rows + per - 1) / per)), 256, sizeof(float4) * rpb * groups, st>>>(
+        x, rows, C, ld, per, out);
+    return check_launch("colsum_v4_kernel");
+  }
   const int ctiles = (C + 31) / 32;
   long long chunks = (4LL * num_sms() + ctiles - 1) / ctiles;
   if (chunks > (rows + 63) / 64) chunks = (rows + 63) / 64;

@@ -97,7 +97,11 @@ class _Unit(object):
         the CHAIN auxiliary stream (disjoint outputs, same inputs)."""
         B = g.shape[0]
         s, k = self.stride, self.k
-        gx = _empty(B, h_in, w_in, self.I)
+        # a 1x1 stride-2 convolution reaches one of the four output phases only: one contiguous memset instead of
+        # three strided fills
+        sparse = s > 1 and k == 1 and addend is None
+        gx = torch.zeros((B, h_in, w_in, self.I), device="cuda", dtype=torch.float32) if sparse \
+            else _empty(B, h_in, w_in, self.I)
         two_lanes = s > 1 and k > 1 and streams.enabled()
         if two_lanes:
             streams.fork(streams.CHAIN)
@@ -107,13 +111,11 @@ class _Unit(object):
                 off = (ph * w_in + pw) * self.I
                 strides = (h_in * w_in * self.I, s * w_in * self.I, s * self.I)
                 if not dh:  # this output phase receives no contribution from the convolution
-                    view = gx[:, ph::s, pw::s]
                     if addend is not None:
+                        view = gx[:, ph::s, pw::s]
                         src = addend[:, ph::s, pw::s]
                         view.copy_(src if mask_src is None else src * (mask_src[:, ph::s, pw::s] > 0))
-                    else:
-                        view.zero_()
-                    continue
+                    continue  # (without addend: gx was allocated zero-filled, see above)
                 lane = streams.on_aux(streams.CHAIN) if (two_lanes and ph == 1) else _NullCtx()
                 with lane:
                     dense.conv_nhwc(g, self.wft, self.I, (dh, dw, None, slot), 1, gx, h_in // s, w_in // s,

@@ -45,3 +45,48 @@ def test_linear_and_point_decoder_autograd_vs_torch():
     assert (y.detach().cpu().double() - yd.detach()).abs().max() < 1e-5 * yd.abs().max()
     for a, r in ((xs, xd), (ws, wd), (bs, bd)):
         assert (a.grad.cpu().double() - r.grad).abs().max() < 1e-4 * r.grad.abs().max()
+
+
+@pytest.mark.parametrize("rows,C,ld", [(64 * 64 * 64, 64, 64), (4096, 512, 512), (41088, 128, 128), (41088, 288, 288),
+                                       (1000, 257, 288), (37, 3, 32), (5, 64, 64), (100003, 16, 16)])
+def test_colsum_vector_and_scalar_paths(rows, C, ld):
+    """BatchNorm-beta / bias gradients: out[c] = sum_r x[r, c] (vector kernel when C and ld are multiples of 4)."""
+    import torch
+    from obman_train_b200 import mlp
+    g = torch.Generator().manual_seed(rows + C)
+    x = torch.randn(rows, ld, generator=g).cuda()
+    got = mlp.colsum(x, C)
+    ref = x[:, :C].double().sum(0)
+    scale = x[:, :C].double().abs().sum(0)
+    assert got.shape == (C,)
+    assert ((got.double() - ref).abs() <= 2e-6 * scale + 1e-6).all()
+
+
+@pytest.mark.parametrize("B,H,C", [(3, 16, 64), (2, 64, 8)])
+def test_maxpool_and_stem_pack_vs_torch(B, H, C):
+    import torch
+    import torch.nn.functional as F
+    from obman_train_b200._lib import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(B * H + C)
+    x = torch.randn(B, H, H, C, generator=g).cuda()   # NHWC
+    out = torch.empty(B, H // 2, H // 2, C, device="cuda")
+    idx = torch.empty(B, H // 2, H // 2, C, device="cuda", dtype=torch.uint8)
+    call("obman_maxpool_fwd", ptr(x), B, H, H, C, ptr(out), ptr(idx), stream_ptr())
+    xr = x.permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    ref = F.max_pool2d(xr, 3, 2, 1)
+    assert torch.equal(out.permute(0, 3, 1, 2), ref)
+    go = torch.randn(B, H // 2, H // 2, C, generator=g).cuda()
+    gx = torch.empty_like(x)
+    call("obman_maxpool_bwd", ptr(go), ptr(idx), B, H, H, C, ptr(gx), stream_ptr())
+    ref.backward(go.permute(0, 3, 1, 2))
+    assert torch.allclose(gx.permute(0, 3, 1, 2), xr.grad, atol=1e-6)
+    # stem pack: (B,3,H,W) -> (B, H/2, W/2 + 4, 16), channel (ph*2+pw)*3 + c, two zero pixels either side
+    img = torch.randn(B, 3, H, H, generator=g).cuda()
+    xs = torch.full((B, H // 2, H // 2 + 4, 16), float("nan"), device="cuda")
+    call("obman_stem_pack", ptr(img), B, H, H, ptr(xs), stream_ptr())
+    assert torch.isfinite(xs).all()
+    assert (xs[:, :, :2] == 0).all() and (xs[:, :, -2:] == 0).all() and (xs[..., 12:] == 0).all()
+    for ph in range(2):
+        for pw in range(2):
+            for c in range(3):
+                assert torch.equal(xs[:, :, 2:-2, (ph * 2 + pw) * 3 + c], img[:, c, ph::2, pw::2])

@@ -75,18 +75,18 @@ def epoch_pass(loader, model, epoch, optimizer=None, debug=False, freeze_batchno
     log = _DeviceLossLog()
     time_meters = AverageMeters()
     dists, vis_rows = [], []
-    captured = False
     end = time.time()
     n_steps = len(loader) if hasattr(loader, "__len__") else None
     for batch_idx, sample in enumerate(loader):
         time_meters.add_loss_value("data_time", time.time() - end)
         if train:
             if use_graph:
-                if not captured:
-                    optimizer.capture(sample)
-                    captured = True
-                optimizer.replay(sample)
+                if getattr(optimizer, "_graph", None) is None:
+                    optimizer.capture(dict(sample))   # the first batch's tensors become the static input buffers
+                optimizer.replay(sample)              # copies this batch (and its left/right mask) into them
                 _, results, losses = optimizer.static_outputs()
+                if "joints" in results:               # static output: the next replay overwrites it
+                    results = dict(results, joints=results["joints"].clone())
             else:
                 _, results, losses = optimizer.step(sample, return_all=True)
         else:

@@ -79,11 +79,30 @@ class ManoBranch(nn.Module):
                           torch.tensor([i for i, f in enumerate(flags) if not f], dtype=torch.long, device=device))
         return cache[key]
 
-    def forward(self, inp, sides, root_palm=False, shape=None, pose=None, use_stereoshape=False):
+    def forward(self, inp, sides, root_palm=False, shape=None, pose=None, use_stereoshape=False, side_mask=None):
+        """``side_mask`` (extension, optional): device bool tensor (B,), True = right hand.  When given, BOTH MANO
+        layers run on the whole batch and the result is selected per sample on the device, so the launch sequence does
+        not depend on the left/right pattern of the batch (a captured CUDA graph stays valid for any ``sides``); the
+        MANO layer is 0.55 MMAC per sample, the duplicate is cheaper than a re-capture.  Without it the reference's
+        gather / scatter by side (manobranch.py:133-207) is used."""
         base_features = self.base_layer(inp)
         pose = mlp.linear(base_features, self.pose_reg.weight, self.pose_reg.bias)
         mano_pose = pose
         B = pose.shape[0]
+        if side_mask is not None and not use_stereoshape:
+            if self.use_shape:
+                shape = mlp.linear(base_features, self.shape_reg[0].weight, self.shape_reg[0].bias)
+            else:
+                shape = None
+            trans = torch.Tensor([0])
+            verts_r, joints_r = self.mano_layer_right(mano_pose, th_betas=shape, th_trans=trans, root_palm=root_palm)
+            verts_l, joints_l = self.mano_layer_left(mano_pose, th_betas=shape, th_trans=trans, root_palm=root_palm)
+            if self.adapt_skeleton:
+                joints_r = torch.einsum("ij,bjc->bic", self.right_skeleton_reg.weight, joints_r)
+                joints_l = torch.einsum("ij,bjc->bic", self.left_skeleton_reg.weight, joints_l)
+            m = side_mask[:B].to(torch.bool).view(B, 1, 1)
+            return {"verts": torch.where(m, verts_r, verts_l), "joints": torch.where(m, joints_r, joints_l),
+                    "shape": shape, "pose": pose}
         flags = [side == "right" for side in sides][:B]
         n_right = int(sum(flags))
         n_left = B - n_right

@@ -129,7 +129,7 @@ class HandNet(nn.Module):
             streams.fork(streams.BRANCH)
             with streams.on_aux(streams.BRANCH):
                 mano_results = self.mano_branch(features, sides=sample[BaseQueries.sides], root_palm=root_palm,
-                                                use_stereoshape=False)
+                                                use_stereoshape=False, side_mask=sample.get("sides_mask"))
                 if not no_loss:
                     mano_total_loss, mano_losses = self.mano_loss.compute_loss(mano_results, sample)
                     if total_loss is None:

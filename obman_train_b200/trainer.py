@@ -64,17 +64,18 @@ class FlatAdamTrainer(object):
     def zero_grad(self):
         self.flat_g.zero_()
 
-    def step(self, sample):
-        """Returns the (device) total loss of this rank's shard."""
+    def step(self, sample, return_all=False):
+        """Returns the (device) total loss of this rank's shard; with ``return_all`` the model's full
+        ``(total_loss, results, losses)`` triple (what epochpass3d.py:80-82 unpacks)."""
         # Gradients are produced by autograd as fresh tensors (p.grad = None, so AccumulateGrad adopts them without
         # an add kernel per parameter) and gathered into the flat buffer with one fused multi-tensor copy.
         for p in self.params:
             p.grad = None
-        loss, _, _ = self.model.forward(sample)
+        loss, results, losses = self.model.forward(sample)
         loss.backward()
         self.gather_grads()
         self.reduce_and_update()
-        return loss
+        return (loss, results, losses) if return_all else loss
 
     def gather_grads(self):
         have = [(v, p.grad) for v, p in zip(self.grad_views, self.params) if p.grad is not None]
@@ -126,18 +127,35 @@ class FlatAdamTrainer(object):
         if self.world_size > 1:
             # NCCL inside a captured graph needs the communicator warmed up outside of capture
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+        sides = self._sides_of(sample)
+        if sides is not None and "sides_mask" not in sample:
+            # graph mode: the left/right pattern enters through a device mask instead of the launch sequence
+            sample["sides_mask"] = torch.tensor([s == "right" for s in sides], dtype=torch.bool).cuda()
+        # the warm-up steps (allocator / cuBLAS-free lazy initialisation outside of capture) must not train: the
+        # parameters, the Adam moments and the step counter are restored afterwards
+        saved = (self.flat_p.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_count)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self.step(sample)
         torch.cuda.current_stream().wait_stream(side)
+        self.flat_p.copy_(saved[0])
+        self.exp_avg.copy_(saved[1])
+        self.exp_avg_sq.copy_(saved[2])
+        self.step_count = saved[3]
+        del saved
         torch.cuda.synchronize()
         self._static_sample = sample
         self._graph = torch.cuda.CUDAGraph()
         steps_before = self.step_count
         with torch.cuda.graph(self._graph):
-            self._static_loss = self.step(sample)
+            loss, results, losses = self.step(sample, return_all=True)
+        # Static output tensors of the captured step, rewritten by every replay.  Detached views: holding the autograd
+        # graph would keep its AccumulateGrad nodes (and their stream affinity) alive across steps.
+        det = lambda d: {k: (v.detach() if torch.is_tensor(v) else v) for k, v in d.items()}  # noqa: E731
+        self._static_loss = loss.detach()
+        self._static_all = (self._static_loss, det(results), det(losses))
         # the Adam bias corrections are baked into the captured launch; keep them exact by passing the
         # step number through device memory instead (see adam_update)
         self.step_count = steps_before
@@ -149,6 +167,7 @@ class FlatAdamTrainer(object):
             for k, v in sample.items():
                 if torch.is_tensor(v):
                     self._static_sample[k].copy_(v, non_blocking=True)
+            self.set_sides(self._sides_of(sample), sample.get("root"))
         self.step_count += 1
         self._push_hyper()
         self._graph.replay()
@@ -209,6 +228,31 @@ class FlatAdamTrainer(object):
         self.step_count = steps.pop() if steps else 0
         self._scale_view.fill_(self.lr_scale)
 
+    @staticmethod
+    def _sides_of(sample):
+        for k, v in sample.items():
+            if getattr(k, "value", k) == "sides" and isinstance(v, (list, tuple)):
+                return list(v)
+        return None
+
+    def set_sides(self, sides, root=None):
+        """Left/right pattern of the next replayed batch (list of "left"/"right"); ``root`` must be the captured one."""
+        if root is not None and root != self._static_sample.get("root"):
+            raise RuntimeError("FlatAdamTrainer: the captured step was built for root={!r}, got {!r}".format(
+                self._static_sample.get("root"), root))
+        if sides is None or "sides_mask" not in self._static_sample:
+            return
+        mask = self._static_sample["sides_mask"]
+        if len(sides) != mask.numel():
+            raise RuntimeError("FlatAdamTrainer: captured batch size {}, got {} sides".format(mask.numel(), len(sides)))
+        mask.copy_(torch.tensor([s == "right" for s in sides], dtype=torch.bool))
+
+    def static_outputs(self):
+        """``(total_loss, results, losses)`` of the captured step: the same device tensors after every replay."""
+        if self._graph is None:
+            raise RuntimeError("FlatAdamTrainer.static_outputs: call capture(sample) first")
+        return self._static_all
+
     def grads_are_views(self):
         """Autograd must have accumulated in place into the flat buffer (sanity check for tests)."""
         base = self.flat_g.untyped_storage().data_ptr()
@@ -235,7 +279,7 @@ class PinnedFeeder(object):
             raise RuntimeError("PinnedFeeder: call trainer.capture(sample) first")
         self.trainer = trainer
         self.static = trainer._static_sample
-        self.keys = [k for k, v in self.static.items() if torch.is_tensor(v)]
+        self.keys = [k for k, v in self.static.items() if torch.is_tensor(v) and k != "sides_mask"]
         self.staging = {k: torch.empty_like(self.static[k]) for k in self.keys}
         self.copy_stream = torch.cuda.Stream()
         self.ready = torch.cuda.Event()
@@ -261,6 +305,7 @@ class PinnedFeeder(object):
             for k in self.keys:
                 self.staging[k].copy_(host_sample[k], non_blocking=True)
             self.ready.record(self.copy_stream)
+        self._staged_sides = FlatAdamTrainer._sides_of(host_sample)
         self._staged = True
 
     def step(self, next_host_sample=None):
@@ -272,6 +317,7 @@ class PinnedFeeder(object):
         for k in self.keys:
             self.static[k].copy_(self.staging[k], non_blocking=True)
         self.free.record(cur)
+        self.trainer.set_sides(self._staged_sides)
         self._staged, self._consumed_once = False, True
         if next_host_sample is not None:
             self.prefetch(next_host_sample)

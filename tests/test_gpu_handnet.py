@@ -1,5 +1,7 @@
 """End-to-end parity of the drop-in HandNet (all stages in libobman_b200.so) against the fp64 CPU oracle:
 total loss, every logged loss, vertex coordinates and all parameter gradients."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -153,6 +155,21 @@ def test_aux_stream_overlap_graph_replay_and_pinned_feeder_match_serial_eager_st
         torch.cuda.synchronize()
         assert abs(loss_g - loss_s) <= 1e-6 * abs(loss_s)
         assert close(trainer.flat_g, g_s, 1e-5) and close(trainer.flat_p - p0, p_s - p0, 2e-2)
+        # a different left/right pattern goes through the SAME graph (device side mask, no re-capture)
+        flipped = dict(sample)
+        flipped[[k for k in sample if getattr(k, "value", k) == "sides"][0]] = ["left", "left", "right", "left"]
+        streams.set_enabled(False)
+        restore()
+        loss_fe = trainer.step({k: v for k, v in flipped.items() if k != "sides_mask"}).item()
+        g_fe = trainer.flat_g.clone()
+        streams.set_enabled(True)
+        restore()
+        loss_fg = trainer.replay(flipped).item()
+        torch.cuda.synchronize()
+        assert abs(loss_fe - loss_s) > 1e-6 * abs(loss_s)          # the pattern matters ...
+        assert abs(loss_fg - loss_fe) <= 1e-6 * abs(loss_fe)        # ... and the replay follows it
+        assert close(trainer.flat_g, g_fe, 1e-5)
+        trainer.replay(sample)                                      # back to the original pattern
         # pinned host feed: a different batch first (so the static buffers really get overwritten), then this one
         feeder = PinnedFeeder(trainer)
         other = enum_sample(make_sample(4, 64, 78), device="cpu")
@@ -170,3 +187,27 @@ def test_aux_stream_overlap_graph_replay_and_pinned_feeder_match_serial_eager_st
             feeder.prefetch(enum_sample(host, device="cpu"))
     finally:
         streams.set_enabled(prev)
+
+
+def test_training_driver_runs_resumes_and_writes_reference_format_checkpoints(tmp_path):
+    """netscripts.train.run: two short epochs on one GPU (CUDA-graph step, device-side loss log), checkpoint written
+    with DataParallel-style keys, resume continues from the stored epoch with the stored Adam state."""
+    from obman_train_b200.netscripts import train
+    small = dict(atlas_ico_divisions=2, atlas_separate_encoder=False)
+    args = train.build_parser().parse_args(["--exp_id", str(tmp_path / "run"), "--epochs", "2", "--batch_size", "4",
+                                            "--steps_per_epoch", "3", "--img_size", "64", "--log_every", "0"])
+    lines = []
+    hist = train.run(args, model_kwargs=small, out=lines.append)
+    assert [h["epoch"] for h in hist] == [1, 2] and all(np.isfinite(h["train_total"]) for h in hist)
+    ckpt = torch.load(str(tmp_path / "run" / "checkpoint.pth.tar"), weights_only=False)
+    assert ckpt["epoch"] == 2 and all(k.startswith("module.") for k in ckpt["state_dict"])
+    steps = {int(float(v["step"])) for v in ckpt["optimizer"]["state"].values()}
+    assert steps == {6}   # 2 epochs x 3 steps, one fused Adam step each
+    args2 = train.build_parser().parse_args(["--exp_id", str(tmp_path / "run"), "--epochs", "3", "--batch_size", "4",
+                                             "--steps_per_epoch", "3", "--img_size", "64", "--log_every", "0",
+                                             "--resume", str(tmp_path / "run" / "checkpoint.pth.tar")])
+    hist2 = train.run(args2, model_kwargs=small, out=lines.append)
+    assert [h["epoch"] for h in hist2] == [3]
+    ckpt2 = torch.load(str(tmp_path / "run" / "checkpoint.pth.tar"), weights_only=False)
+    assert {int(float(v["step"])) for v in ckpt2["optimizer"]["state"].values()} == {9}
+    assert os.path.isfile(str(tmp_path / "run" / "model_best.pth.tar"))

@@ -41,7 +41,9 @@ CFG = dict(resnet_version=18, mano_root="synthetic", mano_comps=30, mano_use_sha
 
 
 def make_sample(B, H, seed, device="cpu"):
-    from obman_train_b200.queries import TransQueries, BaseQueries
+    # the reference model is the consumer here: key the dict with ITS enums (served by the import hook), whatever
+    # obman_train_b200.queries resolved to at import time
+    from handobjectdatasets.queries import TransQueries, BaseQueries
     g = torch.Generator().manual_seed(seed)
     verts, _ = load_contacts()
     hand = torch.tensor(verts * 1000, dtype=torch.float32).unsqueeze(0).repeat(B, 1, 1)

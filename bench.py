@@ -416,6 +416,10 @@ def main():
         run_reference(args)
     else:
         run_b200(args)
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -1071,6 +1071,15 @@ static int pick_bn(int N, long long m_tiles) {
   // Column tile: minimise padded columns / relative tile efficiency (measured: 256-wide tiles are the most
   // efficient per column, 64-wide the least), but only take 256 when the grid still covers most of the SMs.
   if (N <= 64) return 64;
+  {
+    // experiment knob: column tile for grids that would not fill the GPU with 128-wide tiles
+    static int small_grid_bn = -1;
+    if (small_grid_bn < 0) {
+      const char* e = getenv("OBMAN_GEMM_SMALLGRID_BN");
+      small_grid_bn = e ? atoi(e) : 0;
+    }
+    if (small_grid_bn == 64 && m_tiles * ((N + 127) / 128) < num_sms()) return 64;
+  }
   const double eff[3] = {0.6, 0.85, 1.0};
   const int bn[3] = {64, 128, 256};
   int best = 128;

@@ -111,9 +111,21 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// Epilogue operand prefetch for one row (16 bytes per lane): residual addend and ReLU-mask source of columns
+// col .. col+3 of the row at element offset row_off; neutral values when the row / column / alignment rules it out.
+__device__ __forceinline__ void epilogue_prefetch(const GemmEpilogue& epi, const GemmProgram& prog, long long row_off,
+                                                  int col, bool ptr_ok, float4& add, float4& msk) {
+  add = make_float4(0.f, 0.f, 0.f, 0.f);
+  msk = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (ptr_ok && row_off >= 0 && (row_off & 3) == 0 && col + 3 < prog.N) {
+    if (epi.addend) add = __ldg(reinterpret_cast<const float4*>(epi.addend + row_off + col));
+    if (epi.mask_src) msk = __ldg(reinterpret_cast<const float4*>(epi.mask_src + row_off + col));
+  }
+}
+
 // Epilogue shared by the GEMM kernels: wait for the accumulator, then TMEM -> registers -> global.
 // Called by the four epilogue warps (q = TMEM lane quadrant, r = q * 32 + lane = tile row); `smem` is the tile
-// buffer base (its first 17 KB are reused for staging, every operand read has retired by then).
+// buffer base (its first 16 KB are reused for staging, every operand read has retired by then).
 template <int BN, int MODE>
 __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, uint32_t tmem_base, uint64_t* accum,
                                               const GemmProgram& prog, const GemmEpilogue& epi, int m0, int n0,
@@ -121,6 +133,36 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, uint32_t tmem_base,
     // ---- epilogue ----
     // TMEM -> registers (lane = tile row) -> XOR-swizzled shared-memory transpose -> each store / addend / mask
     // instruction touches 4 rows x 128 contiguous bytes (the row-per-lane layout would touch 32 rows x 16 bytes).
+    // The global reads (residual addend, ReLU-mask source) of the first 32-column chunk are issued BEFORE the wait for
+    // the accumulator, so their latency hides behind the last MMAs.  (Fetching chunk c+1 row group by row group while
+    // chunk c is consumed was measured slower: the late rows' loads are exposed again and interleave with the stores.)
+    const int cc = lane & 7;     // 16-byte column chunk handled by this lane after the transpose
+    const int rsub = lane >> 3;  // row within each group of 4
+    long long ro[8];             // element offsets of the 8 rows this lane stores (row 4 i + rsub of the warp's 32), -1 = none
+    float4 add4[8], msk4[8];
+    bool ptr_ok = false;
+    if (MODE != 2) {
+      bool row_ok;
+      long long row_off;
+      if (MODE == 0 && prog.spatial) {
+        const int tw = r % prog.TW;
+        const int th = (r / prog.TW) % prog.TH;
+        const int tn = r / (prog.TW * prog.TH);
+        const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
+        row_ok = n < prog.n_img && h < prog.h_out && w < prog.w_out;
+        row_off = n * epi.sN + h * epi.sH + w * epi.sW;
+      } else {
+        row_ok = (m0 + r) < prog.M;
+        row_off = (long long)(m0 + r) * epi.ld;
+      }
+      const long long mine = row_ok ? row_off : -1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ro[i] = __shfl_sync(0xffffffffu, mine, 4 * i + rsub);
+      ptr_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
+                 reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0 && !epi.accumulate;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) epilogue_prefetch(epi, prog, ro[i], n0 + 4 * cc, ptr_ok, add4[i], msk4[i]);
+    }
     mbar_wait(accum, 0);
     tc_fence_after();
     if (r == 0) trace_stamp(epi, 6);
@@ -148,47 +190,17 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, uint32_t tmem_base,
     } else {
     // all MMAs (and therefore all TMA loads and operand reads) have retired: stage 0 is free for staging
     uint8_t* wbase = smem + q * 4096;                                   // 32 rows x 128 B per warp
-    long long* rowinfo = reinterpret_cast<long long*>(smem + 16384);    // element offset of every tile row, -1 = none
-    {
-      bool row_ok;
-      long long row_off;
-      if (MODE == 0 && prog.spatial) {
-        const int tw = r % prog.TW;
-        const int th = (r / prog.TW) % prog.TH;
-        const int tn = r / (prog.TW * prog.TH);
-        const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
-        row_ok = n < prog.n_img && h < prog.h_out && w < prog.w_out;
-        row_off = n * epi.sN + h * epi.sH + w * epi.sW;
-      } else {
-        row_ok = (m0 + r) < prog.M;
-        row_off = (long long)(m0 + r) * epi.ld;
-      }
-      rowinfo[r] = row_ok ? row_off : -1;
-    }
-    __syncwarp();  // each warp only ever reads the rowinfo entries of its own 32 rows
-    const bool ptr_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
-                          reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0 && !epi.accumulate;
-    const int cc = lane & 7;     // 16-byte column chunk handled by this lane after the transpose
-    const int rsub = lane >> 3;  // row within each group of 4
-    long long ro[8];             // element offsets of the 8 rows this lane stores (row 4 i + rsub of the warp's 32)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) ro[i] = rowinfo[q * 32 + 4 * i + rsub];
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= prog.N) break;  // warp-uniform
       const int col = n0 + c0 + 4 * cc;
       const bool colvec = (col + 3 < prog.N) && ptr_ok;
       // issue every global read of this chunk (residual, ReLU-mask source, bias) before touching the accumulator:
-      // they are independent, so their latencies overlap instead of forming 8 serial round trips
-      float4 add4[8], msk4[8];
+      // they are independent, so their latencies overlap instead of forming 8 serial round trips (chunk 0 was
+      // fetched before the accumulator wait)
+      if (c0 > 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        add4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        msk4[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (colvec && ro[i] >= 0 && (ro[i] & 3) == 0) {
-          if (epi.addend) add4[i] = __ldg(reinterpret_cast<const float4*>(epi.addend + ro[i] + col));
-          if (epi.mask_src) msk4[i] = __ldg(reinterpret_cast<const float4*>(epi.mask_src + ro[i] + col));
-        }
+        for (int i = 0; i < 8; ++i) epilogue_prefetch(epi, prog, ro[i], col, ptr_ok, add4[i], msk4[i]);
       }
       float bias4[4] = {0.f, 0.f, 0.f, 0.f};
       if (epi.bias) {
@@ -213,29 +225,30 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, uint32_t tmem_base,
       for (int i = 0; i < 8; ++i) {
         const int rr = 4 * i + rsub;
         const long long row_off = ro[i];
-        if (row_off < 0 || col >= prog.N) continue;
-        const float4 a = *reinterpret_cast<const float4*>(wbase + rr * 128 + ((cc ^ (rr & 7)) << 4));
-        float x[4] = {epi.alpha * a.x + bias4[0], epi.alpha * a.y + bias4[1], epi.alpha * a.z + bias4[2],
-                      epi.alpha * a.w + bias4[3]};
-        if (colvec && ((row_off & 3) == 0)) {
-          x[0] += add4[i].x; x[1] += add4[i].y; x[2] += add4[i].z; x[3] += add4[i].w;
-          if (epi.relu) {
+        if (row_off >= 0 && col < prog.N) {
+          const float4 a = *reinterpret_cast<const float4*>(wbase + rr * 128 + ((cc ^ (rr & 7)) << 4));
+          float x[4] = {epi.alpha * a.x + bias4[0], epi.alpha * a.y + bias4[1], epi.alpha * a.z + bias4[2],
+                        epi.alpha * a.w + bias4[3]};
+          if (colvec && ((row_off & 3) == 0)) {
+            x[0] += add4[i].x; x[1] += add4[i].y; x[2] += add4[i].z; x[3] += add4[i].w;
+            if (epi.relu) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
-          }
-          x[0] = msk4[i].x > 0.f ? x[0] : 0.f; x[1] = msk4[i].y > 0.f ? x[1] : 0.f;
-          x[2] = msk4[i].z > 0.f ? x[2] : 0.f; x[3] = msk4[i].w > 0.f ? x[3] : 0.f;
-          *reinterpret_cast<float4*>(epi.out + row_off + col) = make_float4(x[0], x[1], x[2], x[3]);
-        } else {
+              for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+            }
+            x[0] = msk4[i].x > 0.f ? x[0] : 0.f; x[1] = msk4[i].y > 0.f ? x[1] : 0.f;
+            x[2] = msk4[i].z > 0.f ? x[2] : 0.f; x[3] = msk4[i].w > 0.f ? x[3] : 0.f;
+            *reinterpret_cast<float4*>(epi.out + row_off + col) = make_float4(x[0], x[1], x[2], x[3]);
+          } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (col + e >= prog.N) break;
-            float y = x[e];
-            if (epi.addend) y += epi.addend[row_off + col + e];
-            if (epi.relu) y = fmaxf(y, 0.f);
-            if (epi.mask_src) y = epi.mask_src[row_off + col + e] > 0.f ? y : 0.f;
-            if (epi.accumulate) atomicAdd(epi.out + row_off + col + e, y);
-            else epi.out[row_off + col + e] = y;
+            for (int e = 0; e < 4; ++e) {
+              if (col + e >= prog.N) break;
+              float y = x[e];
+              if (epi.addend) y += epi.addend[row_off + col + e];
+              if (epi.relu) y = fmaxf(y, 0.f);
+              if (epi.mask_src) y = epi.mask_src[row_off + col + e] > 0.f ? y : 0.f;
+              if (epi.accumulate) atomicAdd(epi.out + row_off + col + e, y);
+              else epi.out[row_off + col + e] = y;
+            }
           }
         }
       }

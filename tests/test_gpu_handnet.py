@@ -211,3 +211,36 @@ def test_training_driver_runs_resumes_and_writes_reference_format_checkpoints(tm
     ckpt2 = torch.load(str(tmp_path / "run" / "checkpoint.pth.tar"), weights_only=False)
     assert {int(float(v["step"])) for v in ckpt2["optimizer"]["state"].values()} == {9}
     assert os.path.isfile(str(tmp_path / "run" / "model_best.pth.tar"))
+
+
+def test_full_size_step_is_batch_slicing_invariant():
+    """BASELINE configs[1] at full size (B=64, 256x256, ico-3, 600 GT points): the fp64 oracle cannot run this in
+    seconds, so parity is carried by a size-independent property - every operator on the path is per-sample (SURVEY.md
+    §8e), hence the per-sample outputs of the full batch must equal those of the same samples run as small batches
+    (different tile shapes, grid sizes and split-K factors underneath), and the batch losses must be the means of the
+    slice losses."""
+    from obman_train_b200.networks.handnet import HandNet
+    cfg = dict(FULL_CFG)
+    cfg.update(atlas_separate_encoder=False, atlas_ico_divisions=3, contact_lambda=0, collision_lambda=0,
+               atlas_lambda_regul_edges=0)
+    torch.manual_seed(3)
+    model = HandNet(**cfg).eval().cuda()
+    randomise_bn(model, 4)
+    model.cuda()
+    B = 64
+    host = make_sample(B, 256, 9)
+    with torch.no_grad():
+        total, results, losses = model.forward(enum_sample(host))
+        pieces = []
+        for lo, hi in ((0, 2), (2, 10), (10, 64)):
+            sl = {k: (v[lo:hi] if torch.is_tensor(v) or isinstance(v, list) else v) for k, v in host.items()}
+            pieces.append((hi - lo, model.forward(enum_sample(sl))))
+    for key in ("verts", "joints", "objpoints3d", "objtrans", "objscale"):
+        full = results[key]
+        part = torch.cat([p[1][1][key] for p in pieces])
+        scale = full.abs().max().item()
+        assert (full - part).abs().max().item() <= 2e-5 * scale, (key, (full - part).abs().max().item(), scale)
+    for key in ("mano_verts3d", "mano_joints3d", "final_chamfer_loss", "atlas_objpoints3d", "atlas_trans3d"):
+        mean = sum(n * float(p[2][key]) for n, p in pieces) / B
+        assert abs(float(losses[key]) - mean) <= 2e-5 * abs(mean), (key, float(losses[key]), mean)
+    assert torch.isfinite(total).all()

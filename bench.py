@@ -353,11 +353,11 @@ def run_b200(args):
     tc_peak = bf16 if args.precision == "bf16x3" else bf16 / 2.0
     passes = 1 if args.precision == "tf32" else 3
     # DRAM traffic of the dominant kernel family per launch, from the committed ncu capture of this command
-    # (profiles/gemm_traffic_r1d.json <- profiles/launches_r1d_bench_step.csv); only valid for the default workload
+    # (profiles/gemm_traffic_r1j.json <- profiles/launches_r1j_bench_step.csv); only valid for the default workload
     traffic, traffic_src = None, None
     if args.config == 2 and args.precision == "bf16x3":
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic_r1d.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic_r1j.json")))
             traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
         except Exception:  # noqa: BLE001
             pass

@@ -1051,12 +1051,23 @@ static int dispatch_gemm(int BN, int passes, int ts, const GemmMaps& maps, const
     occ2 = (e && e[0] == '1') ? 0 : 1;
   }
   const int cl = cluster_for(grid.x);
+  static int deep_small = -1;
+  if (deep_small < 0) {
+    // off by default: measured (round 1j) -2 % on the isolated 8x8x512 kernels but +1 % on the step, because a
+    // 198 KB CTA keeps the other streams' kernels off its SM
+    const char* e = getenv("OBMAN_GEMM_DEEP_SMALL");
+    deep_small = (e && e[0] == '1') ? 1 : 0;
+  }
 #define OBMAN_GEMM_CASE(bn)                                                                         \
   if (BN == bn) {                                                                                   \
     if (MODE == 0 && ts == 2) {                                                                     \
       constexpr int occ = (bn <= 128 ? 2 : 1);                                                      \
       if (cl == 4) return launch_gemm<bn, 3, 0, 2, occ, 4>(maps, prog, epi, grid, st);              \
       if (cl == 2) return launch_gemm<bn, 3, 0, 2, occ, 2>(maps, prog, epi, grid, st);              \
+      /* a grid that cannot put two CTAs on an SM anyway gets the one-CTA configuration: twice the */ \
+      /* pipeline stages (6 instead of 3-4) for the same tile                                      */ \
+      if (deep_small && (long long)grid.x * grid.y <= num_sms())                                    \
+        return launch_gemm<bn, 3, 0, 2, 1>(maps, prog, epi, grid, st);                              \
       return launch_gemm<bn, 3, 0, 2, occ>(maps, prog, epi, grid, st);                              \
     }                                                                                               \
     if (MODE == 0 && ts && passes == 3) {                                                           \

@@ -339,6 +339,14 @@ def run_b200(args):
             for tag, fl, t in dense.last_profile[-per:]:
                 f.write("%-60s %9.3f %8.4f %8.1f\n" % (tag, fl / 1e9, t, fl / t / 1e9 if t > 0 else 0))
 
+    in_sync = None
+    if world > 1:
+        # replicas must still hold identical parameters after the run (weights are never re-broadcast)
+        chk = torch.stack([trainer.flat_p.double().sum(), trainer.flat_p.double().pow(2).sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.equal(lo, hi))
     if rank != 0:
         return
     peaks = {}
@@ -371,7 +379,7 @@ def run_b200(args):
         "config": workload_config(world), "clocks": clocks,
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(kernels),
+        "gpu_launches": int(kernels), "replicas_in_sync": in_sync,
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (all conv/GEMM launches of a step)",
                      "achieved": prof["tflops"], "peak": tc_peak, "unit": "TFLOP/s",
                      "frac": prof["tflops"] / tc_peak,
@@ -416,10 +424,8 @@ def main():
         run_reference(args)
     else:
         run_b200(args)
-        import torch.distributed as dist
-        if dist.is_initialized():
-            dist.barrier()
-            dist.destroy_process_group()
+        # No dist.barrier() / destroy_process_group() here: with the captured step graphs (which hold NCCL kernels)
+        # still alive the teardown was observed to hang at N=2 (round 1k); the processes simply exit.
 
 
 if __name__ == "__main__":

@@ -17,6 +17,20 @@ from ._lib import call, ptr, stream_ptr
 BN_EPS = 1e-5
 DEBUG = None  # set to a dict to capture intermediate gradients (diagnostics only)
 
+# Gradient sink (set by FlatAdamTrainer for the duration of a step): an object with
+#   view(param_data_ptr) -> tensor view of the flat gradient buffer shaped like that parameter, or None
+#   stage_done(first_ptr, last_ptr)  called once per encoder when the gradients of layer3 + layer4 (94 % of the
+#                                    encoder's parameters) are complete on the WGRAD stream
+# With a sink the weight-gradient kernels write straight into the flat buffer (no per-parameter gradient tensors,
+# no gather copy) and the trainer can start the all-reduce of that range under the rest of the backward pass.
+_grad_sink = None
+
+
+def set_grad_sink(sink):
+    global _grad_sink
+    prev, _grad_sink = _grad_sink, sink
+    return prev
+
 # (name, out_ch, in_ch, ksize, stride) of the 20 conv+BN units in state-dict order
 def resnet18_units():
     units = [("conv1", "bn1", 64, 3, 7, 2)]
@@ -57,6 +71,7 @@ class _Unit(object):
 
     def __init__(self, w, gamma, beta, mean, var, ksize, stride, stem=False, need_dgrad=True, packed=False):
         self.w, self.gamma, self.mean = w, gamma, mean
+        self.beta_ptr = beta.data_ptr()
         self.O, self.I = w.shape[0], w.shape[1]
         self.k, self.stride, self.stem = ksize, stride, stem
         self.Ip = 64 if stem else self.I
@@ -132,12 +147,21 @@ class _Unit(object):
         return dwraw
 
     def finish(self, dwraw, gbeta_sum):
-        gw = torch.empty_like(self.w)
-        ggamma = torch.empty_like(self.gamma)
-        gbeta = torch.empty_like(self.gamma)
+        """-> (gw, ggamma, gbeta); entries are None where the gradient went straight into the sink's flat buffer."""
+        sink = _grad_sink
+        views = [None, None, None]
+        if sink is not None:
+            views = [sink.view(self.w.data_ptr()), sink.view(self.gamma.data_ptr()), sink.view(self.beta_ptr)]
+        direct = all(v is not None for v in views)
+        gw = views[0] if direct else torch.empty_like(self.w)
+        ggamma = views[1] if direct else torch.empty_like(self.gamma)
+        gbeta = views[2] if direct else torch.empty_like(self.gamma)
         call("obman_bn_wgrad_finish", ptr(dwraw), dwraw.stride(0), ptr(self.w), None, ptr(self.scale),
              ptr(self.rstd), ptr(self.mean), ptr(gbeta_sum), self.O, self.I, self.k, self.k, self.Ip,
              int(self.stem), ptr(gw), ptr(ggamma), ptr(gbeta), None, stream_ptr())
+        if direct:
+            sink.wrote(self.w.data_ptr(), self.gamma.data_ptr(), self.beta_ptr)
+            return None, None, None
         return gw, ggamma, gbeta
 
 
@@ -266,6 +290,11 @@ class _EncoderFn(torch.autograd.Function):
                 streams.join(streams.CHAIN)
             keep.append(gres)
             g2 = u1.dgrad(g1, h, w_, addend=gres, mask_src=x, passes=pb)
+            if bidx == 4 and _grad_sink is not None:
+                # layer4 and layer3 are done on the WGRAD stream: their flat-buffer range can go on the wire now
+                first = blocks[4][0]                      # layer3.0.conv1
+                last = blocks[7][1]                       # layer4.1.conv2 (bn2 is its last parameter)
+                _grad_sink.stage_done(first.w.data_ptr(), last.beta_ptr, streams.aux_stream() if streams.enabled() else None)
         # g2 is now the gradient w.r.t. the max-pool output (already masked by p > 0)
         gc1 = _empty(B, H // 2, W // 2, 64)
         call("obman_maxpool_bwd", ptr(g2), ptr(pidx), B, H // 2, W // 2, 64, ptr(gc1), st)

@@ -140,5 +140,4 @@ def build_parser():
 
 if __name__ == "__main__":
     run(build_parser().parse_args())
-    if dist.is_initialized():
-        dist.destroy_process_group()
+    # no destroy_process_group(): tearing NCCL down while captured graphs that contain its kernels are alive can hang

@@ -15,10 +15,68 @@ import torch.distributed as dist
 from ._lib import call, ptr, stream_ptr
 
 
+def complement_ranges(done, total):
+    """[lo, hi) ranges of [0, total) not covered by the (possibly unordered, non-overlapping) ranges in ``done``."""
+    out, pos = [], 0
+    for lo, hi in sorted(done):
+        if lo > pos:
+            out.append((pos, lo))
+        pos = max(pos, hi)
+    if pos < total:
+        out.append((pos, total))
+    return out
+
+
+class _GradSink(object):
+    """Hands the encoder views of the flat gradient buffer (encoder.set_grad_sink) and starts the all-reduce of a
+    finished range while the rest of the backward pass is still running."""
+
+    def __init__(self, trainer):
+        self.t = trainer
+        self.by_ptr = {}
+        for p, off, view in zip(trainer.params, trainer.offsets, trainer.grad_views):
+            self.by_ptr[p.data_ptr()] = (off, p.numel(), view)
+        self.written = set()
+        self.reduced = []
+        self.comm_stream = None
+
+    def begin(self):
+        self.written.clear()
+        self.reduced = []
+
+    def view(self, data_ptr):
+        e = self.by_ptr.get(data_ptr)
+        return None if e is None else e[2]
+
+    def wrote(self, *ptrs):
+        self.written.update(ptrs)
+
+    def stage_done(self, first_ptr, last_ptr, producer_stream):
+        t = self.t
+        if t.world_size <= 1 or not t.overlap_allreduce:
+            return
+        a, b = self.by_ptr.get(first_ptr), self.by_ptr.get(last_ptr)
+        if a is None or b is None:
+            return
+        lo, hi = a[0], b[0] + b[1]
+        # every parameter slot inside the range must have been written by the encoder
+        for ptr_, (off, n, _) in self.by_ptr.items():
+            if lo <= off < hi and ptr_ not in self.written:
+                return
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream()
+        src = producer_stream if producer_stream is not None else torch.cuda.current_stream()
+        self.comm_stream.wait_stream(src)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(t.flat_g[lo:hi], op=dist.ReduceOp.SUM)
+        self.reduced.append((lo, hi))
+
+
 class FlatAdamTrainer(object):
     """``step(sample)`` = zero grads -> HandNet.forward -> backward -> [all-reduce] -> fused Adam."""
 
-    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, world_size=1):
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, world_size=1,
+                 direct_grads=True, overlap_allreduce=True):
         self.model = model
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.world_size = world_size
@@ -48,6 +106,12 @@ class FlatAdamTrainer(object):
         self.params = [p for _, p in params]
         self.numel = total
         self.param_numel = sum(p.numel() for _, p in params)
+        # direct_grads: the encoder's weight-gradient kernels write into the flat buffer (no gather copy);
+        # overlap_allreduce: the layer3 + layer4 range (94 % of an encoder) is all-reduced under the rest of backward
+        self.direct_grads = direct_grads and dev.type == "cuda"
+        self.overlap_allreduce = overlap_allreduce
+        self.offsets = offsets
+        self._sink = _GradSink(self) if self.direct_grads else None
         self.step_count = 0
         # {step number, lr multiplier} in device memory: a captured graph reads both at replay time
         self._hyper_dev = torch.tensor([0.0, 1.0], device=dev, dtype=torch.float32)
@@ -59,7 +123,6 @@ class FlatAdamTrainer(object):
         order = {id(p): i for i, p in enumerate(q for q in model.parameters() if q.requires_grad)}
         self.optim_index = [order[id(p)] for p in self.params]
         self.optim_len = len(order)
-        self.offsets = offsets
 
     def zero_grad(self):
         self.flat_g.zero_()
@@ -71,15 +134,27 @@ class FlatAdamTrainer(object):
         # an add kernel per parameter) and gathered into the flat buffer with one fused multi-tensor copy.
         for p in self.params:
             p.grad = None
-        loss, results, losses = self.model.forward(sample)
-        loss.backward()
+        if self._sink is not None:
+            from . import encoder
+            self._sink.begin()
+            prev = encoder.set_grad_sink(self._sink)
+            try:
+                loss, results, losses = self.model.forward(sample)
+                loss.backward()
+            finally:
+                encoder.set_grad_sink(prev)
+        else:
+            loss, results, losses = self.model.forward(sample)
+            loss.backward()
         self.gather_grads()
         self.reduce_and_update()
         return (loss, results, losses) if return_all else loss
 
     def gather_grads(self):
+        written = self._sink.written if self._sink is not None else ()
         have = [(v, p.grad) for v, p in zip(self.grad_views, self.params) if p.grad is not None]
-        missing = [v for v, p in zip(self.grad_views, self.params) if p.grad is None]
+        missing = [v for v, p in zip(self.grad_views, self.params)
+                   if p.grad is None and p.data_ptr() not in written]
         if missing:
             torch._foreach_zero_(missing)
         torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
@@ -89,7 +164,12 @@ class FlatAdamTrainer(object):
     def all_reduce_grads(self):
         """The only data-path collective of the step: one sum all-reduce of the flat gradient buffer."""
         if self.world_size > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+            done = self._sink.reduced if self._sink is not None else []
+            for lo, hi in complement_ranges(done, self.numel):
+                dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM)
+            if done:  # ranges that went out early on the communication stream
+                torch.cuda.current_stream().wait_stream(self._sink.comm_stream)
+                self._sink.reduced = []
 
     def reduce_and_update(self):
         self.all_reduce_grads()

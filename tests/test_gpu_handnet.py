@@ -244,3 +244,32 @@ def test_full_size_step_is_batch_slicing_invariant():
         mean = sum(n * float(p[2][key]) for n, p in pieces) / B
         assert abs(float(losses[key]) - mean) <= 2e-5 * abs(mean), (key, float(losses[key]), mean)
     assert torch.isfinite(total).all()
+
+
+def test_direct_flat_buffer_gradients_match_gathered_gradients():
+    """FlatAdamTrainer(direct_grads=True): the encoder's weight-gradient kernels write straight into the flat gradient
+    buffer (encoder.set_grad_sink); the result must equal the autograd-returned gradients gathered by a copy."""
+    from obman_train_b200.networks.handnet import HandNet
+    from obman_train_b200.trainer import FlatAdamTrainer
+    sample = enum_sample(make_sample(4, 64, 31))
+    grads = {}
+    for direct in (False, True):
+        torch.manual_seed(6)
+        model = HandNet(**FULL_CFG).eval().cuda()
+        trainer = FlatAdamTrainer(model, lr=1e-4, direct_grads=direct)
+        trainer.flat_g.fill_(float("nan"))      # every slot that matters must be rewritten by the step
+        loss = trainer.step(sample)
+        torch.cuda.synchronize()
+        assert trainer.grads_are_views()
+        if direct:
+            n_enc = sum(1 for n in trainer.names if "base_net" in n)
+            assert len(trainer._sink.written) == n_enc > 100   # both encoders, conv + bn weight + bn bias
+        g = trainer.flat_g.clone()
+        # padding between parameter slots is never read back into a parameter: mask it out
+        used = torch.zeros_like(g, dtype=torch.bool)
+        for p_, off in zip(trainer.params, trainer.offsets):
+            used[off:off + p_.numel()] = True
+        assert torch.isfinite(g[used]).all()
+        grads[direct] = torch.where(used, g, torch.zeros_like(g))
+    d = (grads[True] - grads[False]).norm() / grads[False].norm()
+    assert d < 1e-5, d

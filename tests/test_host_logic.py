@@ -1,0 +1,132 @@
+"""CPU checks of the host-side contracts the CUDA convolution path is driven by (no GPU, no library calls):
+the tap tables of ``dense.fprop_taps`` / ``dense.dgrad_taps`` and the weight / stem layouts documented in
+include/obman_b200.h, executed by a small torch emulator of ``obman_conv_nhwc``'s semantics (shifted-box taps over
+NHWC phase views, zero fill outside) and compared with ``torch.nn.functional.conv2d`` and its autograd."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from obman_train_b200 import dense
+from obman_train_b200.encoder import resnet18_units, stem_view
+
+
+def emu_conv_nhwc(x, w, c_out, taps, in_step, h_out, w_out):
+    """out[n,h,w,:] = sum_t xview_t[n, h+dh[t], w+dw[t], :] @ w[:, slot[t]*C:(slot[t]+1)*C]^T (header contract)."""
+    dh, dw, phase, slot = taps
+    n, _, _, c = x.shape
+    out = torch.zeros(n, h_out, w_out, c_out, dtype=x.dtype)
+    for t in range(len(dh)):
+        ph = phase[t] if (phase is not None and in_step == 2) else 0
+        view = x[:, (ph >> 1)::in_step, (ph & 1)::in_step]
+        hv, wv = view.shape[1], view.shape[2]
+        shifted = torch.zeros(n, h_out, w_out, c, dtype=x.dtype)
+        h_lo, h_hi = max(0, -dh[t]), min(h_out, hv - dh[t])
+        w_lo, w_hi = max(0, -dw[t]), min(w_out, wv - dw[t])
+        if h_lo < h_hi and w_lo < w_hi:
+            shifted[:, h_lo:h_hi, w_lo:w_hi] = view[:, h_lo + dh[t]:h_hi + dh[t], w_lo + dw[t]:w_hi + dw[t]]
+        out += shifted @ w[:, slot[t] * c:(slot[t] + 1) * c].t()
+    return out
+
+
+def fold_layouts(w):
+    """(O,I,KH,KW) -> fprop operand (O, KH*KW*I) and dgrad operand (I, KH*KW*O) of obman_fold_conv (scale 1)."""
+    O, I, KH, KW = w.shape
+    wf = w.permute(0, 2, 3, 1).reshape(O, KH * KW * I)
+    wft = w.permute(1, 2, 3, 0).reshape(I, KH * KW * O)
+    return wf, wft
+
+
+@pytest.mark.parametrize("k,stride", [(3, 1), (3, 2), (1, 2), (1, 1)])
+def test_fprop_and_dgrad_tap_tables_reproduce_conv2d_and_its_gradient(k, stride):
+    g = torch.Generator().manual_seed(k * 10 + stride)
+    N, H, C, O = 2, 8, 5, 7
+    x = torch.randn(N, H, H, C, generator=g, dtype=torch.float64)
+    w = torch.randn(O, C, k, k, generator=g, dtype=torch.float64)
+    wf, wft = fold_layouts(w)
+    ho = H // stride
+    dh, dw, phase, slot, step = dense.fprop_taps(k, stride, k // 2)
+    assert step == stride and len(dh) == k * k and slot == list(range(k * k))
+    y = emu_conv_nhwc(x, wf, O, (dh, dw, phase, slot), step, ho, ho)
+    xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    ref = F.conv2d(xr, w, stride=stride, padding=k // 2)
+    assert torch.allclose(y.permute(0, 3, 1, 2), ref, atol=1e-10)
+    # data gradient: one emulated launch per output phase, written interleaved (encoder._Unit.dgrad)
+    gy = torch.randn(N, ho, ho, O, generator=g, dtype=torch.float64)
+    ref.backward(gy.permute(0, 3, 1, 2))
+    gx = torch.zeros(N, H, H, C, dtype=torch.float64)
+    covered = 0
+    for ph in range(stride):
+        for pw in range(stride):
+            tdh, tdw, tslot = dense.dgrad_taps(k, stride, k // 2, (ph, pw))
+            covered += len(tdh)
+            if not tdh:
+                continue
+            gx[:, ph::stride, pw::stride] = emu_conv_nhwc(gy, wft, C, (tdh, tdw, None, tslot), 1, H // stride, H // stride)
+    assert covered == k * k          # every filter tap belongs to exactly one output phase
+    assert torch.allclose(gx.permute(0, 3, 1, 2), xr.grad, atol=1e-10)
+
+
+def emu_stem_pack(img):
+    """obman_stem_pack: (B,3,H,W) -> (B, H/2, W/2 + 4, 16), channel (ph*2+pw)*3 + c, two zero pixels either side."""
+    B, _, H, W = img.shape
+    out = torch.zeros(B, H // 2, W // 2 + 4, 16, dtype=img.dtype)
+    for ph in range(2):
+        for pw in range(2):
+            for c in range(3):
+                out[:, :, 2:-2, (ph * 2 + pw) * 3 + c] = img[:, c, ph::2, pw::2]
+    return out
+
+
+def stem_weight_layout(w):
+    """obman_fold_conv(stem=1): (O,3,7,7) -> (O, 4*64); slot = a + 2 for the vertical tap a in [-2, 1],
+    channel q*16 + (ph*2+pw)*3 + c  <->  kh = 2a + ph + 3, kw = 2(q-2) + pw + 3 (zero outside the 7x7 window)."""
+    O = w.shape[0]
+    out = torch.zeros(O, 256, dtype=w.dtype)
+    for slot in range(4):
+        for q in range(4):
+            for ph in range(2):
+                for pw in range(2):
+                    kh, kw = 2 * (slot - 2) + ph + 3, 2 * (q - 2) + pw + 3
+                    if 0 <= kh < 7 and 0 <= kw < 7:
+                        for c in range(3):
+                            out[:, slot * 64 + q * 16 + (ph * 2 + pw) * 3 + c] = w[:, c, kh, kw]
+    return out
+
+
+def test_stem_as_four_tap_convolution_over_the_overlapping_view():
+    g = torch.Generator().manual_seed(3)
+    B, H, O = 2, 16, 6
+    img = torch.randn(B, 3, H, H, generator=g, dtype=torch.float64)
+    w = torch.randn(O, 3, 7, 7, generator=g, dtype=torch.float64)
+    xs = emu_stem_pack(img)
+    n, ho, wo, c, sN, sH, sW = stem_view(xs)
+    assert (n, ho, wo, c, sN, sH, sW) == (B, H // 2, H // 2, 64, (H // 2) * (H // 2 + 4) * 16, (H // 2 + 4) * 16, 16)
+    # materialise what the overlapping TMA view reads: pixel j = 4 neighbouring 16-channel pixels j .. j+3 (padded)
+    view = torch.as_strided(xs, (n, ho, wo, c), (sN, sH, sW, 1))
+    assert torch.equal(view[:, :, 5, 16:32], xs[:, :, 6, :])
+    taps = ([-2, -1, 0, 1], [0, 0, 0, 0], [0] * 4, [0, 1, 2, 3])     # encoder._Unit(stem=True).taps
+    y = emu_conv_nhwc(view.contiguous(), stem_weight_layout(w), O, taps, 1, ho, wo)
+    ref = F.conv2d(img, w, stride=2, padding=3)
+    assert torch.allclose(y.permute(0, 3, 1, 2), ref, atol=1e-10)
+
+
+def test_resnet18_unit_table_matches_the_reference_state_dict_order():
+    """20 conv+BN units in the order their parameters appear in ResNet-18's state dict (resnet.py:99-152)."""
+    from obman_train_b200.networks.bases import resnet
+    units = resnet18_units()
+    assert len(units) == 20 and units[0] == ("conv1", "bn1", 64, 3, 7, 2)
+    model = resnet.resnet18(pretrained=False)
+    names = [n for n, _ in model.named_parameters() if not n.startswith("fc.")]
+    expected = []
+    for conv, bn, O, I, k, s in units:
+        expected += [conv + ".weight", bn + ".weight", bn + ".bias"]
+        wshape = tuple(dict(model.named_parameters())[conv + ".weight"].shape)
+        assert wshape == (O, I, k, k), (conv, wshape)
+    assert names == expected
+    # 2.369 GMAC forward per 256x256 image (fc excluded)
+    macs = 128 * 128 * 64 * 3 * 7 * 7          # stem: 256 -> 128
+    size = {"layer1": 64, "layer2": 32, "layer3": 16, "layer4": 8}   # output size of every unit of a stage
+    for conv, _, O, I, k, s in units[1:]:
+        h_out = size[conv.split(".")[0]]
+        macs += h_out * h_out * O * I * k * k
+    assert abs(macs / 1e9 - 2.369) < 0.005, macs / 1e9

@@ -150,3 +150,49 @@ def test_reference_handnet_state_dict_loads_into_product(tmp_path, mano_tables_n
     for k, v in ref.state_dict().items():
         assert torch.equal(own[k], v), k
     assert trainer.optim_len == len(opt.state_dict()["param_groups"][0]["params"])
+
+
+def test_reload_model_rebuilds_from_opts_and_checkpoint(tmp_path):
+    """netscripts.reload.reload_model (reload.py:35-111): options missing from old ``opt.pkl`` files get the reference's
+    defaults; a checkpoint with one key missing falls back to the non-strict load with a warning."""
+    import pickle
+    import numpy as np
+    from obman_train_b200.netscripts import reload as rl
+    opts = {"atlas_lambda_regul_edges": 0.0, "atlas_lambda": 0.167, "center_idx": 0, "hidden_neurons": [1024, 256],
+            "use_shape": True, "mano_lambda_verts": 0.167, "atlas_predict_trans": True, "atlas_predict_scale": True,
+            "atlas_final_lambda": 0.167, "mano_lambda_joints3d": 0.167}
+    exp = tmp_path / "exp"
+    exp.mkdir()
+    with open(str(exp / "opt.pkl"), "wb") as f:
+        pickle.dump(opts, f)
+    assert rl.get_opts(str(exp / "checkpoint.pth.tar")) == opts and rl.get_opts(str(exp)) == opts
+    src = rl.reload_model.__globals__["HandNet"](
+        resnet_version=18, atlas_mesh=True, atlas_points_nb=642, atlas_lambda_regul_edges=0.0, atlas_lambda=0.167,
+        atlas_final_lambda=0.167, atlas_predict_trans=True, atlas_predict_scale=True, atlas_ico_divisions=3,
+        mano_root="synthetic", mano_center_idx=0, mano_comps=30, mano_neurons=[1024, 256], mano_use_shape=True,
+        mano_use_pca=True, mano_lambda_verts=0.167, mano_lambda_joints3d=0.167)
+    torch.manual_seed(9)
+    for p in src.parameters():
+        p.data.normal_()
+    state = {"module." + k: v for k, v in src.state_dict().items()}
+    torch.save({"epoch": 3, "state_dict": state, "best_score": 1.0}, str(exp / "checkpoint.pth.tar"))
+    model = rl.reload_model(str(exp / "checkpoint.pth.tar"), opts, mano_root="synthetic", ico_divisions=3)
+    assert not model.training
+    for (k, a), (_, b) in zip(src.state_dict().items(), model.state_dict().items()):
+        assert torch.equal(a, b), k
+    # one parameter missing: strict load fails, the reference's non-strict fallback kicks in (reload.py:100-108)
+    del state["module.atlas_branch.decode_scale.2.bias"]
+    torch.save({"epoch": 3, "state_dict": state, "best_score": 1.0}, str(exp / "partial.pth.tar"))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        rl.reload_model(str(exp / "partial.pth.tar"), opts, mano_root="synthetic")
+    assert any("trying without strict" in str(x.message) for x in w)
+    # no_beta drops the shape regressor
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        nb = rl.reload_model(str(exp / "checkpoint.pth.tar"), opts, mano_root="synthetic", no_beta=True)
+    assert not any(k.startswith("mano_branch.shape_reg") for k in nb.state_dict())
+    out = tmp_path / "m.obj"
+    rl.save_obj(str(out), np.array([[0.0, 1.0, 2.0], [1, 0, 0], [0, 0, 1]]), np.array([[0, 1, 2]]))
+    assert open(str(out)).read().splitlines() == ["v 0.000000 1.000000 2.000000", "v 1.000000 0.000000 0.000000",
+                                                  "v 0.000000 0.000000 1.000000", "f 1 2 3"]

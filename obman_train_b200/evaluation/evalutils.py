@@ -1,23 +1,26 @@
-"""Running averages with the reference's interface (/root/reference/mano_train/evaluation/evalutils.py:1-30):
-``AverageMeters.add_loss_value(name, value, n)`` and ``.average_meters[name].avg / .val / .sum / .count`` are what
-``traineval.py`` / ``Monitor`` read after an epoch."""
+"""Running averages behind the reference's meter interface
+(/root/reference/mano_train/evaluation/evalutils.py:1-30): ``AverageMeters.add_loss_value(name, value, n)`` feeds
+``average_meters[name]``, whose ``val`` (last value), ``sum``, ``count`` and ``avg`` are what traineval.py and the
+Monitor read after an epoch.  ``epoch_pass`` fills them once per pass from the device-side loss log."""
 
 
 class AverageMeter(object):
+    __slots__ = ("val", "sum", "count")
+
     def __init__(self):
         self.reset()
 
     def reset(self):
-        self.val = 0
-        self.avg = 0
-        self.sum = 0
-        self.count = 0
+        self.val, self.sum, self.count = 0, 0, 0
 
     def update(self, val, n=1):
         self.val = val
         self.sum += val * n
         self.count += n
-        self.avg = self.sum / self.count
+
+    @property
+    def avg(self):
+        return self.sum / self.count if self.count else 0
 
 
 class AverageMeters(object):
@@ -25,6 +28,4 @@ class AverageMeters(object):
         self.average_meters = {}
 
     def add_loss_value(self, loss_name, loss_val, n=1):
-        if loss_name not in self.average_meters:
-            self.average_meters[loss_name] = AverageMeter()
-        self.average_meters[loss_name].update(loss_val, n=n)
+        self.average_meters.setdefault(loss_name, AverageMeter()).update(loss_val, n=n)

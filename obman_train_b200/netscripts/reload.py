@@ -22,6 +22,17 @@ _OPT_DEFAULTS = (("absolute_lambda", 0), ("atlas_predict_trans", False), ("atlas
                  ("atlas_separate_encoder", False), ("atlas_final_lambda", 0), ("atlas_predict_scale", False))
 
 
+# HandNet keyword <- key of the experiment's opt.pkl (reload.py:76-104); most share the name, three do not
+_HANDNET_FROM_OPTS = tuple((k, k) for k in (
+    "absolute_lambda", "atlas_lambda_regul_edges", "atlas_lambda_laplacian", "atlas_predict_trans",
+    "atlas_predict_scale", "atlas_residual", "atlas_lambda", "atlas_final_lambda", "atlas_separate_encoder",
+    "contact_lambda", "collision_lambda", "mano_adapt_skeleton", "mano_use_pca", "mano_lambda_verts",
+    "mano_lambda_joints3d", "mano_lambda_joints2d")) + (("mano_center_idx", "center_idx"),
+                                                        ("mano_neurons", "hidden_neurons"))
+# what the reference hard-codes for every reloaded model
+_FIXED = dict(resnet_version=18, atlas_mesh=True, atlas_points_nb=642, mano_comps=30)
+
+
 def save_obj(filename, verticies, faces):
     """Wavefront .obj writer (reload.py:16-22); faces are 0-based on input, 1-based in the file."""
     with open(filename, "w") as fp:
@@ -44,33 +55,9 @@ def reload_model(model_path, checkpoint_opts, mano_root="misc/mano", ico_divisio
     for key, default in _OPT_DEFAULTS:
         checkpoint_opts.setdefault(key, default)
     mano_use_shape = False if no_beta else checkpoint_opts["use_shape"]
-    model = HandNet(
-        resnet_version=18,
-        absolute_lambda=checkpoint_opts["absolute_lambda"],
-        atlas_mesh=True,
-        atlas_points_nb=642,
-        atlas_lambda_regul_edges=checkpoint_opts["atlas_lambda_regul_edges"],
-        atlas_lambda_laplacian=checkpoint_opts["atlas_lambda_laplacian"],
-        atlas_predict_trans=checkpoint_opts["atlas_predict_trans"],
-        atlas_predict_scale=checkpoint_opts["atlas_predict_scale"],
-        atlas_residual=checkpoint_opts["atlas_residual"],
-        atlas_lambda=checkpoint_opts["atlas_lambda"],
-        atlas_final_lambda=checkpoint_opts["atlas_final_lambda"],
-        atlas_ico_divisions=ico_divisions,
-        atlas_separate_encoder=checkpoint_opts["atlas_separate_encoder"],
-        contact_lambda=checkpoint_opts["contact_lambda"],
-        collision_lambda=checkpoint_opts["collision_lambda"],
-        mano_adapt_skeleton=checkpoint_opts["mano_adapt_skeleton"],
-        mano_root=mano_root,
-        mano_center_idx=checkpoint_opts["center_idx"],
-        mano_comps=30,
-        mano_neurons=checkpoint_opts["hidden_neurons"],
-        mano_use_shape=mano_use_shape,
-        mano_use_pca=checkpoint_opts["mano_use_pca"],
-        mano_lambda_verts=checkpoint_opts["mano_lambda_verts"],
-        mano_lambda_joints3d=checkpoint_opts["mano_lambda_joints3d"],
-        mano_lambda_joints2d=checkpoint_opts["mano_lambda_joints2d"],
-    )
+    kwargs = {handnet_kw: checkpoint_opts[opt_key] for handnet_kw, opt_key in _HANDNET_FROM_OPTS}
+    kwargs.update(_FIXED, atlas_ico_divisions=ico_divisions, mano_root=mano_root, mano_use_shape=mano_use_shape)
+    model = HandNet(**kwargs)
     model.eval()
     try:
         modelio.load_checkpoint(model, resume_path=model_path, strict=True)

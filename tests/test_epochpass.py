@@ -154,3 +154,34 @@ def test_epoch_pass_world2_gloo_reduces_losses_and_gathers_distances(tmp_path):
     ref = EvalUtil()
     ref.feed_distances(d)
     assert res["auc"] == pytest.approx(float(ref.get_measures(0, 50, 20)[3]), rel=1e-6)
+
+
+def test_freeze_helpers_and_trainer_parameter_selection():
+    """netutils.rec_freeze / freeze_batchnorm_stats (netutils.py:4-19) and their effect on FlatAdamTrainer: frozen
+    parameters stay out of the flat buffers, and the optimizer indices follow the reference's
+    ``filter(requires_grad, model.parameters())`` numbering (traineval.py:105-116)."""
+    from obman_train_b200.networks import netutils
+    from obman_train_b200.trainer import FlatAdamTrainer
+    torch.manual_seed(0)
+    enc = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4))
+    head = torch.nn.Sequential(torch.nn.Linear(4, 5), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 2))
+    model = torch.nn.ModuleDict({"base_net": enc, "head": head})
+    netutils.freeze_batchnorm_stats(model)
+    assert all(m.momentum == 0 for m in model.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm))
+    assert all(p.requires_grad for p in model.parameters())
+    netutils.rec_freeze(model["base_net"])
+    assert not any(p.requires_grad for p in enc.parameters()) and all(p.requires_grad for p in head.parameters())
+    trainer = FlatAdamTrainer(model)
+    assert trainer.names == ["head." + n for n, _ in head.named_parameters()]
+    assert trainer.optim_len == len(list(head.parameters())) and trainer.optim_index == list(range(trainer.optim_len))
+    ref_opt = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=1e-4)
+    assert len(ref_opt.state_dict()["param_groups"][0]["params"]) == trainer.optim_len
+    # the frozen encoder's storage was left alone, the trainable parameters became views of the flat buffer
+    base = trainer.flat_p.untyped_storage().data_ptr()
+    assert all(p.untyped_storage().data_ptr() == base for p in head.parameters())
+    assert all(p.untyped_storage().data_ptr() != base for p in enc.parameters())
+    m = AverageMeters()
+    m.add_loss_value("a", 2.0, n=3)
+    m.add_loss_value("a", 4.0)
+    a = m.average_meters["a"]
+    assert (a.val, a.sum, a.count, a.avg) == (4.0, 10.0, 4, 2.5)

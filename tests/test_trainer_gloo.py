@@ -78,3 +78,30 @@ def test_bench_reference_arm_runs_on_cpu():
               "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0
+
+
+def test_bench_product_arm_fails_loudly_without_cuda():
+    """The product path has no CPU fallback: without a CUDA device bench.py must stop with an error, not fall back."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("needs a machine without CUDA")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr and not any(l.startswith("{") for l in r.stdout.splitlines())
+
+
+def test_complement_ranges_and_side_mask_helpers():
+    from obman_train_b200.trainer import FlatAdamTrainer, complement_ranges
+    assert complement_ranges([], 10) == [(0, 10)]
+    assert complement_ranges([(4, 6), (0, 2)], 10) == [(2, 4), (6, 10)]
+    assert complement_ranges([(0, 10)], 10) == []
+    assert complement_ranges([(3, 10)], 10) == [(0, 3)]
+    from obman_train_b200.queries import BaseQueries
+    assert FlatAdamTrainer._sides_of({BaseQueries.sides: ["left", "right"], "root": "wrist"}) == ["left", "right"]
+    assert FlatAdamTrainer._sides_of({"sides": ("right",)}) == ["right"]
+    assert FlatAdamTrainer._sides_of({"images": 0}) is None

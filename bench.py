@@ -47,6 +47,17 @@ def use_config3():
                 "ManoLayer + AtlasNet(ico-4, 2562 pts) + Chamfer(2500 GT) + contact_zones loss, 256x256")
 
 
+def use_config4():
+    """BASELINE.json configs[3]: global batch 1024 = 8 x 128 per GPU, the full loss stack: configs[2] plus the
+    edge-length regulariser on the 5120-face mesh; weak scaling like the headline."""
+    global PER_GPU_BATCH, WORKLOAD
+    use_config3()
+    PER_GPU_BATCH = 128
+    CFG.update(atlas_lambda_regul_edges=0.1)
+    WORKLOAD = ("BASELINE.json configs[3]: per-GPU batch 128 (1024 on 8 GPUs), full loss stack: 2x ResNet-18 + ManoLayer + "
+                "AtlasNet(ico-4) + Chamfer(2500 GT) + contact_zones + edge regulariser, 256x256")
+
+
 def _hand_targets(B, g):
     if CFG.get("contact_lambda"):
         # hand-shaped targets (MANO template, mm) so that the contact masks are non-trivial (SURVEY.md 8d config 3)
@@ -414,12 +425,15 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3],
-                    help="2 = BASELINE configs[1] (default, the headline); 3 = BASELINE configs[2] (B=256, contact)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="2 = BASELINE configs[1] (default, the headline); 3 = configs[2] (B=256, contact); "
+                         "4 = configs[3] (128 per GPU, full loss stack, meant for --gpus 8)")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch tensor-core profile of one step here")
     args = ap.parse_args()
     if args.config == 3:
         use_config3()
+    elif args.config == 4:
+        use_config4()
     if args.impl == "reference":
         run_reference(args)
     else:

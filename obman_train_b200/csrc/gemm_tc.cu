@@ -97,16 +97,21 @@ template <int BN, int PASSES, int TS, int OCC>
 struct GemmCfg {
   static constexpr int B_TILE_BYTES = BN * BK * 4;
   // TS == 1: A_raw | B_hi | B_lo (tf32).  TS == 2: A_raw | B with bf16 hi|lo interleaved per 32-element block.
-  static constexpr int STAGE_BYTES = TS == 2 ? (A_TILE_BYTES + B_TILE_BYTES)
-                                     : TS    ? (A_TILE_BYTES + 2 * B_TILE_BYTES)
-                                             : (A_TILE_BYTES + B_TILE_BYTES) * (PASSES == 3 ? 2 : 1);
-  static constexpr int A_COLS = TS == 2 ? 32 : 64;   // TMEM columns per stage: A hi | A lo
+  // TS == 3 (experimental, OBMAN_GEMM_STACK64): as 2, but the B tile is landed as 2*BN rows x 64 bytes (all hi rows,
+  // then all lo rows) so that ONE N = 2*BN MMA yields a_hi*b_hi and a_hi*b_lo side by side: N = 64 MMAs only reach
+  // 54 % of the tensor rate (profiles/mma_chain_r1j.txt), N = 128 MMAs the full rate.  Two accumulators (2*BN columns).
+  static constexpr bool BF = TS == 2 || TS == 3;
+  static constexpr int ACC_COLS = TS == 3 ? 2 * BN : BN;
+  static constexpr int STAGE_BYTES = BF ? (A_TILE_BYTES + B_TILE_BYTES)
+                                     : TS ? (A_TILE_BYTES + 2 * B_TILE_BYTES)
+                                          : (A_TILE_BYTES + B_TILE_BYTES) * (PASSES == 3 ? 2 : 1);
+  static constexpr int A_COLS = BF ? 32 : 64;   // TMEM columns per stage: A hi | A lo
   static constexpr int STAGES_RAW = ((OCC == 2 ? 104 : 200) * 1024) / STAGE_BYTES;
   static constexpr int STAGES_SMEM = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   // TS: every stage also owns A_COLS TMEM columns; 512 columns per SM in total
-  static constexpr int STAGES_TMEM = ((OCC == 2 ? 256 : 512) - BN) / A_COLS;
+  static constexpr int STAGES_TMEM = ((OCC == 2 ? 256 : 512) - ACC_COLS) / A_COLS;
   static constexpr int STAGES = TS ? (STAGES_SMEM < STAGES_TMEM ? STAGES_SMEM : STAGES_TMEM) : STAGES_SMEM;
-  static constexpr int TMEM_NEED = TS ? BN + STAGES * A_COLS : BN;
+  static constexpr int TMEM_NEED = TS ? ACC_COLS + STAGES * A_COLS : BN;
   static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -257,6 +262,107 @@ __device__ __forceinline__ void gemm_epilogue(uint8_t* smem, uint32_t tmem_base,
     }  // MODE != 2
 }
 
+// Epilogue of the stacked-N variant (TS == 3, MODE 0): the result is the SUM of accumulator columns [c] and [BN + c]
+// (a_hi*b_hi + a_lo*b_hi and a_hi*b_lo).  16-column chunks (two 16-register TMEM reads instead of one 32-register read),
+// staging 32 rows x 64 bytes per warp, every store / addend / mask instruction covers 8 rows x 64 contiguous bytes.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_stacked(uint8_t* smem, uint32_t tmem_base, uint64_t* accum,
+                                                      const GemmProgram& prog, const GemmEpilogue& epi, int m0, int n0,
+                                                      int n_img0, int h0, int w0, int q, int lane, int r) {
+  const int cc = lane & 3;     // 16-byte column chunk of the 64-byte staged row
+  const int rsub = lane >> 2;  // row within each group of 8
+  long long ro[4];
+  float4 add4[4], msk4[4];
+  bool row_ok;
+  long long row_off;
+  if (prog.spatial) {
+    const int tw = r % prog.TW;
+    const int th = (r / prog.TW) % prog.TH;
+    const int tn = r / (prog.TW * prog.TH);
+    const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
+    row_ok = n < prog.n_img && h < prog.h_out && w < prog.w_out;
+    row_off = n * epi.sN + h * epi.sH + w * epi.sW;
+  } else {
+    row_ok = (m0 + r) < prog.M;
+    row_off = (long long)(m0 + r) * epi.ld;
+  }
+  const long long mine = row_ok ? row_off : -1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) ro[i] = __shfl_sync(0xffffffffu, mine, 8 * i + rsub);
+  const bool ptr_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
+                        reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0 && !epi.accumulate;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) epilogue_prefetch(epi, prog, ro[i], n0 + 4 * cc, ptr_ok, add4[i], msk4[i]);
+  mbar_wait(accum, 0);
+  tc_fence_after();
+  if (r == 0) trace_stamp(epi, 6);
+  uint8_t* wbase = smem + q * 2048;   // 32 rows x 64 B per warp (stage 0 is free: every operand read has retired)
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    if (n0 + c0 >= prog.N) break;  // warp-uniform
+    const int col = n0 + c0 + 4 * cc;
+    const bool colvec = (col + 3 < prog.N) && ptr_ok;
+    if (c0 > 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) epilogue_prefetch(epi, prog, ro[i], col, ptr_ok, add4[i], msk4[i]);
+    }
+    float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (epi.bias) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (col + e < prog.N) bias4[e] = __ldg(epi.bias + col + e);
+    }
+    uint32_t v[16], v2[16];
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    tmem_ld_32x16(lane_addr + (uint32_t)c0, v);
+    tmem_ld_32x16(lane_addr + (uint32_t)(BN + c0), v2);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("" : "+f"(msk4[i].x), "+f"(msk4[i].y), "+f"(msk4[i].z), "+f"(msk4[i].w));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float4 t;
+      t.x = __uint_as_float(v[4 * c]) + __uint_as_float(v2[4 * c]);
+      t.y = __uint_as_float(v[4 * c + 1]) + __uint_as_float(v2[4 * c + 1]);
+      t.z = __uint_as_float(v[4 * c + 2]) + __uint_as_float(v2[4 * c + 2]);
+      t.w = __uint_as_float(v[4 * c + 3]) + __uint_as_float(v2[4 * c + 3]);
+      *reinterpret_cast<float4*>(wbase + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = t;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = 8 * i + rsub;
+      const long long roff = ro[i];
+      if (roff < 0 || col >= prog.N) continue;
+      const float4 a = *reinterpret_cast<const float4*>(wbase + rr * 64 + ((cc ^ ((rr >> 1) & 3)) << 4));
+      float x[4] = {epi.alpha * a.x + bias4[0], epi.alpha * a.y + bias4[1], epi.alpha * a.z + bias4[2],
+                    epi.alpha * a.w + bias4[3]};
+      if (colvec && ((roff & 3) == 0)) {
+        x[0] += add4[i].x; x[1] += add4[i].y; x[2] += add4[i].z; x[3] += add4[i].w;
+        if (epi.relu) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+        }
+        x[0] = msk4[i].x > 0.f ? x[0] : 0.f; x[1] = msk4[i].y > 0.f ? x[1] : 0.f;
+        x[2] = msk4[i].z > 0.f ? x[2] : 0.f; x[3] = msk4[i].w > 0.f ? x[3] : 0.f;
+        *reinterpret_cast<float4*>(epi.out + roff + col) = make_float4(x[0], x[1], x[2], x[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (col + e >= prog.N) break;
+          float y = x[e];
+          if (epi.addend) y += epi.addend[roff + col + e];
+          if (epi.relu) y = fmaxf(y, 0.f);
+          if (epi.mask_src) y = epi.mask_src[roff + col + e] > 0.f ? y : 0.f;
+          if (epi.accumulate) atomicAdd(epi.out + roff + col + e, y);
+          else epi.out[roff + col + e] = y;
+        }
+      }
+    }
+    __syncwarp();  // staging is overwritten by the next chunk
+  }
+}
+
 // CL > 1 (TS path only): thread-block cluster of CL CTAs along the M-tile axis.  They share the weight tile, so
 // each CTA fetches 1/CL of it and TMA-multicasts it to all of them: the kernels were L2->SM bandwidth bound
 // (~9 TB/s measured against ~42 B/clk/SM), the weight tile being 2/3 of the bytes of every K block.
@@ -337,7 +443,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
     return smem + s * Cfg::STAGE_BYTES + (TS ? A_TILE_BYTES + B_TILE_BYTES : 2 * A_TILE_BYTES + B_TILE_BYTES);
   };
   // TS: TMEM columns of stage s: [BN + A_COLS s, + A_COLS/2) = A hi, next A_COLS/2 = A lo
-  auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(BN + Cfg::A_COLS * s); };
+  auto tmem_a = [&](int s) { return tmem_base + (uint32_t)(Cfg::ACC_COLS + Cfg::A_COLS * s); };
 
   // MODE 1: number of 32-column groups of this tile that exist (B = stacked input taps).
   // MODE 2 (roles swapped: A = stacked input taps, B = dY channels): number of 32-row groups that exist.
@@ -401,8 +507,15 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
           if (TS == 1)
             tma_load_2d_mc(stage_blo(s) + cl_rank * ROWS * 128, &maps.b_lo, &full[s], kc, n0 + cl_rank * ROWS, CL_MASK);
         } else {
+          if (TS == 3) {
+            // packed row of this K block = 64 bytes of hi then 64 bytes of lo: two 64-byte-wide boxes (SW64 map) land
+            // them as rows 0..BN-1 (hi) and BN..2BN-1 (lo) of one 2*BN x 64-byte tile
+            tma_load_2d(stage_b(s), &maps.b, &full[s], prog.tap_bk[tap] + kb * BK, n0);
+            tma_load_2d(stage_b(s) + BN * 64, &maps.b, &full[s], prog.tap_bk[tap] + kb * BK + 16, n0);
+          } else {
           tma_load_2d(stage_b(s), &maps.b, &full[s], prog.tap_bk[tap] + kb * BK, n0);
           if (TS == 1) tma_load_2d(stage_blo(s), &maps.b_lo, &full[s], prog.tap_bk[tap] + kb * BK, n0);
+          }
         }
         if (it == 0) trace_stamp(epi, 2);
         if (it == n_iters - 1) trace_stamp(epi, 3);
@@ -410,7 +523,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = TS == 2 ? umma_idesc_bf16(BM, BN) : umma_idesc_tf32(BM, BN, MODE != 0, MODE != 0);
+    const uint32_t idesc = Cfg::BF ? umma_idesc_bf16(BM, BN) : umma_idesc_tf32(BM, BN, MODE != 0, MODE != 0);
+    const uint32_t idesc_wide = umma_idesc_bf16(BM, 2 * BN);   // TS == 3 only
     // K-major: 4 k-steps of 32 bytes inside the 128-byte row (SW128, 8-row groups 1024 B apart).
     // MN-major (TF32 => SW128 with 32-byte atoms): 4 k-steps of 8 pixel rows (1024 B), 4-row K atoms 512 B
     // apart (SBO), 32-channel groups 4096 B apart (LBO)
@@ -428,7 +542,16 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         if (it == 0) trace_stamp(epi, 4);
         const uint32_t a_hi = smem_u32(stage_a(s)), b_hi = smem_u32(stage_b(s));
         const uint32_t a_lo = smem_u32(stage_alo(s)), b_lo = smem_u32(stage_blo(s));
-        if (TS == 2) {
+        if (TS == 3) {
+          // stacked B: rows 0..BN-1 = b_hi, rows BN..2BN-1 = b_lo, 64-byte rows (SW64: 8-row groups 512 B apart)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint64_t db = umma_desc(b_hi + k * 32, 16, 512, 4);
+            const uint32_t ta_hi = tmem_a(s) + k * 8, ta_lo = tmem_a(s) + 16 + k * 8;
+            umma_f16_ts(tmem_base, ta_hi, db, idesc_wide, (it > 0 || k > 0) ? 1u : 0u);   // [a_hi*b_hi | a_hi*b_lo]
+            umma_f16_ts(tmem_base, ta_lo, db, idesc, 1u);                                  // columns 0..BN-1 += a_lo*b_hi
+          }
+        } else if (TS == 2) {
           // bf16 hi|lo: every 128-byte B row holds 32 hi then 32 lo values of this K block; K = 16 per MMA
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
@@ -482,7 +605,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         const uint32_t ph = (it / S) & 1;
         mbar_wait(&full[s], ph);
         const uint32_t row = smem_u32(stage_a(s)) + r * 128;
-        if (TS == 2) {
+        if (Cfg::BF) {
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -490,7 +613,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
             split_bf16x2(v.x, v.y, hi[2 * j], lo[2 * j]);
             split_bf16x2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
           }
-          const uint32_t dst = lane_base + (uint32_t)(BN + Cfg::A_COLS * s);
+          const uint32_t dst = lane_base + (uint32_t)(Cfg::ACC_COLS + Cfg::A_COLS * s);
           tmem_st_32x16(dst, hi);
           tmem_st_32x16(dst + 16, lo);
           tmem_st_wait();
@@ -542,7 +665,8 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
         mbar_arrive(&conv[s]);
       }
     }
-    gemm_epilogue<BN, MODE>(smem, tmem_base, accum, prog, epi, m0, n0, n_img0, h0, w0, q, lane, r);
+    if (TS == 3) gemm_epilogue_stacked<BN>(smem, tmem_base, accum, prog, epi, m0, n0, n_img0, h0, w0, q, lane, r);
+    else gemm_epilogue<BN, MODE>(smem, tmem_base, accum, prog, epi, m0, n0, n_img0, h0, w0, q, lane, r);
   }
   tc_fence_before();
   __syncthreads();
@@ -1060,6 +1184,11 @@ static int dispatch_gemm(int BN, int passes, int ts, const GemmMaps& maps, const
   }
 #define OBMAN_GEMM_CASE(bn)                                                                         \
   if (BN == bn) {                                                                                   \
+    if (MODE == 0 && ts == 3) {                                                                     \
+      if (bn == 64) return launch_gemm<64, 3, 0, 3, 2>(maps, prog, epi, grid, st);                  \
+      set_error("gemm_tc: the stacked-N variant exists for 64-wide tiles only");                    \
+      return OBMAN_ERR_UNSUPPORTED;                                                                 \
+    }                                                                                               \
     if (MODE == 0 && ts == 2) {                                                                     \
       constexpr int occ = (bn <= 128 ? 2 : 1);                                                      \
       if (cl == 4) return launch_gemm<bn, 3, 0, 2, occ, 4>(maps, prog, epi, grid, st);              \
@@ -1117,6 +1246,17 @@ static int pick_bn(int N, long long m_tiles) {
   return best;
 }
 
+// Experimental (default off, untested on hardware at the end of round 1): stacked-N MMAs for 64-wide column tiles on the
+// 3xBF16 path, see GemmCfg / TS == 3.  OBMAN_GEMM_STACK64=1 switches it on.
+static bool stack64_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OBMAN_GEMM_STACK64");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v != 0;
+}
+
 static bool ts_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -1150,7 +1290,8 @@ extern "C" int obman_gemm(const float* A, long long lda, const float* W, const f
   const long long m_tiles = (M + BM - 1) / BM;
   const int BN = pick_bn(N, m_tiles);
   const bool bf = passes == OBMAN_PREC_3XBF16;
-  const int ts = bf ? 2 : ((W_lo != nullptr) && passes == 3 && ts_enabled());
+  int ts = bf ? 2 : ((W_lo != nullptr) && passes == 3 && ts_enabled());
+  if (ts == 2 && BN == 64 && stack64_enabled() && cluster_for(m_tiles) == 1) ts = 3;
   OBMAN_REQUIRE(W_lo == nullptr || passes == 1 || ts == 1, "obman_gemm: pre-split weights need the TS path (OBMAN_GEMM_TS=0 set?)");
   OBMAN_REQUIRE(!bf || (ldw % 32 == 0 && ldw >= (K + 31) / 32 * 32),
                 "obman_gemm: packed bf16 weights need ldw = K rounded up to 32 (see obman_pack_bf16)");
@@ -1164,7 +1305,9 @@ extern "C" int obman_gemm(const float* A, long long lda, const float* W, const f
     uint64_t dimsb[2] = {(uint64_t)(bf ? (K + 31) / 32 * 32 : K), (uint64_t)N};
     uint64_t stridesb[1] = {(uint64_t)ldw * 4};
     uint32_t boxb[2] = {BK, (uint32_t)(ts ? BN / cluster_for(m_tiles) : BN)};
-    rc = make_tensor_map(&maps.b, W, 2, dimsb, stridesb, boxb);
+    if (ts == 3) boxb[0] = 16;   // 64-byte-wide boxes: hi half and lo half of a packed K block are fetched separately
+    rc = make_tensor_map(&maps.b, W, 2, dimsb, stridesb, boxb,
+                         ts == 3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     if (ts == 1) {
       rc = make_tensor_map(&maps.b_lo, W_lo, 2, dimsb, stridesb, boxb);
@@ -1293,7 +1436,8 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
   const long long m_tiles = (long long)((n_img + TN - 1) / TN) * prog.tiles_h * prog.tiles_w;
   const int BN = pick_bn(c_out, m_tiles);
   const bool bf = passes == OBMAN_PREC_3XBF16;
-  const int ts = bf ? 2 : ((w_lo != nullptr) && passes == 3 && ts_enabled());
+  int ts = bf ? 2 : ((w_lo != nullptr) && passes == 3 && ts_enabled());
+  if (ts == 2 && BN == 64 && stack64_enabled() && cluster_for(m_tiles) == 1) ts = 3;
   OBMAN_REQUIRE(w_lo == nullptr || passes == 1 || ts == 1, "obman_conv_nhwc: pre-split weights need the TS path");
   OBMAN_REQUIRE(!bf || c_in % 32 == 0, "obman_conv_nhwc: packed bf16 weights need c_in %% 32 == 0 (c_in=%d)", c_in);
   if (bf) passes = 3;
@@ -1323,7 +1467,9 @@ extern "C" int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, in
     uint64_t dimsb[2] = {(uint64_t)w_slots * (uint64_t)c_in, (uint64_t)c_out};
     uint64_t stridesb[1] = {dimsb[0] * 4};
     uint32_t boxb[2] = {BK, (uint32_t)(ts ? BN / cluster_for(m_tiles) : BN)};
-    int rc = make_tensor_map(&maps.b, w, 2, dimsb, stridesb, boxb);
+    if (ts == 3) boxb[0] = 16;   // see obman_gemm
+    int rc = make_tensor_map(&maps.b, w, 2, dimsb, stridesb, boxb,
+                             ts == 3 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     if (ts == 1) {
       rc = make_tensor_map(&maps.b_lo, w_lo, 2, dimsb, stridesb, boxb);

@@ -130,3 +130,21 @@ def test_resnet18_unit_table_matches_the_reference_state_dict_order():
         h_out = size[conv.split(".")[0]]
         macs += h_out * h_out * O * I * k * k
     assert abs(macs / 1e9 - 2.369) < 0.005, macs / 1e9
+
+
+def test_streams_module_is_a_no_op_when_disabled():
+    """OBMAN_OVERLAP=0 / streams.set_enabled(False): fork / join / on_aux must not touch CUDA at all (CPU-safe)."""
+    from obman_train_b200 import streams
+    prev = streams.set_enabled(False)
+    try:
+        assert streams.enabled() is False
+        streams.fork()
+        streams.fork(streams.CHAIN)
+        with streams.on_aux(streams.BRANCH):
+            x = torch.ones(3) * 2
+        streams.join(streams.BRANCH)
+        streams.join()
+        assert x.sum().item() == 6.0
+        assert (streams.WGRAD, streams.CHAIN, streams.BRANCH) == (0, 1, 2)
+    finally:
+        assert streams.set_enabled(prev) is False

@@ -728,6 +728,38 @@ static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const Gemm
 // converted ring when its MMAs retire.  SWAP = 1: rows = stacked taps, columns = dY channels (c_out <= 64).
 constexpr int TRACE_IT = 12;   // main-loop iteration whose inner phases obman_debug_trace records (slots 8..15)
 
+// Epilogue of the swapped + stacked weight-gradient variant (SWAP == 2): D[m, n] = acc[m, n] + acc[m, BN + n] with
+// m = stacked (tap, c_in) index, n = output channel; dw is (c_out, taps*c_in) row-major, element (m, n) at n*ld + m, so
+// the 32 lanes of a warp (consecutive m) make every column one coalesced access (same as gemm_epilogue's MODE 2).
+template <int BN>
+__device__ __forceinline__ void wgrad_epilogue_swapped_stacked(uint32_t tmem_base, uint64_t* accum,
+                                                               const GemmProgram& prog, const GemmEpilogue& epi,
+                                                               int m0, int n0, int q, int r) {
+  mbar_wait(accum, 0);
+  tc_fence_after();
+  if (r == 0) trace_stamp(epi, 6);
+  const bool row_ok = (m0 + r) < prog.M;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    if (n0 + c0 >= prog.N) break;  // warp-uniform
+    uint32_t v[16], v2[16];
+    tmem_ld_32x16(lane_addr + (uint32_t)c0, v);
+    tmem_ld_32x16(lane_addr + (uint32_t)(BN + c0), v2);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int col = n0 + c0 + j;
+      if (col >= prog.N) break;
+      float* dst = epi.out + (long long)col * epi.ld + (m0 + r);
+      const float y = epi.alpha * (__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+      if (epi.accumulate) atomicAdd(dst, y);
+      else *dst = y;
+    }
+  }
+}
+
 template <int BN, int SWAP, int OCC>
 struct WgradCfg {
   static constexpr int A_RAW = 128 * 128;              // 4 groups x 32 pixels x 32 channels fp32
@@ -737,10 +769,13 @@ struct WgradCfg {
   static constexpr int BUDGET = (OCC == 2 ? 104 : 200) * 1024;
   static constexpr int R = 2;                          // raw stages
   static constexpr int C_SMEM = (BUDGET - R * RAW_BYTES) / B_CONV;
-  static constexpr int C_TMEM = ((OCC == 2 ? 256 : 512) - BN) / 32;
+  // SWAP == 2 (experimental, OBMAN_WGRAD_STACK64): roles swapped AND the converted B operand stacked as 2*BN rows of
+  // 64 bytes (hi rows, then lo rows), two accumulators - the weight-gradient counterpart of GemmCfg's TS == 3
+  static constexpr int ACC_COLS = SWAP == 2 ? 2 * BN : BN;
+  static constexpr int C_TMEM = ((OCC == 2 ? 256 : 512) - ACC_COLS) / 32;
   static constexpr int C0 = C_SMEM < C_TMEM ? C_SMEM : C_TMEM;
   static constexpr int C = C0 > 6 ? 6 : C0;            // converted stages
-  static constexpr int TMEM_NEED = BN + C * 32;
+  static constexpr int TMEM_NEED = ACC_COLS + C * 32;
   static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512));
   static constexpr int SMEM_BYTES = R * RAW_BYTES + C * B_CONV + 1024 + 256;
   // one splitter thread per operand row: 4 warps for the 128 A rows (also the epilogue warps), BN / 32 for B
@@ -858,7 +893,16 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
         if (it == 0) trace_stamp(epi, 4);
         if (it == TRACE_IT) trace_stamp(epi, 13);
         const uint32_t b = smem_u32(conv_b(cs));
-        const uint32_t ta = tmem_base + (uint32_t)(BN + 32 * cs);
+        const uint32_t ta = tmem_base + (uint32_t)(Cfg::ACC_COLS + 32 * cs);
+        if (SWAP == 2) {
+          const uint32_t idesc_wide = umma_idesc_bf16(BM, 2 * BN);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint64_t db = umma_desc(b + k * 32, 16, 512, 4);   // 2*BN rows x 64 B, SW64
+            umma_f16_ts(tmem_base, ta + k * 8, db, idesc_wide, (it > 0 || k > 0) ? 1u : 0u);   // [a_hi*b_hi | a_hi*b_lo]
+            umma_f16_ts(tmem_base, ta + 16 + k * 8, db, idesc, 1u);                             // cols 0..BN-1 += a_lo*b_hi
+          }
+        } else {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const uint64_t db = umma_desc(b + k * 32, 16, 1024, 2);
@@ -866,6 +910,7 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
           umma_f16_ts(tmem_base, ta + 16 + k * 8, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
           umma_f16_ts(tmem_base, ta + k * 8, dbl, idesc, 1u);
           umma_f16_ts(tmem_base, ta + k * 8, db, idesc, 1u);
+        }
         }
         umma_commit(&empty[cs]);
         if (it == TRACE_IT) trace_stamp(epi, 14);
@@ -895,7 +940,7 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
         for (int p = 0; p < 16; ++p) hi[p] = lo[p] = 0u;
       }
       mbar_arrive(&rawfree[rs]);
-      const uint32_t dst = lane_base + (uint32_t)(BN + 32 * cs);
+      const uint32_t dst = lane_base + (uint32_t)(Cfg::ACC_COLS + 32 * cs);
       tmem_st_32x16(dst, hi);
       tmem_st_32x16(dst + 16, lo);
       tmem_st_wait();
@@ -903,7 +948,8 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
       mbar_arrive(&conv[cs]);
       if (r == 0 && it == TRACE_IT) trace_stamp(epi, 12);
     }
-    gemm_epilogue<BN, SWAP ? 2 : 1>(smem, tmem_base, accum, prog, epi, m0, n0, 0, 0, 0, q, lane, r);
+    if (SWAP == 2) wgrad_epilogue_swapped_stacked<BN>(tmem_base, accum, prog, epi, m0, n0, q, r);
+    else gemm_epilogue<BN, SWAP ? 2 : 1>(smem, tmem_base, accum, prog, epi, m0, n0, 0, 0, 0, q, lane, r);
   } else {
     // ---- B rows: one warp per 32-channel group; K-major rows [32 hi | 32 lo], hand-swizzled for SW128 ----
     const int g = warp - 6;
@@ -921,11 +967,21 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
         for (int p = 0; p < 16; ++p) hi[p] = lo[p] = 0u;
       }
       mbar_arrive(&rawfree[rs]);
+      if (SWAP == 2) {
+        // stacked: row n (64 B of hi) and row BN + n (64 B of lo), hand-swizzled for SW64 (16-byte chunk ^ row bits 1..2)
+        const uint32_t row_hi = smem_u32(conv_b(cs)) + n * 64, row_lo = row_hi + BN * 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sts_v4(row_hi + ((j ^ ((n >> 1) & 3)) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          sts_v4(row_lo + ((j ^ ((n >> 1) & 3)) << 4), lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+      } else {
       const uint32_t row = smem_u32(conv_b(cs)) + n * 128;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         sts_v4(row + ((j ^ (n & 7)) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
         sts_v4(row + (((j + 4) ^ (n & 7)) << 4), lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+      }
       }
       fence_proxy_async_smem();
       mbar_arrive(&conv[cs]);
@@ -1600,7 +1656,15 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
   epi.trace = g_trace; epi.trace_cap = g_trace_cap;
   dim3 grid((unsigned)(m_tiles * prog.n_tiles), 1, (unsigned)splits);
   if (bf) {
-    if (swapped) return launch_wgrad_bf16<64, 1, 2>(maps, prog, epi, grid, st);
+    if (swapped) {
+      static int wstack = -1;
+      if (wstack < 0) {
+        const char* e = getenv("OBMAN_WGRAD_STACK64");   // experimental, default off (not yet run on hardware)
+        wstack = (e && e[0] == '1') ? 1 : 0;
+      }
+      if (wstack) return launch_wgrad_bf16<64, 2, 2>(maps, prog, epi, grid, st);
+      return launch_wgrad_bf16<64, 1, 2>(maps, prog, epi, grid, st);
+    }
     if (BN == 256) return launch_wgrad_bf16<256, 0, 1>(maps, prog, epi, grid, st);
     if (BN == 128) return launch_wgrad_bf16<128, 0, 1>(maps, prog, epi, grid, st);
     return launch_wgrad_bf16<64, 0, 1>(maps, prog, epi, grid, st);

@@ -41,3 +41,40 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
+
+
+def test_every_public_op_refuses_cpu_tensors_instead_of_falling_back():
+    """There is no CPU path: each Python entry point of the product must raise on host tensors."""
+    import numpy as np
+    import pytest
+    import torch
+    from obman_train_b200 import dense, encoder, functional as Fb, mlp
+    from obman_train_b200.manopth.manolayer import ManoLayer
+    from obman_train_b200.networks.branches.atlasbranch import edge_loss
+    from obman_train_b200.networks.branches.atlasutils import ChamferLoss
+    from obman_train_b200.networks.branches.laplacianloss import LaplacianLoss
+    from obman_train_b200.icosphere import icosphere
+    x = torch.randn(2, 12, 3)
+    y = torch.randn(2, 9, 3)
+    verts, faces = icosphere(0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Fb.chamfer(x, y)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ChamferLoss()(x, y)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Fb.nearest_neighbours(x, y)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Fb.mesh_exterior(x, x, torch.tensor(np.asarray(faces), dtype=torch.int32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        LaplacianLoss(faces, torch.tensor(verts, dtype=torch.float32))(x)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        edge_loss(x, faces)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        dense.gemm(torch.randn(4, 32), torch.randn(8, 32), passes=3)
+    with pytest.raises(RuntimeError):
+        mlp.linear(torch.randn(4, 32), torch.randn(8, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        encoder.resnet18_features(torch.randn(1, 3, 64, 64), [])
+    layer = ManoLayer(center_idx=0, ncomps=30, side="right", mano_root="synthetic")
+    with pytest.raises(RuntimeError):
+        layer(torch.zeros(2, 33), th_betas=torch.zeros(2, 10))

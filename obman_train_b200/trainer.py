@@ -253,6 +253,13 @@ class FlatAdamTrainer(object):
         self._graph.replay()
         return self._static_loss
 
+    def release_graph(self):
+        """Drop the captured step (graph, static inputs / outputs).  Must run before the NCCL process group is
+        destroyed: a live graph holds NCCL kernels, and tearing the communicator down underneath it hangs."""
+        self._graph = None
+        self._static_all = self._static_loss = None
+        self._static_sample = None
+
     # ---- checkpoint interchange with torch.optim.Adam (modelio.load_checkpoint / save_checkpoint) ---------------
     def state_dict(self):
         """Optimizer state in ``torch.optim.Adam.state_dict()`` format, indexed like the reference's optimizer, so a

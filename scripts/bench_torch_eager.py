@@ -20,7 +20,9 @@ def run(allow_tf32, steps=10, warmup=3):
     torch.backends.cudnn.allow_tf32 = allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
-    model = HandNet(**bench.CFG).eval()
+    wl = bench.Workload(int(os.environ.get("EAGER_CONFIG", "2")))
+    batch = int(os.environ.get("EAGER_BATCH", str(wl.batch)))
+    model = HandNet(**wl.cfg).eval()
     state = {k: v.detach().clone().cuda() for k, v in model.state_dict().items()}
     leaves = []
     for k, v in state.items():
@@ -31,11 +33,13 @@ def run(allow_tf32, steps=10, warmup=3):
     tables = {s: {k: v.detach().cuda() for k, v in getattr(model.mano_branch, "mano_layer_" + s).named_buffers()
                   if k != "th_faces"} for s in ("right", "left")}
     grid, faces = model.atlas_branch.test_verts.cuda(), model.atlas_branch.test_faces
-    sample = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in bench.synthetic_sample(bench.PER_GPU_BATCH, 0).items()}
+    from obman_train_b200.assets import load_contacts
+    zones = load_contacts()[1]
+    sample = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in wl.sample(batch, 0).items()}
 
     def step():
         opt.zero_grad()
-        total, _, _ = nets.handnet_forward(state, bench.CFG, sample, tables, grid, faces, None)
+        total, _, _ = nets.handnet_forward(state, wl.cfg, sample, tables, grid, faces, zones)
         total.backward()
         opt.step()
 
@@ -49,9 +53,9 @@ def run(allow_tf32, steps=10, warmup=3):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"allow_tf32_cudnn": allow_tf32, "ms_per_step": ms, "images_per_s": bench.PER_GPU_BATCH / ms * 1e3}
+    return {"allow_tf32_cudnn": allow_tf32, "ms_per_step": ms, "images_per_s": batch / ms * 1e3, "batch": batch, "workload": wl.name}
 
 
 if __name__ == "__main__":
     out = [run(True), run(False)]
-    print(json.dumps({"comparator": "eager PyTorch (cuDNN/cuBLAS) reference algorithm, batch 64, one B200", "runs": out}))
+    print(json.dumps({"comparator": "eager PyTorch (cuDNN/cuBLAS) reference algorithm, one B200", "runs": out}))

@@ -11,17 +11,16 @@ import bench  # noqa: E402
 
 
 def main():
-    if os.environ.get("PROF_CONFIG", "2") == "3":
-        bench.use_config3()
+    wl = bench.Workload(int(os.environ.get("PROF_CONFIG", "3")))
     from obman_train_b200 import dense
     from obman_train_b200.networks.handnet import HandNet
     from obman_train_b200.trainer import FlatAdamTrainer
     from obman_train_b200.queries import TransQueries, BaseQueries
     dense.set_precision("bf16x3", "bf16x3")
     torch.manual_seed(0)
-    model = HandNet(**bench.CFG).eval().cuda()
+    model = HandNet(**wl.cfg).eval().cuda()
     trainer = FlatAdamTrainer(model, lr=1e-4)
-    host = bench.synthetic_sample(bench.PER_GPU_BATCH, 1000)
+    host = wl.sample(wl.batch, 1000)
     sample = {TransQueries.images: host["images"].cuda(), BaseQueries.sides: host["sides"], "root": host["root"],
               TransQueries.joints3d: host["joints3d"].cuda(), TransQueries.verts3d: host["verts3d"].cuda(),
               TransQueries.objpoints3d: host["objpoints3d"].cuda()}

@@ -4,7 +4,10 @@
  * an ATen/cuDNN/cuBLAS call chain.  Each entry point below replaces one such chain and
  * is what a maintainer would bind from Python (ctypes stub in INTEGRATION.md).  Conventions:
  *   - plain C types only; every pointer is a DEVICE pointer owned by the caller (inputs, outputs and
- *     workspaces); the library allocates nothing and keeps no reference after return;
+ *     workspaces) EXCEPT the small descriptor tables that say so (convolution tap tables tap_dh / tap_dw /
+ *     tap_phase / tap_wslot, the term tables of the scalar-loss stage): those are HOST arrays, read during the
+ *     call and copied into the kernel's parameters; the library allocates nothing and keeps no reference after
+ *     return;
  *   - `stream` is the caller's cudaStream_t (as void*); all work is enqueued asynchronously on it;
  *   - return 0 on success, a negative code on failure (OBMAN_ERR_*), message via obman_get_last_error();
  *   - tensors are dense row-major fp32 unless stated; point clouds are (B, P, 3) xyz-interleaved,
@@ -43,9 +46,13 @@ int obman_nn_fwd(const float* x, const float* y, int B, int N, int M, float* min
  * min1/idx1 (B,N): nearest gt of every pred; min2/idx2 (B,M): nearest pred of every gt (saved for bwd). */
 int obman_chamfer_fwd(const float* preds, const float* gts, int B, int N, int M, float* loss1,
                       float* loss2, float* min1, int* idx1, float* min2, int* idx2, void* stream);
-/* Autograd of the above: gloss1/gloss2 (B) -> gpreds (B,N,3) and, if non-null, ggts (B,M,3). */
+/* Autograd of the above: gloss1/gloss2 -> gpreds (B,N,3) and, if non-null, ggts (B,M,3).  g_stride 1: gloss1/gloss2
+ * are (B) vectors; g_stride 0: each points to ONE float that applies to every sample (the gradient of
+ * torch.mean(loss_1 + loss_2), atlasbranch.py:235,243, without materialising the expanded vector).  Scatter-free:
+ * the inverse of the nearest-neighbour index is built per sample in shared memory, every output element is written
+ * once in a fixed order (bit-reproducible); clouds beyond ~18 k points take a float-atomic fallback. */
 int obman_chamfer_bwd(const float* preds, const float* gts, const int* idx1, const int* idx2,
-                      const float* gloss1, const float* gloss2, int B, int N, int M, float* gpreds,
+                      const float* gloss1, const float* gloss2, int g_stride, int B, int N, int M, float* gpreds,
                       float* ggts, void* stream);
 
 /* ---- Contact loss -------------------------------------------------------------------------------
@@ -205,6 +212,37 @@ int obman_edge_loss_fwd(const float* V, const int* faces, int B, int N, int F, f
 /* vf (N,Kf) int32: ids of the faces incident to each vertex, -1 padded (vertex-centric gather, no atomics). */
 int obman_edge_loss_bwd(const float* V, const int* faces, const int* vf, const float* stats,
                         const float* gloss, int B, int N, int F, int Kf, float* gV, void* stream);
+/* ---- Scalar-loss stage (csrc/loss_head.cu) -------------------------------------------------------------------
+ * Tables (a, b, ga, p, q, rows, width, ... slot, group) are HOST arrays of n_terms entries whose pointer entries are
+ * device pointers; they are copied into the kernel's parameters.  `weights` is a DEVICE float vector indexed by
+ * `slot`: loss lambdas are read at execution time, so a captured CUDA graph follows HandNet.decay_regul
+ * (traineval.py:401-404).  All reductions have a fixed order.
+ *
+ * GT object statistics of AtlasLoss.compute_loss (atlasbranch.py:211-227): gt (B,M,3) -> centroid (B,3) = mean_i gt,
+ * scale (B) = max_i |gt_i - centroid|, centred (B,M,3) = gt - centroid (each output nullable). */
+int obman_object_targets(const float* gt, int B, int M, float* centroid, float* scale, float* centred, void* stream);
+/* Up to 8 torch mse_loss terms in one launch (ManoLoss.compute_loss manobranch.py:251-324; trans / scale terms
+ * atlasbranch.py:211-227): terms[k] = mean over rows[k] x [col0[k], col1[k]) of (a_k - b_k)^2 on (rows, width) row-major
+ * tensors (b_k NULL = compare with zero); wsum[0] = sum_k weights[slot[k]] * terms[k].  partial: 32 * n_terms floats;
+ * ticket: one int that is zero before the first call (the kernel leaves it zero). */
+int obman_sq_terms_fwd(const float* const* a, const float* const* b, const int* rows, const int* width,
+                       const int* col0, const int* col1, const int* slot, int n_terms, const float* weights,
+                       float* partial, int* ticket, float* terms, float* wsum, void* stream);
+/* ga_k (rows, width) = gwsum[0] * weights[slot[k]] * d terms[k] / d a_k (zero outside the column range); ga_k NULL = skip. */
+int obman_sq_terms_bwd(const float* const* a, const float* const* b, float* const* ga, const int* rows,
+                       const int* width, const int* col0, const int* col1, const int* slot, int n_terms,
+                       const float* weights, const float* gwsum, void* stream);
+/* total[0] = sum_k weights[slot[k]] * vals[k], vals[k] = scale[k] * (sum_i p_k[i] + sum_i q_k[i]) over len[k] elements
+ * (q_k nullable; len 1 = a scalar loss, len B = per-sample losses such as ChamferLoss's loss_1 / loss_2 with
+ * scale = 1/B).  aux[0..3] = the weighted sum restricted to group 0..3 (e.g. contact_loss, handnet.py:363-367),
+ * aux[4 + k] = vals[k].  At most 12 terms. */
+int obman_loss_combine_fwd(const float* const* p, const float* const* q, const int* len, const float* scale,
+                           const int* slot, const int* group, int n_terms, const float* weights, float* total,
+                           float* aux, void* stream);
+/* gterm[k] = gtotal[0] * weights[slot[k]] * scale[k]: the gradient of every element of term k. */
+int obman_loss_combine_bwd(const int* slot, const float* scale, int n_terms, const float* weights,
+                           const float* gtotal, float* gterm, void* stream);
+
 /* Fused torch.optim.Adam step (traineval.py:113-116) on flat fp32 buffers (16-byte aligned); g is multiplied by
  * grad_scale.  hyper_dev: device float[2] = {1-based step number, learning-rate multiplier} - device memory so that a
  * captured CUDA graph keeps exact bias corrections and follows StepLR (traineval.py:179-182): lr_eff = lr * hyper_dev[1]. */

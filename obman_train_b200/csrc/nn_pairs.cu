@@ -110,12 +110,97 @@ chamfer_mean_kernel(const float* __restrict__ minx, const float* __restrict__ mi
   if (threadIdx.x == 0) (dir == 0 ? loss1 : loss2)[b] = s / (float)n;
 }
 
-// d loss / d points for loss = sum_b gl1[b]*mean_j minx[b,j] + gl2[b]*mean_i miny[b,i].
+// d loss / d points for loss = sum_b gl1[b]*mean_j minx[b,j] + gl2[b]*mean_i miny[b,i], for ONE of the two clouds
+// ("a", A points; the other cloud "o" has O points):
+//   ga[t] = 2 s_a (a_t - o_{idx_a[t]})                                   direct term: own nearest neighbour
+//         + sum over { i : idx_o[i] == t } of 2 s_o (a_t - o_i)          scatter term: points of o whose nearest is a_t
+// with s_a = g_a[b] / A, s_o = g_o[b] / O.  The scatter term is turned into a gather: one CTA per sample builds the
+// inverse of idx_o in shared memory (counting sort with integer atomics: counts -> exclusive scan -> bucket lists), every
+// thread then owns output points and sums its bucket in ascending index order.  No float atomics, no zero-fill of the
+// output, every output element written exactly once, bit-reproducible.  HBM bytes: 12 A + 12 O + 4 (A + O) read, 12 A
+// written.  Shared memory: (2 A + 2 + O) ints.
+constexpr int CH_BWD_THREADS = 512;
+
+__global__ void __launch_bounds__(CH_BWD_THREADS)
+chamfer_bwd_gather_kernel(const float* __restrict__ a, const float* __restrict__ o,
+                          const int* __restrict__ idx_a, const int* __restrict__ idx_o,
+                          const float* __restrict__ g_a, const float* __restrict__ g_o, int g_stride,
+                          int A, int O, float* __restrict__ ga) {
+  extern __shared__ int sh[];
+  int* offs = sh;              // [A + 1] bucket offsets (exclusive scan of the counts)
+  int* cursor = sh + A + 1;    // [A]     counts, then fill cursors
+  int* list = sh + 2 * A + 1;  // [O]     indices of the other cloud, grouped by the point of `a` they map to
+  __shared__ int warp_tot[CH_BWD_THREADS / 32];
+  __shared__ int carry;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const float* __restrict__ ab = a + (size_t)b * A * 3;
+  const float* __restrict__ ob = o + (size_t)b * O * 3;
+  const int* __restrict__ ia = idx_a + (size_t)b * A;
+  const int* __restrict__ io = idx_o + (size_t)b * O;
+  for (int t = tid; t < A; t += CH_BWD_THREADS) cursor[t] = 0;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int i = tid; i < O; i += CH_BWD_THREADS) atomicAdd(&cursor[io[i]], 1);
+  __syncthreads();
+  // exclusive scan of the counts, CH_BWD_THREADS entries per round
+  for (int base = 0; base < A; base += CH_BWD_THREADS) {
+    const int t = base + tid;
+    const int c = t < A ? cursor[t] : 0;
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if ((tid & 31) >= d) incl += v;
+    }
+    if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    int before = carry;
+    for (int w = 0; w < (tid >> 5); ++w) before += warp_tot[w];
+    if (t < A) offs[t] = before + incl - c;
+    __syncthreads();
+    if (tid == CH_BWD_THREADS - 1) carry = before + incl;
+    __syncthreads();
+  }
+  if (tid == 0) offs[A] = carry;
+  for (int t = tid; t < A; t += CH_BWD_THREADS) cursor[t] = 0;
+  __syncthreads();
+  for (int i = tid; i < O; i += CH_BWD_THREADS) {
+    const int j = io[i];
+    list[offs[j] + atomicAdd(&cursor[j], 1)] = i;
+  }
+  __syncthreads();
+  const float sa = 2.f * g_a[(size_t)b * g_stride] / (float)A;
+  const float so = 2.f * g_o[(size_t)b * g_stride] / (float)O;
+  float* __restrict__ gab = ga + (size_t)b * A * 3;
+  for (int t = tid; t < A; t += CH_BWD_THREADS) {
+    const float x = ab[3 * t], y = ab[3 * t + 1], z = ab[3 * t + 2];
+    const int n1 = ia[t];
+    float gx = sa * (x - ob[3 * n1]), gy = sa * (y - ob[3 * n1 + 1]), gz = sa * (z - ob[3 * n1 + 2]);
+    const int lo = offs[t], hi = offs[t + 1];
+    // ascending order of the bucket's indices whatever order the fill left them in (buckets hold ~O/A entries)
+    int prev = -1;
+    for (int e = lo; e < hi; ++e) {
+      int best = 0x7fffffff;
+      for (int f = lo; f < hi; ++f) {
+        const int v = list[f];
+        if (v > prev && v < best) best = v;
+      }
+      prev = best;
+      gx = fmaf(so, x - ob[3 * best], gx);
+      gy = fmaf(so, y - ob[3 * best + 1], gy);
+      gz = fmaf(so, z - ob[3 * best + 2], gz);
+    }
+    gab[3 * t] = gx; gab[3 * t + 1] = gy; gab[3 * t + 2] = gz;
+  }
+}
+
+// Fallback for clouds whose inverse index does not fit in shared memory (> ~18 k points): float atomics.
 // gx / gy must be zero-initialised; gy may be null (targets without grad).
 __global__ void __launch_bounds__(256)
 chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
                    const int* __restrict__ idxx, const int* __restrict__ idxy,
-                   const float* __restrict__ gl1, const float* __restrict__ gl2, int N, int M,
+                   const float* __restrict__ gl1, const float* __restrict__ gl2, int g_stride, int N, int M,
                    float* __restrict__ gx, float* __restrict__ gy) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,7 +209,7 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
   float* gxb = gx + (size_t)b * N * 3;
   float* gyb = gy ? gy + (size_t)b * M * 3 : nullptr;
   if (t < N) {
-    const float s = 2.f * gl1[b] / (float)N;
+    const float s = 2.f * gl1[(size_t)b * g_stride] / (float)N;
     const int i = idxx[(size_t)b * N + t];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -134,7 +219,7 @@ chamfer_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
     }
   }
   if (t < M) {
-    const float s = 2.f * gl2[b] / (float)M;
+    const float s = 2.f * gl2[(size_t)b * g_stride] / (float)M;
     const int j = idxy[(size_t)b * M + t];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -188,17 +273,41 @@ extern "C" int obman_chamfer_fwd(const float* preds, const float* gts, int B, in
   return check_launch("chamfer_mean_kernel");
 }
 
+static int chamfer_bwd_side(const float* a, const float* o, const int* idx_a, const int* idx_o, const float* g_a,
+                            const float* g_o, int g_stride, int B, int A, int O, float* ga, cudaStream_t st) {
+  const size_t smem = sizeof(int) * (size_t)(2 * A + 2 + O);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(chamfer_bwd_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(smem > 48 * 1024 ? smem : 48 * 1024));
+    if (e != cudaSuccess) {
+      set_error("chamfer_bwd: cudaFuncSetAttribute(%zu bytes) failed: %s", smem, cudaGetErrorString(e));
+      return OBMAN_ERR_CUDA;
+    }
+    configured = smem > 48 * 1024 ? smem : 48 * 1024;
+  }
+  chamfer_bwd_gather_kernel<<<B, CH_BWD_THREADS, smem, st>>>(a, o, idx_a, idx_o, g_a, g_o, g_stride, A, O, ga);
+  return check_launch("chamfer_bwd_gather_kernel");
+}
+
 extern "C" int obman_chamfer_bwd(const float* preds, const float* gts, const int* idx1,
-                                 const int* idx2, const float* gloss1, const float* gloss2, int B,
+                                 const int* idx2, const float* gloss1, const float* gloss2, int g_stride, int B,
                                  int N, int M, float* gpreds, float* ggts, void* stream) {
   OBMAN_REQUIRE(B > 0 && N > 0 && M > 0 && B <= 65535, "obman_chamfer_bwd: bad sizes");
   OBMAN_REQUIRE(preds && gts && idx1 && idx2 && gloss1 && gloss2 && gpreds,
                 "obman_chamfer_bwd: null argument");
+  OBMAN_REQUIRE(g_stride == 0 || g_stride == 1, "obman_chamfer_bwd: g_stride must be 0 (one scalar) or 1 (per sample)");
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem_max = 200 * 1024;
+  if (sizeof(int) * (size_t)(2 * N + 2 + M) <= smem_max && sizeof(int) * (size_t)(2 * M + 2 + N) <= smem_max) {
+    int rc = chamfer_bwd_side(preds, gts, idx1, idx2, gloss1, gloss2, g_stride, B, N, M, gpreds, st);
+    if (rc || !ggts) return rc;
+    return chamfer_bwd_side(gts, preds, idx2, idx1, gloss2, gloss1, g_stride, B, M, N, ggts, st);
+  }
   cudaMemsetAsync(gpreds, 0, sizeof(float) * (size_t)B * N * 3, st);
   if (ggts) cudaMemsetAsync(ggts, 0, sizeof(float) * (size_t)B * M * 3, st);
   int n = max(N, M);
   chamfer_bwd_kernel<<<dim3((n + 255) / 256, B), 256, 0, st>>>(preds, gts, idx1, idx2, gloss1,
-                                                               gloss2, N, M, gpreds, ggts);
+                                                               gloss2, g_stride, N, M, gpreds, ggts);
   return check_launch("chamfer_bwd_kernel");
 }

@@ -70,11 +70,20 @@ class _ChamferFn(torch.autograd.Function):
         preds, gts, idx1, idx2 = ctx.saved_tensors
         B, N, _ = preds.shape
         M = gts.shape[1]
-        g1 = _prep(g1, "g1")
-        g2 = _prep(g2, "g2")
+        # the gradient of torch.mean(loss_1 + loss_2) (atlasbranch.py:235,243) and of the device-side loss total
+        # (losshead.combine) arrives as ONE scalar expanded over the batch: pass it as such (g_stride 0) instead of
+        # materialising the (B,) vector
+        if g1.dim() == 1 and g2.dim() == 1 and B > 1 and g1.stride(0) == 0 and g2.stride(0) == 0:
+            g_stride = 0
+        else:
+            g1 = _prep(g1, "g1")
+            g2 = _prep(g2, "g2")
+            g_stride = 1
+        if not (g1.is_cuda and g2.is_cuda and g1.dtype == torch.float32 and g2.dtype == torch.float32):
+            raise RuntimeError("chamfer backward: expected CUDA float32 gradients")
         gpreds = torch.empty_like(preds)
         ggts = torch.empty_like(gts) if ctx.needs_input_grad[1] else None
-        call("obman_chamfer_bwd", ptr(preds), ptr(gts), ptr(idx1), ptr(idx2), ptr(g1), ptr(g2), B, N,
+        call("obman_chamfer_bwd", ptr(preds), ptr(gts), ptr(idx1), ptr(idx2), ptr(g1), ptr(g2), g_stride, B, N,
              M, ptr(gpreds), ptr(ggts), stream_ptr())
         return gpreds, ggts
 

@@ -11,10 +11,9 @@ autograd Function that fails on torch >= 1.5 (Appendix A.17), the one here compu
 import numpy as np
 import torch
 from torch import nn
-import torch.nn.functional as torch_f
 
 from ... import functional as Fb
-from ... import mlp
+from ... import losshead, mlp
 from ...icosphere import icosphere
 from ...queries import TransQueries
 from . import atlasutils
@@ -146,9 +145,25 @@ def edge_loss(edges, faces):
 
 
 class AtlasLoss:
+    """Object-branch loss (atlasbranch.py:170-287): centred and final Chamfer terms, translation / scale regression
+    against the GT centroid and extent, optional edge-length and Laplacian mesh regularisers.
+
+    Device-side: GT statistics are one kernel (losshead.object_targets), the two regression terms one kernel
+    (losshead.sq_terms), every Chamfer / regulariser term comes from its own fused kernel, and the weighted total is
+    one kernel (losshead.combine) that reads the lambdas from a device vector - so ``HandNet.decay_regul``
+    (handnet.py:188-196) takes effect inside a captured CUDA graph.  The lambda attributes stay plain Python numbers
+    (``decay_regul`` rescales them from outside); they are mirrored into the device vector at every call."""
+
+    _WEIGHTS = ("lambda_atlas", "final_lambda_atlas", "trans_weight", "scale_weight", "edge_regul_lambda",
+                "lambda_laplacian")
+
     def __init__(self, lambda_atlas=1, atlas_loss="chamfer", final_lambda_atlas=1, trans_weight=0,
                  scale_weight=0, edge_regul_lambda=None, lambda_laplacian=0, laplacian_faces=None,
                  laplacian_verts=None):
+        if atlas_loss != "chamfer":
+            raise ValueError("Removed support for earth mover distance !")   # the reference's message (atlasbranch.py:197)
+        self.atlas_loss = atlas_loss
+        self.chamfer_loss = atlasutils.ChamferLoss()
         self.lambda_atlas = lambda_atlas
         self.final_lambda_atlas = final_lambda_atlas
         self.trans_weight = trans_weight
@@ -156,56 +171,70 @@ class AtlasLoss:
         self.edge_regul_lambda = edge_regul_lambda
         self.lambda_laplacian = lambda_laplacian
         if lambda_laplacian:
-            # atlasbranch.py:189-192; the reference's own class is a legacy autograd Function that fails on
-            # torch >= 1.5 - this one computes the same loss on the device
+            # the reference's own class is a legacy autograd Function that fails on torch >= 1.5 (SURVEY.md
+            # Appendix A.17); this one computes the same loss on the device
             from .laplacianloss import LaplacianLoss
             self.laplacian_loss = LaplacianLoss(laplacian_faces, laplacian_verts)
-        self.atlas_loss = atlas_loss
-        if self.atlas_loss == "chamfer":
-            self.chamfer_loss = atlasutils.ChamferLoss()
-        else:
-            raise ValueError("Removed support for earth mover distance !")
+        self._weights = losshead.LossWeights(self._WEIGHTS + ("one",))
+        self._weights["one"] = 1.0
+        self._scratch = losshead._Workspace()
+
+    def sync_weights(self):
+        """Mirror the lambda attributes into the device vector (a fill kernel per CHANGED value)."""
+        for name in self._WEIGHTS:
+            self._weights[name] = getattr(self, name)
+
+    def _chamfer_term(self, pred_points, gt_points, weight_name):
+        """Symmetric Chamfer distance as a combine term: mean_b(loss_1 + loss_2) = (sum loss_1 + sum loss_2) / B.
+        A weight that is zero (the README recipe leaves --atlas_lambda at 0) still gets its
+        forward value logged but is cut off from the backward pass."""
+        loss_1, loss_2 = self.chamfer_loss(pred_points, gt_points)
+        if not self._weights[weight_name]:
+            loss_1, loss_2 = loss_1.detach(), loss_2.detach()
+        return ((loss_1, loss_2), 1.0 / loss_1.shape[0], self._weights.slot[weight_name], 0)
 
     def compute_loss(self, preds, target):
-        atlas_losses = {}
-        if (TransQueries.objpoints3d in target and (self.lambda_atlas or self.final_lambda_atlas)) or (
-                TransQueries.center3d in target and self.trans_weight):
-            gt = target[TransQueries.objpoints3d]
-            if "objtrans" in preds and TransQueries.objpoints3d in target and ("objpointscentered3d" in preds):
-                obj_centroids = gt.mean(1)
-                trans3d_loss = torch_f.mse_loss(preds["objtrans"], obj_centroids)
-                atlas_losses["atlas_trans3d"] = trans3d_loss
-                centered_objpoints3d = gt - obj_centroids.unsqueeze(1)
-                if "objscale" in preds:
-                    obj_scales = torch.norm(centered_objpoints3d, 2, 2).max(1)[0]
-                    scale3d_loss = torch_f.mse_loss(preds["objscale"], obj_scales.unsqueeze(1))
-                    atlas_losses["atlas_scale3d"] = scale3d_loss
-                else:
-                    scale3d_loss = 0
-                loss_1, loss_2 = self.chamfer_loss(preds["objpointscentered3d"], centered_objpoints3d)
-                sym_loss = torch.mean(loss_1 + loss_2)
-                obj_mesh = preds["objpointscentered3d"]
-                final_loss_1, final_loss_2 = self.chamfer_loss(preds["objpoints3d"], gt)
-                sym_final_loss = torch.mean(final_loss_1 + final_loss_2)
-                atlas_losses["final_{}_loss".format(self.atlas_loss)] = sym_final_loss
-                final_loss = (self.lambda_atlas * sym_loss + self.final_lambda_atlas * sym_final_loss
-                              + self.trans_weight * trans3d_loss + self.scale_weight * scale3d_loss)
-            else:
-                if "objpoints3d" in preds and self.lambda_atlas:
-                    loss_1, loss_2 = self.chamfer_loss(preds["objpoints3d"], gt)
-                    sym_loss = torch.mean((loss_1 + loss_2))
-                    final_loss = self.lambda_atlas * sym_loss
-                    obj_mesh = preds["objpoints3d"]
-            if self.edge_regul_lambda is not None and (self.edge_regul_lambda > 0):
-                edge_regul_loss = edge_loss(obj_mesh, preds["objfaces"])
-                atlas_losses["atlas_edge_regul"] = edge_regul_loss
-                final_loss = final_loss + self.edge_regul_lambda * edge_regul_loss
-            if self.lambda_laplacian:  # atlasbranch.py:275-280
-                laplacian_loss = self.laplacian_loss(obj_mesh)
-                atlas_losses["atlas_laplac"] = laplacian_loss
-                final_loss = final_loss + self.lambda_laplacian * laplacian_loss
-        else:
-            sym_loss = None
-            final_loss = torch.zeros(1, device="cuda")
-        atlas_losses["atlas_objpoints3d"] = sym_loss
-        return final_loss, atlas_losses
+        report = {"atlas_objpoints3d": None}
+        has_points = TransQueries.objpoints3d in target
+        if not ((has_points and (self.lambda_atlas or self.final_lambda_atlas))
+                or (TransQueries.center3d in target and self.trans_weight)):
+            return torch.zeros(1, device="cuda"), report
+        self.sync_weights()
+        gt = target[TransQueries.objpoints3d]
+        weights = self._weights.device(gt.device)
+        slot = self._weights.slot
+        terms, logged = [], []   # combine terms; (report key, index of the term whose value is logged)
+        mesh = None
+        if has_points and "objtrans" in preds and "objpointscentered3d" in preds:
+            # regression targets from the GT cloud: centroid, extent, centred copy (atlasbranch.py:211-227)
+            centroid, extent, centred_gt = losshead.object_targets(gt)
+            heads = [(preds["objtrans"], centroid, None, slot["trans_weight"])]
+            if "objscale" in preds:
+                heads.append((preds["objscale"], extent, None, slot["scale_weight"]))
+            head_sum, head_vals = losshead.sq_terms(heads, weights, self._scratch)
+            report["atlas_trans3d"] = head_vals[0:1]
+            if "objscale" in preds:
+                report["atlas_scale3d"] = head_vals[1:2]
+            terms.append((head_sum, 1.0, slot["one"], 0))
+            mesh = preds["objpointscentered3d"]
+            logged.append(("atlas_objpoints3d", len(terms)))
+            terms.append(self._chamfer_term(mesh, centred_gt, "lambda_atlas"))
+            logged.append(("final_{}_loss".format(self.atlas_loss), len(terms)))
+            terms.append(self._chamfer_term(preds["objpoints3d"], gt, "final_lambda_atlas"))
+        elif "objpoints3d" in preds and self.lambda_atlas:
+            mesh = preds["objpoints3d"]
+            logged.append(("atlas_objpoints3d", len(terms)))
+            terms.append(self._chamfer_term(mesh, gt, "lambda_atlas"))
+        if mesh is None:
+            raise RuntimeError("AtlasLoss.compute_loss: nothing to supervise (predictions lack 'objpoints3d' / "
+                               "'objtrans' + 'objpointscentered3d' for the configured weights)")
+        if self.edge_regul_lambda is not None and self.edge_regul_lambda > 0:
+            logged.append(("atlas_edge_regul", len(terms)))
+            terms.append((edge_loss(mesh, preds["objfaces"]), 1.0, slot["edge_regul_lambda"], 0))
+        if self.lambda_laplacian:
+            logged.append(("atlas_laplac", len(terms)))
+            terms.append((self.laplacian_loss(mesh), 1.0, slot["lambda_laplacian"], 0))
+        final_loss, _, values = losshead.combine(terms, weights)
+        for key, k in logged:
+            report[key] = values[k:k + 1]
+        return final_loss, report

@@ -8,9 +8,7 @@ projection), use_trans, adapt_skeleton, dropout, normalize_hand, PCA supervision
 """
 import torch
 from torch import nn
-import torch.nn.functional as torch_f
-
-from ... import mlp
+from ... import losshead, mlp
 from ...manopth.manolayer import ManoLayer
 from ...queries import TransQueries, BaseQueries
 
@@ -140,6 +138,17 @@ class ManoBranch(nn.Module):
 
 
 class ManoLoss:
+    """Weighted sum of the MANO supervision terms (manobranch.py:229-324): vertices, 3-D joints, shape and pose
+    regularisers, optional PCA supervision - every active term in ONE fused kernel launch (losshead.sq_terms) whose
+    weights are read from device memory.  ``compute_loss(preds, target) -> (final_loss (1,), mano_losses)`` with the
+    reference's keys: "mano_verts3d", "mano_shape", "mano_pca" are always reported (None when off), "mano_joints3d"
+    and "pose_reg" only when on, plus "mano_total_loss"."""
+
+    # (attribute holding the weight, logged key, always reported?)
+    _TERMS = (("lambda_verts", "mano_verts3d", True), ("lambda_joints3d", "mano_joints3d", False),
+              ("lambda_shape", "mano_shape", True), ("lambda_pose_reg", "pose_reg", False),
+              ("lambda_pca", "mano_pca", True))
+
     def __init__(self, lambda_verts=None, lambda_joints3d=None, lambda_shape=None, lambda_pose_reg=None,
                  lambda_pca=None, center_idx=9, normalize_hand=False):
         self.lambda_verts = lambda_verts
@@ -149,35 +158,39 @@ class ManoLoss:
         self.lambda_pca = lambda_pca
         self.center_idx = center_idx
         self.normalize_hand = normalize_hand
+        self._weights = losshead.LossWeights([attr for attr, _, _ in self._TERMS])
+        self._scratch = losshead._Workspace()
+
+    def _active(self, preds, target):
+        """(weight attribute, prediction, target or None, column range or None) of every term that is switched on."""
+        out = []
+        if TransQueries.verts3d in target and self.lambda_verts:
+            out.append(("lambda_verts", preds["verts"], target[TransQueries.verts3d], None))
+        if TransQueries.joints3d in target and self.lambda_joints3d:
+            out.append(("lambda_joints3d", preds["joints"], target[TransQueries.joints3d], None))
+        if self.lambda_shape:
+            out.append(("lambda_shape", preds["shape"], None, None))
+        if self.lambda_pose_reg:
+            # the three global-rotation coefficients are not regularised (manobranch.py:307-312)
+            out.append(("lambda_pose_reg", preds["pose"], None, (3, preds["pose"].shape[1])))
+        if BaseQueries.hand_pcas in target and self.lambda_pca:
+            out.append(("lambda_pca", preds["pcas"], target[BaseQueries.hand_pcas], None))
+        return out
 
     def compute_loss(self, preds, target):
-        final_loss = torch.zeros(1, device=preds["pose"].device)
-        mano_losses = {}
-        if TransQueries.verts3d in target and self.lambda_verts:
-            verts3d_loss = torch_f.mse_loss(preds["verts"], target[TransQueries.verts3d])
-            final_loss = final_loss + self.lambda_verts * verts3d_loss
+        dev = preds["pose"].device
+        for attr, _, _ in self._TERMS:
+            self._weights[attr] = getattr(self, attr)
+        mano_losses = {key: None for _, key, always in self._TERMS if always}
+        active = self._active(preds, target)
+        if active:
+            final_loss, values = losshead.sq_terms(
+                [(pred, tgt, cols, self._weights.slot[attr]) for attr, pred, tgt, cols in active],
+                self._weights.device(dev), self._scratch)
+            key_of = {attr: key for attr, key, _ in self._TERMS}
+            for k, (attr, _, _, _) in enumerate(active):
+                mano_losses[key_of[attr]] = values[k:k + 1]
         else:
-            verts3d_loss = None
-        mano_losses["mano_verts3d"] = verts3d_loss
-        if TransQueries.joints3d in target and self.lambda_joints3d:
-            joints3d_loss = torch_f.mse_loss(preds["joints"], target[TransQueries.joints3d])
-            final_loss = final_loss + self.lambda_joints3d * joints3d_loss
-            mano_losses["mano_joints3d"] = joints3d_loss
-        if self.lambda_shape:
-            shape_loss = torch_f.mse_loss(preds["shape"], torch.zeros_like(preds["shape"]))
-            final_loss = final_loss + self.lambda_shape * shape_loss
-        else:
-            shape_loss = None
-        mano_losses["mano_shape"] = shape_loss
-        if self.lambda_pose_reg:
-            pose_reg_loss = torch_f.mse_loss(preds["pose"][:, 3:], torch.zeros_like(preds["pose"][:, 3:]))
-            final_loss = final_loss + self.lambda_pose_reg * pose_reg_loss
-            mano_losses["pose_reg"] = pose_reg_loss
-        if BaseQueries.hand_pcas in target and self.lambda_pca:
-            pca_loss = torch_f.mse_loss(preds["pcas"], target[BaseQueries.hand_pcas])
-            final_loss = final_loss + self.lambda_pca * pca_loss
-        else:
-            pca_loss = None
-        mano_losses["mano_pca"] = pca_loss
+            final_loss = torch.zeros(1, device=dev)
         mano_losses["mano_total_loss"] = final_loss
         return final_loss, mano_losses

@@ -85,6 +85,24 @@ def test_handnet_shared_encoder_ico3_no_contact():
     _check(*_run(cfg, B=2, H=64, seed=10, sides=["right", "right"]))
 
 
+def test_handnet_full_size_256_shared_encoder_ico3_matches_oracle():
+    """BASELINE configs[1] at its real image size (256x256: the 128x128 stem and 64x64 layer-1 tile shapes of the
+    benchmark), B=2, ico-3, against the fp64 oracle - no ReLU-mask / arg-max injection anywhere.  With ~10^5 pixels per
+    channel a handful of ReLU branch flips no longer dominates a weight gradient, hence the tighter norm-wise bound."""
+    cfg = dict(FULL_CFG)
+    cfg.update(atlas_separate_encoder=False, atlas_ico_divisions=3, contact_lambda=0, collision_lambda=0,
+               atlas_lambda_regul_edges=0)
+    _check(*_run(cfg, B=2, H=256, seed=30), grad_rtol=1e-2)
+
+
+def test_handnet_full_size_256_separate_encoder_ico4_contact_matches_oracle():
+    """BASELINE configs[2]'s graph at its real sizes (256x256 images, two encoders, ico-4 = 2562 vertices / 5120 faces,
+    2500 GT points, contact_zones loss), B=2, against the fp64 oracle."""
+    cfg = dict(FULL_CFG)
+    cfg.update(atlas_ico_divisions=4, atlas_lambda_regul_edges=0)
+    _check(*_run(cfg, B=2, H=256, seed=40, n_gt=2500), grad_rtol=1e-2)
+
+
 def test_handnet_with_laplacian_regulariser():
     """atlas_lambda_laplacian > 0 (atlasbranch.py:275-280): the reference's own class no longer runs on torch >= 1.5;
     the oracle restatement is pinned against its numerical body (tests/test_mesh_regul.py)."""

@@ -245,9 +245,11 @@ int obman_loss_combine_bwd(const int* slot, const float* scale, int n_terms, con
 
 /* Fused torch.optim.Adam step (traineval.py:113-116) on flat fp32 buffers (16-byte aligned); g is multiplied by
  * grad_scale.  hyper_dev: device float[2] = {1-based step number, learning-rate multiplier} - device memory so that a
- * captured CUDA graph keeps exact bias corrections and follows StepLR (traineval.py:179-182): lr_eff = lr * hyper_dev[1]. */
-int obman_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
-                    float beta2, float eps, float weight_decay, const float* hyper_dev, float grad_scale,
+ * captured CUDA graph keeps exact bias corrections and follows StepLR (traineval.py:179-182): lr_eff = lr * hyper_dev[1].
+ * The scalar hyper-parameters are doubles: 1 - beta, lr / (1 - beta1^t) and sqrt(1 - beta2^t) are formed in double and
+ * rounded to fp32 once, as torch.optim.Adam does (tests/test_gpu_adam.py: elementwise parity with torch). */
+int obman_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1,
+                    double beta2, double eps, double weight_decay, const float* hyper_dev, double grad_scale,
                     void* stream);
 
 #ifdef __cplusplus

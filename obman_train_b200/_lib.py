@@ -31,6 +31,8 @@ def parse_header(path=HEADER_PATH):
                     argtypes.append(ctypes.c_void_p)
                 elif a.startswith("float "):
                     argtypes.append(ctypes.c_float)
+                elif a.startswith("double "):
+                    argtypes.append(ctypes.c_double)
                 elif a.startswith("long long "):
                     argtypes.append(ctypes.c_longlong)
                 elif a.startswith("int "):

@@ -1,0 +1,343 @@
+// Persistent tcgen05 convolution kernel for the 64-output-channel layers of ResNet-18 (the 7x7/2 stem in its
+// 4-tap space-to-depth form and the four 3x3 convolutions of layer1, fprop and dgrad;
+// mano_train/networks/bases/resnet.py:25-54,154-171).  These layers were the furthest from the tensor-core roofline
+// (27-44 % pipe, 24-30 % of a step's tensor time): N = 64 MMAs issue at 54 % of the N >= 128 rate, the A tile was
+// re-fetched from L2 once per tap (operand delivery ~53 B/clk/SM, the fabric limit), and a 128-pixel tile spends 38 %
+// of its CTA lifetime in prologue and epilogue.  This kernel removes all three:
+//   * ONE CTA per SM loops over output tiles (static round-robin): barrier init, TMEM allocation and the weight fetch
+//     happen once per CTA, not once per tile;
+//   * the WHOLE packed weight matrix (<= 18 (tap, K-block) tiles of 8 KB) stays resident in shared memory, landed in the
+//     stacked layout (rows 0-63 = bf16 hi, rows 64-127 = bf16 lo of the same K block), so one N = 128 MMA yields
+//     a_hi*b_hi | a_hi*b_lo at the full rate and one N = 64 MMA adds a_lo*b_hi: 124 instead of 180 cycles per K = 16;
+//   * the input arrives as ONE halo box per 32 input channels (TMA, zero fill at image borders); the splitter warps
+//     convert it IN PLACE to bf16 hi | lo once, then every tap is a shifted row read + tcgen05.st into a ring of A
+//     stages in tensor memory: input bytes per tile drop ~6x, the per-tap work of a splitter thread is 8 LDS + 2 STTM;
+//   * the accumulator is double-buffered in tensor memory (2 x 128 columns) and drained by eight dedicated epilogue warps
+//     (bias / BN shift, residual add, ReLU, ReLU-mask, coalesced stores through a shared-memory transpose) while the MMA
+//     warp is already working on the next tile.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, then NS sets of four splitter warps, then eight epilogue warps (two per
+// TMEM lane quadrant, 32 output channels each).  Tensor memory: columns 0-255 accumulators, 256-511 eight A stages of 32 columns.
+#include <stdlib.h>
+
+#include "gemm_shared.cuh"
+
+namespace obman {
+
+constexpr int P64_HALO_BYTES = 25600;   // up to 200 halo pixels x 32 channels fp32 (multiple of 1024: swizzle phase)
+constexpr int P64_RA = 2;               // halo boxes in flight
+constexpr int P64_WT_TILE = 8192;       // 128 rows (64 hi + 64 lo) x 64 B
+constexpr int P64_MAX_WT = 18;          // (tap, K-block) weight tiles resident in shared memory
+constexpr int P64_C = 8;                // A stages in tensor memory
+constexpr int P64_STAGING = 16384;      // 8 epilogue warps x 32 rows x 64 B
+template <int NS, int EW> struct P64Threads { static constexpr int value = 32 * (2 + 4 * NS + EW); };
+constexpr int P64_SMEM = P64_MAX_WT * P64_WT_TILE + P64_RA * P64_HALO_BYTES + P64_STAGING + 1024 /*align*/ + 512;
+
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__device__ __forceinline__ void tile_coords(const GemmProgram& prog, int tile, int& n_img0, int& h0, int& w0) {
+  const int tw_i = tile % prog.tiles_w; tile /= prog.tiles_w;
+  const int th_i = tile % prog.tiles_h; tile /= prog.tiles_h;
+  n_img0 = tile * prog.TN;
+  h0 = th_i * prog.TH;
+  w0 = tw_i * prog.TW;
+}
+
+// NS = sets of four splitter warps; iteration gi (= one tap of one K block) belongs to set gi % NS, so NS tcgen05.st
+// round trips are in flight per TMEM lane quadrant (one set alone is latency bound: LDS -> STTM -> wait::st -> arrive).
+// EW = epilogue warps: 8 (two per TMEM lane quadrant, 32 output channels each) or 4 (64 channels each).
+template <int NS, int EW>
+__global__ void __launch_bounds__(P64Threads<NS, EW>::value, 1)
+conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, const GemmEpilogue epi,
+                         int total_tiles) {
+  constexpr int RA = P64_RA, C = P64_C;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wt = smem;
+  uint8_t* halo_base = smem + P64_MAX_WT * P64_WT_TILE;
+  uint8_t* staging = halo_base + RA * P64_HALO_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + P64_STAGING);
+  uint64_t* wfull = bars;                    // weights landed
+  uint64_t* afull = bars + 1;                // [RA] halo box landed
+  uint64_t* afree = afull + RA;              // [RA] splitter warps are done with the halo box
+  uint64_t* conv = afree + RA;               // [C]  A stage written to tensor memory
+  uint64_t* empty = conv + C;                // [C]  MMAs reading the A stage retired
+  uint64_t* accfull = empty + C;             // [2]  accumulator of a tile complete
+  uint64_t* accfree = accfull + 2;           // [2]  epilogue warps have drained the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfree + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
+  const int lane = threadIdx.x & 31;
+  const int T = prog.num_taps, KB = prog.kblocks;
+  const int n_iters = T * KB;
+
+  if (threadIdx.x == 0) {
+    mbar_init(wfull, 1);
+    for (int i = 0; i < RA; ++i) { mbar_init(&afull[i], 1); mbar_init(&afree[i], 128 * NS); }
+    for (int i = 0; i < C; ++i) { mbar_init(&conv[i], 128); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&accfull[i], 1); mbar_init(&accfree[i], 32 * EW); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  auto halo = [&](int i) { return halo_base + i * P64_HALO_BYTES; };
+
+  if (warp == 0) {
+    // ===== TMA producer: the weights once, then one halo box per (tile, K block) =====
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.a[0]);
+      tma_prefetch_desc(&maps.b);
+      mbar_arrive_expect_tx(wfull, (uint32_t)n_iters * P64_WT_TILE);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int tap = 0; tap < T; ++tap) {
+          uint8_t* dst = wt + (kb * T + tap) * P64_WT_TILE;
+          const int kc = prog.tap_bk[tap] + kb * BK;
+          tma_load_2d(dst, &maps.b, wfull, kc, 0);             // 64 rows x 64 B of bf16 hi
+          tma_load_2d(dst + 4096, &maps.b, wfull, kc + 16, 0); // 64 rows x 64 B of bf16 lo
+        }
+      int g = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n_img0, h0, w0;
+        tile_coords(prog, tile, n_img0, h0, w0);
+        for (int kb = 0; kb < KB; ++kb, ++g) {
+          const int a = g % RA;
+          mbar_wait(&afree[a], ((g / RA) & 1) ^ 1);
+          mbar_arrive_expect_tx(&afull[a], (uint32_t)prog.halo_bytes);
+          tma_load_4d(halo(a), &maps.a[0], &afull[a], kb * BK, w0 + prog.halo_dw0, h0 + prog.halo_dh0, n_img0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = umma_idesc_bf16(BM, 64);
+    const uint32_t idesc_wide = umma_idesc_bf16(BM, 128);
+    mbar_wait(wfull, 0);
+    int gi = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int acc = ti & 1;
+      mbar_wait(&accfree[acc], ((ti >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(acc * 128);
+      for (int it = 0; it < n_iters; ++it, ++gi) {
+        const int c = gi % C;
+        mbar_wait(&conv[c], (gi / C) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t b = smem_u32(wt + it * P64_WT_TILE);
+          const uint32_t ta = tmem_base + (uint32_t)(256 + 32 * c);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint64_t db = umma_desc(b + k * 32, 16, 512, 4);   // 128 rows x 64 B, SW64: 8-row groups 512 B apart
+            umma_f16_ts(d, ta + k * 8, db, idesc_wide, (it > 0 || k > 0) ? 1u : 0u);   // [a_hi*b_hi | a_hi*b_lo]
+            umma_f16_ts(d, ta + 16 + k * 8, db, idesc, 1u);                             // columns 0-63 += a_lo*b_hi
+          }
+          umma_commit(&empty[c]);
+          if (it == n_iters - 1) umma_commit(&accfull[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 2 + 4 * NS) {
+    // ===== splitters: halo box -> bf16 hi | lo in place, then one shifted row per tap -> tensor memory =====
+    const int q = warp & 3;
+    const int set = (warp - 2) >> 2;
+    const int r = q * 32 + lane;                 // tile row == TMEM lane
+    const int sid = threadIdx.x - 64;            // 0 .. 128 NS - 1
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int tw = r % prog.TW, th = (r / prog.TW) % prog.TH, tn = r / (prog.TW * prog.TH);
+    const int hp0 = (tn * prog.halo_h + th) * prog.halo_w + tw;
+    // the packed row of halo pixel hp: 16 words of bf16 hi pairs (chunks 0-3), 16 words of lo pairs (chunks 4-7)
+    auto load_row = [&](uint32_t box, int hp, uint32_t* hi, uint32_t* lo) {
+      const uint32_t row = box + (uint32_t)hp * 128u;
+      const int sw = hp & 7;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 h4 = lds_v4(row + ((j ^ sw) << 4));
+        const float4 l4 = lds_v4(row + (((j + 4) ^ sw) << 4));
+        hi[4 * j] = __float_as_uint(h4.x); hi[4 * j + 1] = __float_as_uint(h4.y);
+        hi[4 * j + 2] = __float_as_uint(h4.z); hi[4 * j + 3] = __float_as_uint(h4.w);
+        lo[4 * j] = __float_as_uint(l4.x); lo[4 * j + 1] = __float_as_uint(l4.y);
+        lo[4 * j + 2] = __float_as_uint(l4.z); lo[4 * j + 3] = __float_as_uint(l4.w);
+      }
+    };
+    int g = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < KB; ++kb, ++g) {
+        const int a = g % RA;
+        mbar_wait(&afull[a], (g / RA) & 1);
+        const uint32_t box = smem_u32(halo(a));
+        for (int p = sid; p < prog.halo_pix; p += 128 * NS) {
+          const uint32_t row = box + (uint32_t)p * 128u;
+          const int sw = p & 7;
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = lds_v4(row + ((j ^ sw) << 4));
+            split_bf16x2(v.x, v.y, hi[2 * j], lo[2 * j]);
+            split_bf16x2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sts_v4(row + ((j ^ sw) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            sts_v4(row + (((j + 4) ^ sw) << 4), lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+        }
+        named_barrier_sync(1, 128 * NS);   // every pixel of the box is converted before any tap row is read
+        const int gi0 = g * T;             // iteration index of tap 0 of this box
+        int tap = (set - gi0 % NS + NS) % NS;   // first tap of this box that belongs to this set
+        uint32_t hi[16], lo[16];
+        if (tap < T) load_row(box, hp0 + prog.tap_delta[tap], hi, lo);
+        for (; tap < T; tap += NS) {
+          const int gi = gi0 + tap;
+          const int c = gi % C;
+          mbar_wait(&empty[c], ((gi / C) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t dst = lane_base + (uint32_t)(256 + 32 * c);
+          tmem_st_32x16(dst, hi);
+          tmem_st_32x16(dst + 16, lo);
+          // the next row's shared-memory reads are issued underneath the tensor-memory store round trip
+          uint32_t nhi[16], nlo[16];
+          const bool more = tap + NS < T;
+          if (more) load_row(box, hp0 + prog.tap_delta[tap + NS], nhi, nlo);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&conv[c]);
+          if (more) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { hi[j] = nhi[j]; lo[j] = nlo[j]; }
+          }
+        }
+        fence_proxy_async_smem();   // the box was rewritten through the generic proxy; the next TMA write follows it
+        mbar_arrive(&afree[a]);
+      }
+    }
+  } else {
+    // ===== epilogue: the last EW warps, TMEM lane quadrant = warp % 4, 64 * 4 / EW output channels per warp =====
+    constexpr int COLS = 64 * 4 / EW;
+    const int q = warp & 3;
+    const int part = (warp - (2 + 4 * NS)) >> 2;
+    const int r = q * 32 + lane;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      int n_img0, h0, w0;
+      tile_coords(prog, tile, n_img0, h0, w0);
+      const int acc = ti & 1;
+      gemm_epilogue_stacked<64>(staging + part * 8192, tmem_base + (uint32_t)(acc * 128), &accfull[acc], prog, epi, 0, 0,
+                                n_img0, h0, w0, q, lane, r, (uint32_t)((ti >> 1) & 1), part * COLS, part * COLS + COLS);
+      tc_fence_before();
+      mbar_arrive(&accfree[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static bool conv64_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OBMAN_CONV64");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// Returns 1 when the convolution was launched on the persistent kernel, 0 when the shape does not qualify (the caller
+// then takes the generic shifted-box path), a negative error code on failure.
+int try_conv64(const float* x, int n_img, int h_in, int w_in, int c_in, long long x_sN, long long x_sH, long long x_sW,
+               const float* w, int c_out, int w_slots, int num_taps, const int* tap_dh, const int* tap_dw,
+               const int* tap_wslot, float* out, int h_out, int w_out, long long o_sN, long long o_sH, long long o_sW,
+               const float* bias, const float* addend, const float* mask_src, int relu, cudaStream_t st) {
+  if (!conv64_enabled()) return 0;
+  if (c_out > 64 || c_out % 4 != 0 || c_in % 32 != 0 || w_out < 8 || h_out < 1) return 0;
+  const int KB = c_in / 32;
+  if (num_taps * KB > P64_MAX_WT) return 0;
+  int dh0 = tap_dh[0], dh1 = tap_dh[0], dw0 = tap_dw[0], dw1 = tap_dw[0];
+  for (int t = 1; t < num_taps; ++t) {
+    dh0 = min(dh0, tap_dh[t]); dh1 = max(dh1, tap_dh[t]);
+    dw0 = min(dw0, tap_dw[t]); dw1 = max(dw1, tap_dw[t]);
+  }
+  int TW = 1;
+  while (TW * 2 <= w_out && TW * 2 <= 16) TW *= 2;
+  int TH = 1;
+  while (TH * 2 <= h_out && TW * TH * 2 <= 128) TH *= 2;
+  const int TN = 128 / (TW * TH);
+  const int HW = TW + dw1 - dw0, HH = TH + dh1 - dh0;
+  const int halo_pix = HW * HH * TN;
+  if (halo_pix * 128 > P64_HALO_BYTES || HW > 256 || HH > 256 || TN > 256) return 0;
+  GemmProgram prog;
+  memset(&prog, 0, sizeof(prog));
+  prog.spatial = 1;
+  prog.num_taps = num_taps;
+  prog.kblocks = KB;
+  prog.N = c_out;
+  prog.TN = TN; prog.TH = TH; prog.TW = TW;
+  prog.tiles_h = (h_out + TH - 1) / TH;
+  prog.tiles_w = (w_out + TW - 1) / TW;
+  prog.n_img = n_img; prog.h_out = h_out; prog.w_out = w_out;
+  prog.halo_w = HW; prog.halo_h = HH; prog.halo_dw0 = dw0; prog.halo_dh0 = dh0; prog.halo_pix = halo_pix;
+  prog.halo_bytes = halo_pix * 128;
+  for (int t = 0; t < num_taps; ++t) {
+    prog.tap_bk[t] = (tap_wslot ? tap_wslot[t] : t) * c_in;
+    prog.tap_delta[t] = (tap_dh[t] - dh0) * HW + (tap_dw[t] - dw0);
+  }
+  const long long total = (long long)((n_img + TN - 1) / TN) * prog.tiles_h * prog.tiles_w;
+  if (total > 0x7fffffff) return 0;
+  GemmMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  {
+    uint64_t dims[4] = {(uint64_t)c_in, (uint64_t)w_in, (uint64_t)h_in, (uint64_t)n_img};
+    uint64_t strides[3] = {(uint64_t)x_sW * 4, (uint64_t)x_sH * 4, (uint64_t)x_sN * 4};
+    uint32_t box[4] = {BK, (uint32_t)HW, (uint32_t)HH, (uint32_t)TN};
+    int rc = make_tensor_map(&maps.a[0], x, 4, dims, strides, box);
+    if (rc) return rc;
+    uint64_t dimsb[2] = {(uint64_t)w_slots * (uint64_t)c_in, (uint64_t)c_out};
+    uint64_t stridesb[1] = {dimsb[0] * 4};
+    uint32_t boxb[2] = {16, 64};   // 64-byte-wide boxes: the hi half and the lo half of a packed K block separately
+    rc = make_tensor_map(&maps.b, w, 2, dimsb, stridesb, boxb, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  GemmEpilogue epi;
+  memset(&epi, 0, sizeof(epi));
+  epi.out = out; epi.bias = bias; epi.addend = addend; epi.mask_src = mask_src;
+  epi.alpha = 1.f; epi.relu = relu; epi.accumulate = 0;
+  epi.sN = o_sN; epi.sH = o_sH; epi.sW = o_sW;
+  // OBMAN_CONV64_CFG = <splitter sets><epilogue warps>: 18, 24, 28 (default), 34
+  static int cfg = -1;
+  const int grid = (int)min((long long)num_sms(), total);
+#define OBMAN_P64_CASE(id, NS, EW)                                                                                    \
+  if (cfg == id) {                                                                                                    \
+    static bool attr = false;                                                                                         \
+    if (!attr) {                                                                                                      \
+      cudaError_t err = cudaFuncSetAttribute(conv64_persistent_kernel<NS, EW>,                                        \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, P64_SMEM);                  \
+      if (err != cudaSuccess) {                                                                                       \
+        set_error("conv64: cudaFuncSetAttribute(%d bytes) failed: %s", P64_SMEM, cudaGetErrorString(err));            \
+        return OBMAN_ERR_CUDA;                                                                                        \
+      }                                                                                                               \
+      attr = true;                                                                                                    \
+    }                                                                                                                 \
+    conv64_persistent_kernel<NS, EW><<<grid, P64Threads<NS, EW>::value, P64_SMEM, st>>>(maps, prog, epi, (int)total); \
+  }
+  if (cfg < 0) {
+    const char* e = getenv("OBMAN_CONV64_CFG");
+    cfg = e ? atoi(e) : 28;
+    if (cfg != 18 && cfg != 24 && cfg != 28 && cfg != 34) cfg = 28;
+  }
+  OBMAN_P64_CASE(18, 1, 8)
+  OBMAN_P64_CASE(24, 2, 4)
+  OBMAN_P64_CASE(28, 2, 8)
+  OBMAN_P64_CASE(34, 3, 4)
+#undef OBMAN_P64_CASE
+  int rc = check_launch("conv64_persistent_kernel");
+  return rc ? rc : 1;
+}
+
+}  // namespace obman

@@ -329,41 +329,53 @@ bn_wgrad_finish_kernel(const float* __restrict__ dwraw, long long dw_ld, const f
 // torch.optim.Adam (no amsgrad, no weight decay unless wd != 0), bias-corrected, on flat buffers.
 // hyper_dev = {1-based step number, learning-rate multiplier}: both live in device memory so that a captured CUDA
 // graph applies the right bias correction and follows an lr schedule (StepLR, traineval.py:179-182) without re-capture.
-__device__ __forceinline__ void adam_one(float& pv, float gv, float& mv, float& vv, float lr_bc1, float beta1,
-                                         float beta2, float eps, float wd, float bc2_sqrt, float gscale) {
+// One element of torch.optim.Adam's update, operation for operation as torch's kernels evaluate it in fp32:
+//   grad = g * gscale (+ wd * p);  m = lerp(m, grad, 1 - beta1);  v = beta2 * v + (1 - beta2) * grad^2;
+//   p -= step_size * m / (sqrt(v) / sqrt(bias_correction2) + eps)
+// with the scalars (1 - beta, step_size = lr / bias_correction1, sqrt(bias_correction2)) formed in DOUBLE and rounded to
+// fp32 once, as Python does for torch (1.f - 0.999f would already be off by 1.3e-5 relative).
+__device__ __forceinline__ void adam_one(float& pv, float gv, float& mv, float& vv, float step_size, float omb1,
+                                         float beta2, float omb2, float eps, float wd, float bc2_sqrt, float gscale) {
   float grad = gv * gscale;
   if (wd != 0.f) grad = fmaf(wd, pv, grad);
-  mv = beta1 * mv + (1.f - beta1) * grad;
-  vv = beta2 * vv + (1.f - beta2) * grad * grad;
+  mv = fmaf(omb1, grad - mv, mv);
+  vv = fmaf(omb2 * grad, grad, beta2 * vv);
   const float denom = sqrtf(vv) / bc2_sqrt + eps;
-  pv = pv - lr_bc1 * (mv / denom);
+  pv = pv - step_size * (mv / denom);
 }
 
 // One float4 per thread per array (28 B of HBM traffic per parameter: p, g, m, v read; p, m, v written).
+// hyper_dev = {1-based step number, learning-rate multiplier}: read at execution time (CUDA-graph replay).
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-            float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps, float wd,
+            float* __restrict__ v, long long n, double lr, double beta1, double beta2, float eps, float wd,
             const float* __restrict__ hyper_dev, float gscale) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const double step = (double)hyper_dev[0];
+    s_step_size = (float)(lr * (double)hyper_dev[1] / (1.0 - pow(beta1, step)));
+    s_bc2_sqrt = (float)sqrt(1.0 - pow(beta2, step));
+  }
+  __syncthreads();
   const long long i4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n) return;
-  const float step = hyper_dev[0];
-  const float lr_bc1 = lr * hyper_dev[1] / (1.f - powf(beta1, step));
-  const float bc2_sqrt = sqrtf(1.f - powf(beta2, step));
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const float omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2), b2 = (float)beta2;
   if (i4 + 4 <= n) {
     float4 pv = *reinterpret_cast<float4*>(p + i4);
     const float4 gv = *reinterpret_cast<const float4*>(g + i4);
     float4 mv = *reinterpret_cast<float4*>(m + i4);
     float4 vv = *reinterpret_cast<float4*>(v + i4);
-    adam_one(pv.x, gv.x, mv.x, vv.x, lr_bc1, beta1, beta2, eps, wd, bc2_sqrt, gscale);
-    adam_one(pv.y, gv.y, mv.y, vv.y, lr_bc1, beta1, beta2, eps, wd, bc2_sqrt, gscale);
-    adam_one(pv.z, gv.z, mv.z, vv.z, lr_bc1, beta1, beta2, eps, wd, bc2_sqrt, gscale);
-    adam_one(pv.w, gv.w, mv.w, vv.w, lr_bc1, beta1, beta2, eps, wd, bc2_sqrt, gscale);
+    adam_one(pv.x, gv.x, mv.x, vv.x, step_size, omb1, b2, omb2, eps, wd, bc2_sqrt, gscale);
+    adam_one(pv.y, gv.y, mv.y, vv.y, step_size, omb1, b2, omb2, eps, wd, bc2_sqrt, gscale);
+    adam_one(pv.z, gv.z, mv.z, vv.z, step_size, omb1, b2, omb2, eps, wd, bc2_sqrt, gscale);
+    adam_one(pv.w, gv.w, mv.w, vv.w, step_size, omb1, b2, omb2, eps, wd, bc2_sqrt, gscale);
     *reinterpret_cast<float4*>(p + i4) = pv;
     *reinterpret_cast<float4*>(m + i4) = mv;
     *reinterpret_cast<float4*>(v + i4) = vv;
   } else {
     for (long long i = i4; i < n; ++i)
-      adam_one(p[i], g[i], m[i], v[i], lr_bc1, beta1, beta2, eps, wd, bc2_sqrt, gscale);
+      adam_one(p[i], g[i], m[i], v[i], step_size, omb1, b2, omb2, eps, wd, bc2_sqrt, gscale);
   }
 }
 
@@ -541,14 +553,15 @@ extern "C" int obman_bn_wgrad_finish(const float* dwraw, long long dw_ld, const 
   return check_launch("bn_wgrad_finish_kernel");
 }
 
-extern "C" int obman_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr,
-                               float beta1, float beta2, float eps, float weight_decay,
-                               const float* hyper_dev, float grad_scale, void* stream) {
+extern "C" int obman_adam_step(float* p, const float* g, float* m, float* v, long long n, double lr,
+                               double beta1, double beta2, double eps, double weight_decay,
+                               const float* hyper_dev, double grad_scale, void* stream) {
   OBMAN_REQUIRE(p && g && m && v && n > 0 && hyper_dev, "obman_adam_step: bad arguments");
   OBMAN_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0,
                 "obman_adam_step: buffers must be 16-byte aligned");
+  OBMAN_REQUIRE(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0, "obman_adam_step: betas must be in [0, 1)");
   const long long n4 = (n + 3) / 4;
   adam_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, hyper_dev, grad_scale);
+      p, g, m, v, n, lr, beta1, beta2, (float)eps, (float)weight_decay, hyper_dev, (float)grad_scale);
   return check_launch("adam_kernel");
 }

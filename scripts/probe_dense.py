@@ -243,6 +243,15 @@ CASES.update({
     "wgrad3x3_s1_32_128_128_b3": lambda: case_wgrad(3, 32, 128, 128, 3, 1, 2),
     "wgrad3x3_s1_20_96_160_b3": lambda: case_wgrad(2, 20, 96, 160, 3, 1, 2),
 })
+# persistent 64-output-channel kernel (conv64.cu): many tiles per CTA, ragged tiles, one K block, strided outputs
+CASES.update({
+    "conv3x3_s1_64_64_64_b3_epi_persistent": lambda: case_conv(40, 64, 64, 64, 3, 1, 2, True),
+    "conv3x3_s1_50_64_64_b3_epi_ragged": lambda: case_conv(7, 50, 64, 64, 3, 1, 2, True),
+    "conv3x3_s1_24_32_32_b3": lambda: case_conv(3, 24, 32, 32, 3, 1, 2),
+    "conv3x3_s1_9_64_48_b3_epi": lambda: case_conv(5, 9, 64, 48, 3, 1, 2, True),
+    "dgrad3x3_s1_64_64_64_b3_persistent": lambda: case_dgrad(20, 64, 64, 64, 3, 1, 2),
+    "dgrad3x3_s2_64_64_128_b3": lambda: case_dgrad(6, 64, 64, 128, 3, 2, 2),
+})
 CASES["rounding_mode_p1"] = case_rounding_mode
 CASES["stemlike_wgrad_4x4_128_32_64_p3"] = lambda: case_wgrad(2, 64, 32, 64, 3, 1, 3)
 CASES["wgrad3x3_s1_32_128_128_p3"] = lambda: case_wgrad(3, 32, 128, 128, 3, 1, 3)

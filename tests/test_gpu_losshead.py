@@ -118,7 +118,7 @@ def test_decay_regul_is_followed_by_a_captured_step():
     from obman_train_b200.trainer import FlatAdamTrainer
     from tests.util import FULL_CFG, enum_sample, make_sample
     cfg = dict(FULL_CFG)
-    cfg.update(atlas_lambda_regul_edges=5.0, contact_lambda=0, collision_lambda=0)
+    cfg.update(atlas_lambda_regul_edges=5000.0, contact_lambda=0, collision_lambda=0)   # large: the term must matter
     sample = enum_sample(make_sample(2, 64, 3))
 
     def build():
@@ -135,7 +135,7 @@ def test_decay_regul_is_followed_by_a_captured_step():
     loss_e = tr_e.step(dict(sample))
     model_u, tr_u = build()     # undecayed, for contrast
     loss_u = tr_u.step(dict(sample))
-    assert model_g.atlas_loss.edge_regul_lambda == pytest.approx(1.25)
+    assert model_g.atlas_loss.edge_regul_lambda == pytest.approx(1250.0)
     assert abs(loss_g.item() - loss_e.item()) <= 1e-5 * abs(loss_e.item()), (loss_g.item(), loss_e.item())
     assert abs(loss_u.item() - loss_e.item()) > 1e-3 * abs(loss_e.item())
     assert ((tr_g.flat_p - tr_e.flat_p).norm() / (tr_e.flat_p - tr_u.flat_p).norm()).item() < 0.05

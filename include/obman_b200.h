@@ -212,6 +212,12 @@ int obman_edge_loss_fwd(const float* V, const int* faces, int B, int N, int F, f
 /* vf (N,Kf) int32: ids of the faces incident to each vertex, -1 padded (vertex-centric gather, no atomics). */
 int obman_edge_loss_bwd(const float* V, const int* faces, const int* vf, const float* stats,
                         const float* gloss, int B, int N, int F, int Kf, float* gV, void* stream);
+/* Contact-IoU metric meshiou (contactloss.py:20-47): gt_dists / pred_dists (B,P) squared hand->object distances,
+ * threshs = HOST array of n_thresh (<= 16) thresholds; iou_ws (B, n_thresh) workspace; batch_ious (n_thresh) = mean
+ * over the batch of the per-sample IoU of the thresholded maps; auc[0] = their trapezoid over the thresholds. */
+int obman_contact_iou(const float* gt_dists, const float* pred_dists, int B, int P, const float* threshs,
+                      int n_thresh, float* iou_ws, float* batch_ious, float* auc, void* stream);
+
 /* ---- Scalar-loss stage (csrc/loss_head.cu) -------------------------------------------------------------------
  * Tables (a, b, ga, p, q, rows, width, ... slot, group) are HOST arrays of n_terms entries whose pointer entries are
  * device pointers; they are copied into the kernel's parameters.  `weights` is a DEVICE float vector indexed by

@@ -244,6 +244,71 @@ contact_bwd_kernel(const float* __restrict__ hand, const float* __restrict__ clo
   }
 }
 
+// Contact-IoU metric (meshiou / thresh_ious, contactloss.py:20-47): for every sample and threshold the IoU of the two
+// thresholded contact maps (dists <= thresh; 0 where the union is empty).  One CTA per sample, all thresholds at once.
+constexpr int IOU_MAX_T = 16;
+struct IouThresholds { float t[IOU_MAX_T]; int n; };
+
+__global__ void __launch_bounds__(256)
+contact_iou_kernel(const float* __restrict__ gt, const float* __restrict__ pred, int P, const IouThresholds th,
+                   float* __restrict__ iou /* (B, T) */) {
+  __shared__ int s_inter[IOU_MAX_T], s_union[IOU_MAX_T];
+  const int b = blockIdx.x;
+  if (threadIdx.x < IOU_MAX_T) { s_inter[threadIdx.x] = 0; s_union[threadIdx.x] = 0; }
+  __syncthreads();
+  int inter[IOU_MAX_T], uni[IOU_MAX_T];
+#pragma unroll
+  for (int k = 0; k < IOU_MAX_T; ++k) { inter[k] = 0; uni[k] = 0; }
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float g = gt[(size_t)b * P + i], p = pred[(size_t)b * P + i];
+#pragma unroll
+    for (int k = 0; k < IOU_MAX_T; ++k) {
+      if (k < th.n) {
+        const bool cg = g <= th.t[k], cp = p <= th.t[k];
+        inter[k] += (cg && cp) ? 1 : 0;
+        uni[k] += (cg || cp) ? 1 : 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < IOU_MAX_T; ++k) {
+    if (k < th.n) {
+      int a = inter[k], u = uni[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        u += __shfl_xor_sync(0xffffffffu, u, o);
+      }
+      if ((threadIdx.x & 31) == 0) { atomicAdd(&s_inter[k], a); atomicAdd(&s_union[k], u); }   // integer: order-free
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < th.n)
+    iou[(size_t)b * th.n + threadIdx.x] =
+        s_union[threadIdx.x] != 0 ? (float)s_inter[threadIdx.x] / (float)s_union[threadIdx.x] : 0.f;
+}
+
+// batch_ious[t] = mean_b iou[b, t]; auc = trapezoid of batch_ious over the thresholds (= the reference's mean over the
+// batch of the per-sample trapezoids).  One warp per threshold, fixed summation order.
+__global__ void __launch_bounds__(32 * IOU_MAX_T)
+contact_iou_finalize_kernel(const float* __restrict__ iou, int B, const IouThresholds th,
+                            float* __restrict__ batch_ious, float* __restrict__ auc) {
+  __shared__ float means[IOU_MAX_T];
+  const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (t < th.n) {
+    float s = 0.f;
+    for (int b = lane; b < B; b += 32) s += iou[(size_t)b * th.n + t];
+    s = warp_sum(s) / (float)B;
+    if (lane == 0) { means[t] = s; batch_ious[t] = s; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f;
+    for (int k = 0; k + 1 < th.n; ++k) a += 0.5f * (means[k] + means[k + 1]) * (th.t[k + 1] - th.t[k]);
+    *auc = a;
+  }
+}
+
 }  // namespace obman
 
 using namespace obman;
@@ -311,4 +376,20 @@ extern "C" int obman_contact_bwd(const float* hand, const float* close, const fl
       hand, close, anchor, idx21, attr_mask, rep_mask, fwd_out, g_missed, g_penetr, B, P, N,
       contact_thresh, contact_mode, collision_thresh, collision_mode, target, ghand, gobj);
   return check_launch("contact_bwd_kernel");
+}
+
+extern "C" int obman_contact_iou(const float* gt_dists, const float* pred_dists, int B, int P, const float* threshs,
+                                 int n_thresh, float* iou_ws, float* batch_ious, float* auc, void* stream) {
+  OBMAN_REQUIRE(gt_dists && pred_dists && threshs && iou_ws && batch_ious && auc, "obman_contact_iou: null argument");
+  OBMAN_REQUIRE(B > 0 && P > 0 && n_thresh >= 1 && n_thresh <= IOU_MAX_T,
+                "obman_contact_iou: bad sizes (B=%d P=%d thresholds=%d, at most %d)", B, P, n_thresh, IOU_MAX_T);
+  IouThresholds th;
+  th.n = n_thresh;
+  for (int k = 0; k < IOU_MAX_T; ++k) th.t[k] = k < n_thresh ? threshs[k] : 0.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  contact_iou_kernel<<<B, 256, 0, st>>>(gt_dists, pred_dists, P, th, iou_ws);
+  int rc = check_launch("contact_iou_kernel");
+  if (rc) return rc;
+  contact_iou_finalize_kernel<<<1, 32 * IOU_MAX_T, 0, st>>>(iou_ws, B, th, batch_ious, auc);
+  return check_launch("contact_iou_finalize_kernel");
 }

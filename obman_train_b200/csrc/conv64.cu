@@ -132,11 +132,13 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
         if (lane == 0) {
           const uint32_t b = smem_u32(wt + it * P64_WT_TILE);
           const uint32_t ta = tmem_base + (uint32_t)(256 + 32 * c);
+          if (!(prog.debug_skip & 1) || it == 0) {
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const uint64_t db = umma_desc(b + k * 32, 16, 512, 4);   // 128 rows x 64 B, SW64: 8-row groups 512 B apart
             umma_f16_ts(d, ta + k * 8, db, idesc_wide, (it > 0 || k > 0) ? 1u : 0u);   // [a_hi*b_hi | a_hi*b_lo]
-            umma_f16_ts(d, ta + 16 + k * 8, db, idesc, 1u);                             // columns 0-63 += a_lo*b_hi
+            if (!(prog.debug_skip & 8)) umma_f16_ts(d, ta + 16 + k * 8, db, idesc, 1u);   // columns 0-63 += a_lo*b_hi
+          }
           }
           umma_commit(&empty[c]);
           if (it == n_iters - 1) umma_commit(&accfull[acc]);
@@ -173,7 +175,7 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
         const int a = g % RA;
         mbar_wait(&afull[a], (g / RA) & 1);
         const uint32_t box = smem_u32(halo(a));
-        for (int p = sid; p < prog.halo_pix; p += 128 * NS) {
+        for (int p = sid; p < ((prog.debug_skip & 4) ? 0 : prog.halo_pix); p += 128 * NS) {
           const uint32_t row = box + (uint32_t)p * 128u;
           const int sw = p & 7;
           uint32_t hi[16], lo[16];
@@ -193,7 +195,7 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
         const int gi0 = g * T;             // iteration index of tap 0 of this box
         int tap = (set - gi0 % NS + NS) % NS;   // first tap of this box that belongs to this set
         uint32_t hi[16], lo[16];
-        if (tap < T) load_row(box, hp0 + prog.tap_delta[tap], hi, lo);
+        if (tap < T && !(prog.debug_skip & 2)) load_row(box, hp0 + prog.tap_delta[tap], hi, lo);
         for (; tap < T; tap += NS) {
           const int gi = gi0 + tap;
           const int c = gi % C;
@@ -205,7 +207,7 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
           // the next row's shared-memory reads are issued underneath the tensor-memory store round trip
           uint32_t nhi[16], nlo[16];
           const bool more = tap + NS < T;
-          if (more) load_row(box, hp0 + prog.tap_delta[tap + NS], nhi, nlo);
+          if (more && !(prog.debug_skip & 2)) load_row(box, hp0 + prog.tap_delta[tap + NS], nhi, nlo);
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&conv[c]);
@@ -287,6 +289,16 @@ int try_conv64(const float* x, int n_img, int h_in, int w_in, int c_in, long lon
   for (int t = 0; t < num_taps; ++t) {
     prog.tap_bk[t] = (tap_wslot ? tap_wslot[t] : t) * c_in;
     prog.tap_delta[t] = (tap_dh[t] - dh0) * HW + (tap_dw[t] - dw0);
+  }
+  {
+    // diagnostics only (results are wrong when set): bit 0 skip the MMAs, 1 skip the tap row reads, 2 skip the in-place
+    // split, 3 skip the narrow MMA - which stage bounds the loop
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("OBMAN_CONV64_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    prog.debug_skip = dbg;
   }
   const long long total = (long long)((n_img + TN - 1) / TN) * prog.tiles_h * prog.tiles_w;
   if (total > 0x7fffffff) return 0;

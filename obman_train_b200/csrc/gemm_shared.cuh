@@ -43,6 +43,7 @@ struct GemmProgram {
   // tile origin + (halo_dw0, halo_dh0); halo_pix = pixels of the whole box (all TN images)
   int halo_w, halo_h, halo_dw0, halo_dh0, halo_pix;
   int raster_n;         // MODE 0: blockIdx.x = column tile, blockIdx.y = row tile
+  int debug_skip;       // conv64.cu diagnostics (OBMAN_CONV64_DEBUG), 0 in normal operation
 };
 
 struct GemmEpilogue {

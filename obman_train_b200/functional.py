@@ -175,6 +175,23 @@ def contact_loss(hand, obj, faces_i32, zone_ids, zone_ptr, contact_thresh, conta
     return _ContactFn.apply(hand, obj, faces_i32, zone_ids, zone_ptr, cfg)
 
 
+def contact_iou(gt_dists, pred_dists, threshs):
+    """(batch_ious (T,), auc 0-dim): meshiou of contactloss.py:35-47 on (B,P) squared-distance maps."""
+    import ctypes
+    gt = _prep(gt_dists.detach(), "gt_dists")
+    pred = _prep(pred_dists.detach(), "pred_dists")
+    if gt.shape != pred.shape or gt.dim() != 2:
+        raise RuntimeError("contact_iou: expected two (B,P) tensors")
+    B, P = gt.shape
+    T = len(threshs)
+    th = (ctypes.c_float * T)(*[float(t) for t in threshs])
+    ws = torch.empty((B, T), device=gt.device)
+    ious = torch.empty(T, device=gt.device)
+    auc = torch.empty((), device=gt.device)
+    call("obman_contact_iou", ptr(gt), ptr(pred), B, P, th, T, ptr(ws), ptr(ious), ptr(auc), stream_ptr())
+    return ious, auc
+
+
 # ---------------------------------------------------------------------------------------------------
 # MANO layer
 # ---------------------------------------------------------------------------------------------------

@@ -139,3 +139,26 @@ def test_decay_regul_is_followed_by_a_captured_step():
     assert abs(loss_g.item() - loss_e.item()) <= 1e-5 * abs(loss_e.item()), (loss_g.item(), loss_e.item())
     assert abs(loss_u.item() - loss_e.item()) > 1e-3 * abs(loss_e.item())
     assert ((tr_g.flat_p - tr_e.flat_p).norm() / (tr_e.flat_p - tr_u.flat_p).norm()).item() < 0.05
+
+
+def test_contact_iou_kernel_matches_reference_formula():
+    """meshiou / thresh_ious (contactloss.py:20-47) restated with torch ops, including samples with an empty union."""
+    from obman_train_b200.networks.branches.contactloss import meshiou
+    g = torch.Generator().manual_seed(5)
+    B, P = 9, 778
+    gt = (torch.rand(B, P, generator=g) * 30).cuda()
+    pred = (torch.rand(B, P, generator=g) * 30).cuda()
+    gt[3] += 100.0      # no contact at any threshold in either map: union empty -> IoU 0
+    pred[3] += 100.0
+    threshs = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10]
+    ious, auc = meshiou(gt, pred, threshs)
+    rows = []
+    for t in threshs:
+        a, b = gt <= t, pred <= t
+        inter, union = (a & b).sum(1).double(), (a | b).sum(1).double()
+        rows.append(torch.where(union != 0, inter / union.clamp(min=1), torch.zeros_like(union)))
+    table = torch.stack(rows)                                   # (T, B)
+    ref_auc = np.mean(np.trapezoid(table.cpu().numpy(), axis=0, x=threshs))
+    assert torch.allclose(ious.double(), table.mean(1), rtol=1e-6, atol=1e-7)
+    assert abs(float(auc) - ref_auc) <= 1e-6 * abs(ref_auc)
+    assert table[:, 3].abs().max() == 0

@@ -190,9 +190,19 @@ int obman_bn_wgrad_finish(const float* dwraw, long long dw_ld, const float* w, c
                           const float* gbeta_sum, int O, int I, int KH, int KW, int Ip, int stem,
                           float* gw, float* ggamma, float* gbeta, float* gcbias, void* stream);
 /* AtlasNet decoder layer 1 after the conv1 split (atlasbranch.py:117-131 + atlasutils.py:65-67):
- * out[b,n,c] = relu(G[b*g_bstride + n*C + c] + F[b*C + c]) (c < C), 0 (C <= c < ld). */
-int obman_pointmlp_l1_fwd(const float* G, long long g_bstride, const float* F, int B, int N, int C,
-                          int ld, float* out, void* stream);
+ * out[b,n,c] = relu(sum_{k<3} grid[b*grid_bstride + 3n + k] * W1[c*ldw + k] + F[b*C + c]) (c < C), 0 (C <= c < ld);
+ * W1 = BatchNorm-folded conv1 weights (C, ldw) in fp32 (its first three input channels are the grid point). */
+int obman_pointmlp_l1_fwd(const float* grid, long long grid_bstride, const float* W1, int ldw, const float* F,
+                          int B, int N, int C, int ld, float* out, void* stream);
+/* dst (rows, ld_dst) = alpha * src[:, :C] where mask > 0 (mask NULL = everywhere), zero in columns C .. ld_dst-1:
+ * pad / scale / ReLU-mask glue of the Linear and decoder backward passes in one launch. */
+int obman_pad_scale_mask(const float* src, long long ld_src, const float* mask, long long ld_mask, long long rows,
+                         int C, float alpha, float* dst, int ld_dst, void* stream);
+/* out (K, ld_out) = transpose of w (N, K) in the obman_pack_bf16 layout (B operand of a Linear data gradient). */
+int obman_pack_bf16_t(const float* w, long long ldw, int N, int K, float* out, long long ld_out, void* stream);
+/* out[c * ld_out + k] = sum_r x[r * ld + c] * w[r * K + k], K <= 4: grid part of the decoder's conv1 weight gradient. */
+int obman_weighted_colsum(const float* x, long long rows, int C, long long ld, const float* w, int K, float* out,
+                          long long ld_out, void* stream);
 /* g (B,N, ld) -> gF[b,c] = sum_n g, gG[n,c] = sum_b g (gG may be NULL). */
 int obman_pointmlp_l1_bwd(const float* g, int B, int N, int C, int ld, float* gF, float* gG,
                           void* stream);
@@ -248,6 +258,13 @@ int obman_loss_combine_fwd(const float* const* p, const float* const* q, const i
 /* gterm[k] = gtotal[0] * weights[slot[k]] * scale[k]: the gradient of every element of term k. */
 int obman_loss_combine_bwd(const int* slot, const float* scale, int n_terms, const float* weights,
                            const float* gtotal, float* gterm, void* stream);
+
+/* Per-sample similarity transform of the predicted object (AtlasBranch.forward_inference, atlasbranch.py:133-138):
+ * out[b,n,:] = s[b] * v[b,n,:] + t[b,:]; v, out (B,N,3), s (B) nullable (= 1), t (B,3) nullable (= 0). */
+int obman_affine_points_fwd(const float* v, const float* s, const float* t, int B, int N, float* out, void* stream);
+/* Its gradients (each output nullable): gv = s[b] * g, gs[b] = sum_{n,c} v * g, gt[b,c] = sum_n g[b,n,c]. */
+int obman_affine_points_bwd(const float* g, const float* v, const float* s, int B, int N, float* gv, float* gs,
+                            float* gt, void* stream);
 
 /* Fused torch.optim.Adam step (traineval.py:113-116) on flat fp32 buffers (16-byte aligned); g is multiplied by
  * grad_scale.  hyper_dev: device float[2] = {1-based step number, learning-rate multiplier} - device memory so that a

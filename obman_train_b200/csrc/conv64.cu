@@ -23,14 +23,33 @@
 
 namespace obman {
 
-constexpr int P64_HALO_BYTES = 25600;   // up to 200 halo pixels x 32 channels fp32 (multiple of 1024: swizzle phase)
-constexpr int P64_RA = 2;               // halo boxes in flight
+extern long long* g_trace;
+extern long long g_trace_cap;
+
+// wait-time accounting (obman_debug_trace): a timed mbarrier wait adds the cycles it blocked to `acc`
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
+  if (!timed) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+__device__ __forceinline__ void trace_put(const GemmEpilogue& epi, int k, long long v) {
+  if (epi.trace == nullptr || ((long long)blockIdx.x + 1) * 16 > epi.trace_cap) return;
+  epi.trace[(long long)blockIdx.x * 16 + k] = v;
+}
+
+constexpr int P64_HALO_BYTES = 25600;   // up to 200 halo pixels x 32 channels fp32
+constexpr int P64_RA_MAX = 6;           // halo boxes in flight (as many as fit next to the resident weights, >= 2)
 constexpr int P64_WT_TILE = 8192;       // 128 rows (64 hi + 64 lo) x 64 B
 constexpr int P64_MAX_WT = 18;          // (tap, K-block) weight tiles resident in shared memory
 constexpr int P64_C = 8;                // A stages in tensor memory
-constexpr int P64_STAGING = 16384;      // 8 epilogue warps x 32 rows x 64 B
+constexpr int P64_SMEM_LIMIT = 232448;  // 227 KB of dynamic shared memory per CTA
 template <int NS, int EW> struct P64Threads { static constexpr int value = 32 * (2 + 4 * NS + EW); };
-constexpr int P64_SMEM = P64_MAX_WT * P64_WT_TILE + P64_RA * P64_HALO_BYTES + P64_STAGING + 1024 /*align*/ + 512;
+// shared memory: [weights: n_iters x 8 KB][halo ring: RA x halo_stride][staging: EW x 2 KB][barriers], RA and
+// halo_stride (the box rounded up to 1 KB: swizzle phase) chosen on the host
+__host__ __device__ inline int p64_smem_bytes(int n_wt, int ra, int halo_stride, int ew) {
+  return n_wt * P64_WT_TILE + ra * halo_stride + ew * 2048 + 1024 /*align*/ + 512 /*barriers*/;
+}
 
 __device__ __forceinline__ void named_barrier_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -51,17 +70,20 @@ template <int NS, int EW>
 __global__ void __launch_bounds__(P64Threads<NS, EW>::value, 1)
 conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, const GemmEpilogue epi,
                          int total_tiles) {
-  constexpr int RA = P64_RA, C = P64_C;
+  constexpr int C = P64_C;
+  const int RA = prog.halo_ring;
+  const int T = prog.num_taps, KB = prog.kblocks;
+  const int n_iters = T * KB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wt = smem;
-  uint8_t* halo_base = smem + P64_MAX_WT * P64_WT_TILE;
-  uint8_t* staging = halo_base + RA * P64_HALO_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + P64_STAGING);
+  uint8_t* halo_base = smem + n_iters * P64_WT_TILE;
+  uint8_t* staging = halo_base + RA * prog.halo_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EW * 2048);
   uint64_t* wfull = bars;                    // weights landed
   uint64_t* afull = bars + 1;                // [RA] halo box landed
-  uint64_t* afree = afull + RA;              // [RA] splitter warps are done with the halo box
-  uint64_t* conv = afree + RA;               // [C]  A stage written to tensor memory
+  uint64_t* afree = afull + P64_RA_MAX;      // [RA] splitter warps are done with the halo box
+  uint64_t* conv = afree + P64_RA_MAX;       // [C]  A stage written to tensor memory
   uint64_t* empty = conv + C;                // [C]  MMAs reading the A stage retired
   uint64_t* accfull = empty + C;             // [2]  accumulator of a tile complete
   uint64_t* accfree = accfull + 2;           // [2]  epilogue warps have drained the accumulator
@@ -69,8 +91,6 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
-  const int T = prog.num_taps, KB = prog.kblocks;
-  const int n_iters = T * KB;
 
   if (threadIdx.x == 0) {
     mbar_init(wfull, 1);
@@ -87,7 +107,9 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  auto halo = [&](int i) { return halo_base + i * P64_HALO_BYTES; };
+  auto halo = [&](int i) { return halo_base + i * prog.halo_stride; };
+  const bool timed = epi.trace != nullptr;
+  const long long t_start = clock64();
 
   if (warp == 0) {
     // ===== TMA producer: the weights once, then one halo box per (tile, K block) =====
@@ -103,31 +125,35 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
           tma_load_2d(dst + 4096, &maps.b, wfull, kc + 16, 0); // 64 rows x 64 B of bf16 lo
         }
       int g = 0;
+      long long w_afree = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int n_img0, h0, w0;
         tile_coords(prog, tile, n_img0, h0, w0);
         for (int kb = 0; kb < KB; ++kb, ++g) {
           const int a = g % RA;
-          mbar_wait(&afree[a], ((g / RA) & 1) ^ 1);
+          mbar_wait_timed(&afree[a], ((g / RA) & 1) ^ 1, timed, w_afree);
           mbar_arrive_expect_tx(&afull[a], (uint32_t)prog.halo_bytes);
           tma_load_4d(halo(a), &maps.a[0], &afull[a], kb * BK, w0 + prog.halo_dw0, h0 + prog.halo_dh0, n_img0);
         }
       }
+      trace_put(epi, 1, w_afree);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = umma_idesc_bf16(BM, 64);
     const uint32_t idesc_wide = umma_idesc_bf16(BM, 128);
-    mbar_wait(wfull, 0);
+    long long w_conv = 0, w_accfree = 0, w_wfull = 0;
+    mbar_wait_timed(wfull, 0, timed, w_wfull);
+    const long long t_loop = clock64();
     int gi = 0, ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int acc = ti & 1;
-      mbar_wait(&accfree[acc], ((ti >> 1) & 1) ^ 1);
+      mbar_wait_timed(&accfree[acc], ((ti >> 1) & 1) ^ 1, timed, w_accfree);
       tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)(acc * 128);
       for (int it = 0; it < n_iters; ++it, ++gi) {
         const int c = gi % C;
-        mbar_wait(&conv[c], (gi / C) & 1);
+        mbar_wait_timed(&conv[c], (gi / C) & 1, timed, w_conv);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t b = smem_u32(wt + it * P64_WT_TILE);
@@ -145,6 +171,10 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
         }
         __syncwarp();
       }
+    }
+    if (lane == 0) {
+      trace_put(epi, 6, w_conv); trace_put(epi, 7, w_accfree); trace_put(epi, 8, clock64() - t_loop);
+      trace_put(epi, 11, w_wfull); trace_put(epi, 12, ti);
     }
   } else if (warp < 2 + 4 * NS) {
     // ===== splitters: halo box -> bf16 hi | lo in place, then one shifted row per tap -> tensor memory =====
@@ -170,10 +200,13 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
       }
     };
     int g = 0;
+    long long w_afull = 0, w_empty = 0, t_split = 0;
+    const long long t_loop = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < KB; ++kb, ++g) {
         const int a = g % RA;
-        mbar_wait(&afull[a], (g / RA) & 1);
+        mbar_wait_timed(&afull[a], (g / RA) & 1, timed, w_afull);
+        const long long t_s0 = timed ? clock64() : 0;
         const uint32_t box = smem_u32(halo(a));
         for (int p = sid; p < ((prog.debug_skip & 4) ? 0 : prog.halo_pix); p += 128 * NS) {
           const uint32_t row = box + (uint32_t)p * 128u;
@@ -192,6 +225,7 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
           }
         }
         named_barrier_sync(1, 128 * NS);   // every pixel of the box is converted before any tap row is read
+        if (timed) t_split += clock64() - t_s0;
         const int gi0 = g * T;             // iteration index of tap 0 of this box
         int tap = (set - gi0 % NS + NS) % NS;   // first tap of this box that belongs to this set
         uint32_t hi[16], lo[16];
@@ -199,7 +233,7 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
         for (; tap < T; tap += NS) {
           const int gi = gi0 + tap;
           const int c = gi % C;
-          mbar_wait(&empty[c], ((gi / C) & 1) ^ 1);
+          mbar_wait_timed(&empty[c], ((gi / C) & 1) ^ 1, timed, w_empty);
           tc_fence_after();
           const uint32_t dst = lane_base + (uint32_t)(256 + 32 * c);
           tmem_st_32x16(dst, hi);
@@ -220,6 +254,10 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
         mbar_arrive(&afree[a]);
       }
     }
+    if (sid == 0) {
+      trace_put(epi, 2, w_afull); trace_put(epi, 3, w_empty); trace_put(epi, 4, t_split);
+      trace_put(epi, 5, clock64() - t_loop);
+    }
   } else {
     // ===== epilogue: the last EW warps, TMEM lane quadrant = warp % 4, 64 * 4 / EW output channels per warp =====
     constexpr int COLS = 64 * 4 / EW;
@@ -227,16 +265,25 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
     const int part = (warp - (2 + 4 * NS)) >> 2;
     const int r = q * 32 + lane;
     int ti = 0;
+    const long long t_loop = clock64();
+    long long w_accfull = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       int n_img0, h0, w0;
       tile_coords(prog, tile, n_img0, h0, w0);
       const int acc = ti & 1;
+      if (timed) {   // diagnostics: time blocked on the accumulator (the epilogue function waits again, instantly)
+        const long long t0 = clock64();
+        mbar_wait(&accfull[acc], (uint32_t)((ti >> 1) & 1));
+        w_accfull += clock64() - t0;
+      }
       gemm_epilogue_stacked<64>(staging + part * 8192, tmem_base + (uint32_t)(acc * 128), &accfull[acc], prog, epi, 0, 0,
                                 n_img0, h0, w0, q, lane, r, (uint32_t)((ti >> 1) & 1), part * COLS, part * COLS + COLS);
       tc_fence_before();
       mbar_arrive(&accfree[acc]);
     }
+    if (warp == 2 + 4 * NS && lane == 0) { trace_put(epi, 9, w_accfull); trace_put(epi, 10, clock64() - t_loop); }
   }
+  if (threadIdx.x == 0) trace_put(epi, 0, clock64() - t_start);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -274,6 +321,27 @@ int try_conv64(const float* x, int n_img, int h_in, int w_in, int c_in, long lon
   const int HW = TW + dw1 - dw0, HH = TH + dh1 - dh0;
   const int halo_pix = HW * HH * TN;
   if (halo_pix * 128 > P64_HALO_BYTES || HW > 256 || HH > 256 || TN > 256) return 0;
+  static int cfg = -1;   // OBMAN_CONV64_CFG = <splitter sets><epilogue warps>: 18, 24 (default), 28, 34
+  if (cfg < 0) {
+    const char* e = getenv("OBMAN_CONV64_CFG");
+    cfg = e ? atoi(e) : 24;
+    if (cfg != 18 && cfg != 24 && cfg != 28 && cfg != 34) cfg = 24;
+  }
+  const int ew = cfg % 10;
+  const int halo_stride = (halo_pix * 128 + 1023) / 1024 * 1024;
+  int ring = P64_RA_MAX;
+  {
+    static int ring_cap = -1;
+    if (ring_cap < 0) {
+      const char* e = getenv("OBMAN_CONV64_RING");   // experiment knob: cap on the halo ring depth
+      ring_cap = e ? atoi(e) : P64_RA_MAX;
+      if (ring_cap < 2 || ring_cap > P64_RA_MAX) ring_cap = P64_RA_MAX;
+    }
+    ring = ring_cap;
+  }
+  while (ring > 2 && p64_smem_bytes(num_taps * KB, ring, halo_stride, ew) > P64_SMEM_LIMIT) --ring;
+  const int smem_bytes = p64_smem_bytes(num_taps * KB, ring, halo_stride, ew);
+  if (smem_bytes > P64_SMEM_LIMIT) return 0;
   GemmProgram prog;
   memset(&prog, 0, sizeof(prog));
   prog.spatial = 1;
@@ -286,6 +354,8 @@ int try_conv64(const float* x, int n_img, int h_in, int w_in, int c_in, long lon
   prog.n_img = n_img; prog.h_out = h_out; prog.w_out = w_out;
   prog.halo_w = HW; prog.halo_h = HH; prog.halo_dw0 = dw0; prog.halo_dh0 = dh0; prog.halo_pix = halo_pix;
   prog.halo_bytes = halo_pix * 128;
+  prog.halo_stride = halo_stride;
+  prog.halo_ring = ring;
   for (int t = 0; t < num_taps; ++t) {
     prog.tap_bk[t] = (tap_wslot ? tap_wslot[t] : t) * c_in;
     prog.tap_delta[t] = (tap_dh[t] - dh0) * HW + (tap_dw[t] - dw0);
@@ -321,27 +391,21 @@ int try_conv64(const float* x, int n_img, int h_in, int w_in, int c_in, long lon
   epi.out = out; epi.bias = bias; epi.addend = addend; epi.mask_src = mask_src;
   epi.alpha = 1.f; epi.relu = relu; epi.accumulate = 0;
   epi.sN = o_sN; epi.sH = o_sH; epi.sW = o_sW;
-  // OBMAN_CONV64_CFG = <splitter sets><epilogue warps>: 18, 24, 28 (default), 34
-  static int cfg = -1;
+  epi.trace = g_trace; epi.trace_cap = g_trace_cap;
   const int grid = (int)min((long long)num_sms(), total);
 #define OBMAN_P64_CASE(id, NS, EW)                                                                                    \
   if (cfg == id) {                                                                                                    \
-    static bool attr = false;                                                                                         \
-    if (!attr) {                                                                                                      \
+    static int configured = 0;                                                                                        \
+    if (smem_bytes > configured) {                                                                                    \
       cudaError_t err = cudaFuncSetAttribute(conv64_persistent_kernel<NS, EW>,                                        \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, P64_SMEM);                  \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, P64_SMEM_LIMIT);            \
       if (err != cudaSuccess) {                                                                                       \
-        set_error("conv64: cudaFuncSetAttribute(%d bytes) failed: %s", P64_SMEM, cudaGetErrorString(err));            \
+        set_error("conv64: cudaFuncSetAttribute(%d bytes) failed: %s", P64_SMEM_LIMIT, cudaGetErrorString(err));      \
         return OBMAN_ERR_CUDA;                                                                                        \
       }                                                                                                               \
-      attr = true;                                                                                                    \
+      configured = P64_SMEM_LIMIT;                                                                                    \
     }                                                                                                                 \
-    conv64_persistent_kernel<NS, EW><<<grid, P64Threads<NS, EW>::value, P64_SMEM, st>>>(maps, prog, epi, (int)total); \
-  }
-  if (cfg < 0) {
-    const char* e = getenv("OBMAN_CONV64_CFG");
-    cfg = e ? atoi(e) : 28;
-    if (cfg != 18 && cfg != 24 && cfg != 28 && cfg != 34) cfg = 28;
+    conv64_persistent_kernel<NS, EW><<<grid, P64Threads<NS, EW>::value, smem_bytes, st>>>(maps, prog, epi, (int)total); \
   }
   OBMAN_P64_CASE(18, 1, 8)
   OBMAN_P64_CASE(24, 2, 4)

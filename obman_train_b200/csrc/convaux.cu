@@ -380,11 +380,13 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 }
 
 // AtlasNet decoder, first layer after the algebraic split of conv1 (atlasutils.py:65-67 on the input of
-// atlasbranch.py:117-131): h1[b,n,c] = relu(G[n,c] + F[b,c]) for c < C, 0 for C <= c < ld.
-// G = grid * (s*W[:, :3])^T is batch-independent (or per-sample when g_bstride != 0), F = feat * (s*W[:, 3:])^T + shift.
+// atlasbranch.py:117-131): h1[b,n,c] = relu(sum_k grid[n,k] * W1[c,k] + F[b,c]) for c < C, 0 for C <= c < ld.
+// W1 = folded conv1 weights (C, ldw), columns 0..2 multiply the grid point (batch-independent grid, or per-sample
+// when grid_bstride != 0), F = feat * (s*W[:, 3:])^T + shift.
 __global__ void __launch_bounds__(256)
-pointmlp_l1_fwd_kernel(const float* __restrict__ G, long long g_bstride, const float* __restrict__ F, int B,
-                       int N, int C, int ld, float* __restrict__ out) {
+pointmlp_l1_fwd_kernel(const float* __restrict__ grid, long long grid_bstride, const float* __restrict__ W1,
+                       int ldw, const float* __restrict__ F, int B, int N, int C, int ld,
+                       float* __restrict__ out) {
   const int ld4 = ld / 4;
   const size_t total = (size_t)B * N * ld4;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -393,11 +395,18 @@ pointmlp_l1_fwd_kernel(const float* __restrict__ G, long long g_bstride, const f
   const size_t row = t / ld4;
   const int n = (int)(row % N);
   const int b = (int)(row / N);
+  const float* __restrict__ gp = grid + (size_t)b * grid_bstride + (size_t)n * 3;
+  const float gx = gp[0], gy = gp[1], gz = gp[2];
   float v[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int cc = c + e;
-    v[e] = cc < C ? fmaxf(G[(size_t)b * g_bstride + (size_t)n * C + cc] + F[(size_t)b * C + cc], 0.f) : 0.f;
+    float r = 0.f;
+    if (cc < C) {
+      const float* __restrict__ w = W1 + (size_t)cc * ldw;
+      r = fmaxf(fmaf(gz, w[2], fmaf(gy, w[1], fmaf(gx, w[0], F[(size_t)b * C + cc]))), 0.f);
+    }
+    v[e] = r;
   }
   reinterpret_cast<float4*>(out)[t] = make_float4(v[0], v[1], v[2], v[3]);
 }
@@ -434,17 +443,114 @@ pointmlp_l1_bwd_g_kernel(const float* __restrict__ g, int B, int N, int C, int l
   gG[t] = s;
 }
 
+// dst (rows, ld_dst) <- alpha * src[:, :C] (row stride ld_src), entries whose mask value is <= 0 zeroed (mask nullable, row
+// stride ld_mask), columns C .. ld_dst-1 zero: pad / scale / ReLU-mask glue of the Linear and decoder backward passes in
+// one launch (was fill + compare + multiply + strided copy).
+__global__ void __launch_bounds__(256)
+pad_scale_mask_kernel(const float* __restrict__ src, long long ld_src, const float* __restrict__ mask,
+                      long long ld_mask, long long rows, int C, float alpha, float* __restrict__ dst, int ld_dst) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * ld_dst) return;
+  const long long r = t / ld_dst;
+  const int c = (int)(t - r * ld_dst);
+  float v = 0.f;
+  if (c < C) {
+    v = alpha * src[r * ld_src + c];
+    if (mask && !(mask[r * ld_mask + c] > 0.f)) v = 0.f;
+  }
+  dst[t] = v;
+}
+
+// out (K rows, ld_out) <- transpose of w (N, K; row stride ldw) in the packed bf16 hi|lo layout (see pack_bf16_kernel):
+// the B operand of a Linear layer's data gradient.  One thread per pair of consecutive output columns (n, n+1).
+__global__ void __launch_bounds__(256)
+pack_bf16_t_kernel(const float* __restrict__ w, long long ldw, int N, int K, uint32_t* __restrict__ out,
+                   long long ld_out) {
+  const long long pairs_per_row = ld_out / 2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pairs_per_row * K) return;
+  const long long k = i / pairs_per_row;
+  const int n = (int)(i - k * pairs_per_row) * 2;
+  const float v0 = n < N ? w[(long long)n * ldw + k] : 0.f;
+  const float v1 = n + 1 < N ? w[(long long)(n + 1) * ldw + k] : 0.f;
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+  const uint32_t hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  const uint32_t lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  const int blk = n >> 5, in = (n & 31) >> 1;
+  out[k * ld_out + blk * 32 + in] = hi;
+  out[k * ld_out + blk * 32 + 16 + in] = lo;
+}
+
+// out[c * ld_out + k] = sum_r x[r, c] * w[r, k]  (x (rows, ld), w (rows, K), K <= 4): the grid part of the decoder's conv1
+// weight gradient (the reference's conv1 sees cat(grid, feature): its first three input channels are the grid point).
+// One CTA per 32 columns, fixed summation order.
+__global__ void __launch_bounds__(256)
+weighted_colsum_kernel(const float* __restrict__ x, long long rows, int C, long long ld, const float* __restrict__ w,
+                       int K, float* __restrict__ out, long long ld_out) {
+  __shared__ float red[8][32][4];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    for (long long r = ry; r < rows; r += 8) {
+      const float v = x[r * ld + c];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (k < K) acc[k] = fmaf(v, w[r * K + k], acc[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) red[ry][threadIdx.x & 31][k] = acc[k];
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    for (int k = 0; k < K; ++k) {
+      float s = 0.f;
+      for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x][k];
+      out[(size_t)c * ld_out + k] = s;
+    }
+  }
+}
+
 }  // namespace obman
 
 using namespace obman;
 
-extern "C" int obman_pointmlp_l1_fwd(const float* G, long long g_bstride, const float* F, int B, int N, int C,
-                                     int ld, float* out, void* stream) {
-  OBMAN_REQUIRE(G && F && out && B > 0 && N > 0 && C > 0 && ld >= C && ld % 4 == 0, "obman_pointmlp_l1_fwd: bad arguments");
+extern "C" int obman_pointmlp_l1_fwd(const float* grid, long long grid_bstride, const float* W1, int ldw,
+                                     const float* F, int B, int N, int C, int ld, float* out, void* stream) {
+  OBMAN_REQUIRE(grid && W1 && F && out && B > 0 && N > 0 && C > 0 && ld >= C && ld % 4 == 0 && ldw >= 3,
+                "obman_pointmlp_l1_fwd: bad arguments");
   const size_t total = (size_t)B * N * (ld / 4);
-  pointmlp_l1_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(G, g_bstride, F, B, N, C,
-                                                                                         ld, out);
+  pointmlp_l1_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grid, grid_bstride, W1, ldw,
+                                                                                         F, B, N, C, ld, out);
   return check_launch("pointmlp_l1_fwd_kernel");
+}
+
+extern "C" int obman_pad_scale_mask(const float* src, long long ld_src, const float* mask, long long ld_mask,
+                                    long long rows, int C, float alpha, float* dst, int ld_dst, void* stream) {
+  OBMAN_REQUIRE(src && dst && rows > 0 && C > 0 && ld_dst >= C && ld_src >= C && (!mask || ld_mask >= C),
+                "obman_pad_scale_mask: bad arguments");
+  const long long total = rows * ld_dst;
+  pad_scale_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, ld_src, mask, ld_mask,
+                                                                                        rows, C, alpha, dst, ld_dst);
+  return check_launch("pad_scale_mask_kernel");
+}
+
+extern "C" int obman_pack_bf16_t(const float* w, long long ldw, int N, int K, float* out, long long ld_out,
+                                 void* stream) {
+  OBMAN_REQUIRE(w && out && N > 0 && K > 0 && ldw >= K, "obman_pack_bf16_t: bad arguments");
+  OBMAN_REQUIRE(ld_out % 32 == 0 && ld_out >= N, "obman_pack_bf16_t: ld_out must be a multiple of 32 >= N");
+  const long long n = ld_out / 2 * K;
+  pack_bf16_t_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      w, ldw, N, K, reinterpret_cast<uint32_t*>(out), ld_out);
+  return check_launch("pack_bf16_t_kernel");
+}
+
+extern "C" int obman_weighted_colsum(const float* x, long long rows, int C, long long ld, const float* w, int K,
+                                     float* out, long long ld_out, void* stream) {
+  OBMAN_REQUIRE(x && w && out && rows > 0 && C > 0 && ld >= C && K >= 1 && K <= 4 && ld_out >= K,
+                "obman_weighted_colsum: bad arguments");
+  weighted_colsum_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(x, rows, C, ld, w, K, out, ld_out);
+  return check_launch("weighted_colsum_kernel");
 }
 
 extern "C" int obman_pointmlp_l1_bwd(const float* g, int B, int N, int C, int ld, float* gF, float* gG,

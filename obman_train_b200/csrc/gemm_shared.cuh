@@ -42,6 +42,7 @@ struct GemmProgram {
   // persistent 64-wide kernel (conv64.cu): halo box = halo_w x halo_h pixels per image of the tile, its origin is the
   // tile origin + (halo_dw0, halo_dh0); halo_pix = pixels of the whole box (all TN images)
   int halo_w, halo_h, halo_dw0, halo_dh0, halo_pix;
+  int halo_stride, halo_ring;   // bytes between halo buffers (box rounded up to 1 KB), number of buffers
   int raster_n;         // MODE 0: blockIdx.x = column tile, blockIdx.y = row tile
   int debug_skip;       // conv64.cu diagnostics (OBMAN_CONV64_DEBUG), 0 in normal operation
 };

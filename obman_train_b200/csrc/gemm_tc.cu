@@ -1034,8 +1034,8 @@ int try_conv64(const float* x, int n_img, int h_in, int w_in, int c_in, long lon
                const int* tap_wslot, float* out, int h_out, int w_out, long long o_sN, long long o_sH, long long o_sW,
                const float* bias, const float* addend, const float* mask_src, int relu, cudaStream_t st);   // conv64.cu
 
-static long long* g_trace = nullptr;
-static long long g_trace_cap = 0;
+long long* g_trace = nullptr;       // obman_debug_trace (also read by conv64.cu)
+long long g_trace_cap = 0;
 
 // Cluster size the TS path will run with for a grid of grid_x row tiles (the weight tensor maps are built with a
 // box of BN / cluster rows, so the host code asks before encoding them).

@@ -184,6 +184,48 @@ __global__ void loss_combine_bwd_kernel(const CombineTerms t, const float* __res
   if (k < t.n) gterm[k] = gtotal[0] * weights[t.slot[k]] * t.scale[k];
 }
 
+// ---- per-sample similarity transform of a point cloud ------------------------------------------------------------
+// out[b,n,:] = s[b] * v[b,n,:] + t[b,:]  (AtlasBranch.forward_inference, atlasbranch.py:133-138; s and / or t nullable)
+__global__ void __launch_bounds__(256)
+affine_points_fwd_kernel(const float* __restrict__ v, const float* __restrict__ s, const float* __restrict__ t, int N,
+                         float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 3 * N) return;
+  const float sc = s ? s[b] : 1.f;
+  const float tr = t ? t[3 * b + e % 3] : 0.f;
+  out[(size_t)b * 3 * N + e] = fmaf(sc, v[(size_t)b * 3 * N + e], tr);
+}
+
+// gv = s[b] * g ; gs[b] = sum_{n,c} v * g ; gt[b,c] = sum_n g[b,n,c] : one CTA per sample, fixed summation order
+__global__ void __launch_bounds__(256)
+affine_points_bwd_kernel(const float* __restrict__ g, const float* __restrict__ v, const float* __restrict__ s, int N,
+                         float* __restrict__ gv, float* __restrict__ gs, float* __restrict__ gt) {
+  __shared__ float scratch[32];
+  const int b = blockIdx.x;
+  const float sc = s ? s[b] : 1.f;
+  const float* __restrict__ gb = g + (size_t)b * 3 * N;
+  const float* __restrict__ vb = v + (size_t)b * 3 * N;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // x, y, z sums of g; sum of v * g
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float gg = gb[3 * n + c];
+      acc[c] += gg;
+      acc[3] = fmaf(vb[3 * n + c], gg, acc[3]);
+      if (gv) gv[(size_t)b * 3 * N + 3 * n + c] = sc * gg;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float tot = block_sum(acc[k], scratch);
+    if (threadIdx.x == 0) {
+      if (k < 3) { if (gt) gt[3 * b + k] = tot; }
+      else if (gs) gs[b] = tot;
+    }
+  }
+}
+
 static int fill_sq(SqTerms& t, const float* const* a, const float* const* b, float* const* ga, const int* rows,
                    const int* width, const int* col0, const int* col1, const int* slot, int n) {
   OBMAN_REQUIRE(n >= 1 && n <= LOSS_MAX_TERMS, "sq_terms: n_terms=%d out of [1,%d]", n, LOSS_MAX_TERMS);
@@ -275,4 +317,18 @@ extern "C" int obman_loss_combine_bwd(const int* slot, const float* scale, int n
   for (int k = 0; k < n_terms; ++k) { t.slot[k] = slot[k]; t.scale[k] = scale[k]; }
   loss_combine_bwd_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(t, weights, gtotal, gterm);
   return check_launch("loss_combine_bwd_kernel");
+}
+
+extern "C" int obman_affine_points_fwd(const float* v, const float* s, const float* t, int B, int N, float* out,
+                                       void* stream) {
+  OBMAN_REQUIRE(v && out && B > 0 && N > 0 && B <= 65535, "obman_affine_points_fwd: bad arguments");
+  affine_points_fwd_kernel<<<dim3((3 * N + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(v, s, t, N, out);
+  return check_launch("affine_points_fwd_kernel");
+}
+
+extern "C" int obman_affine_points_bwd(const float* g, const float* v, const float* s, int B, int N, float* gv,
+                                       float* gs, float* gt, void* stream) {
+  OBMAN_REQUIRE(g && v && B > 0 && N > 0, "obman_affine_points_bwd: bad arguments");
+  affine_points_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(g, v, s, N, gv, gs, gt);
+  return check_launch("affine_points_bwd_kernel");
 }

@@ -228,3 +228,35 @@ def object_targets(gt, want_centred=True):
     centred = torch.empty_like(gt) if want_centred else None
     call("obman_object_targets", ptr(gt), B, M, ptr(centroid), ptr(scale), ptr(centred), stream_ptr())
     return centroid, scale, centred
+
+
+class _AffinePointsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, scales, trans):
+        verts = _chk(verts, "verts")
+        B, N, _ = verts.shape
+        s = None if scales is None else _chk(scales, "scales").reshape(B)
+        t = None if trans is None else _chk(trans, "translations")
+        out = torch.empty_like(verts)
+        call("obman_affine_points_fwd", ptr(verts), ptr(s), ptr(t), B, N, ptr(out), stream_ptr())
+        ctx.save_for_backward(verts, s if s is not None else verts.new_empty(0))
+        ctx.has = (scales is not None, trans is not None, None if scales is None else tuple(scales.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        verts, s = ctx.saved_tensors
+        has_s, has_t, s_shape = ctx.has
+        B, N, _ = verts.shape
+        g = _chk(g, "gradient")
+        gv = torch.empty_like(verts) if ctx.needs_input_grad[0] else None
+        gs = torch.empty(B, device=g.device) if (has_s and ctx.needs_input_grad[1]) else None
+        gt = torch.empty((B, 3), device=g.device) if (has_t and ctx.needs_input_grad[2]) else None
+        call("obman_affine_points_bwd", ptr(g), ptr(verts), ptr(s) if has_s else None, B, N, ptr(gv), ptr(gs), ptr(gt),
+             stream_ptr())
+        return gv, None if gs is None else gs.view(s_shape), gt
+
+
+def affine_points(verts, scales=None, translations=None):
+    """scales (B,1) * verts (B,N,3) + translations (B,3) per sample (atlasbranch.py:133-138) as one kernel per direction."""
+    return _AffinePointsFn.apply(verts, scales, translations)

@@ -36,6 +36,25 @@ def _pad_cols(t, width):
     return out
 
 
+def pad_scale_mask(src, width, alpha=1.0, mask=None, cols=None):
+    """(rows, width) buffer = alpha * src[:, :cols] where mask > 0 (mask None: everywhere), zero-padded - one launch."""
+    rows = src.shape[0]
+    C = src.shape[1] if cols is None else cols
+    out = _empty(rows, width)
+    call("obman_pad_scale_mask", ptr(src), src.stride(0), ptr(mask), 0 if mask is None else mask.stride(0), rows, C,
+         float(alpha), ptr(out), width, stream_ptr())
+    return out
+
+
+def packed_transpose(w, n=None, k=None):
+    """(K, r32(N)) packed bf16 hi|lo transpose of w (N,K): the B operand of a Linear layer's data gradient."""
+    N = w.shape[0] if n is None else n
+    K = w.shape[1] if k is None else k
+    out = _empty(K, _r32(N))
+    call("obman_pack_bf16_t", ptr(w), w.stride(0), N, K, ptr(out), out.stride(0), stream_ptr())
+    return out
+
+
 def colsum(t, C=None):
     C = t.shape[1] if C is None else C
     out = _empty(C)
@@ -63,16 +82,22 @@ class _LinearFn(torch.autograd.Function):
         pb = dense.PASSES[dense.get_precision()["bwd"]]
         pw = dense.PASSES[dense.get_precision()["wgrad"]]
         N, K = w.shape
-        if ctx.relu:
-            g = g * (y > 0)
-        gp = _pad_cols(g.contiguous(), _r32(N))
+        # ReLU mask, contiguity and the zero padding of the columns to a multiple of 32 in one launch
+        if not (g.is_cuda and g.dtype == torch.float32):
+            raise RuntimeError("linear backward: expected a CUDA float32 gradient")
+        if g.stride(-1) != 1:
+            g = g.contiguous()
+        gp = pad_scale_mask(g, _r32(N), mask=y if ctx.relu else None)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            wt = _zeros(K, _r32(N))
-            wt[:, :N] = w.t()
-            gx = dense.gemm(gp, wt, passes=pb, n=K, k=N)
+            if pb == dense.BF16X3:
+                gx = dense.gemm(gp, packed_transpose(w), passes=pb, n=K, k=N, packed=True)
+            else:
+                wt = _zeros(K, _r32(N))
+                wt[:, :N] = w.t()
+                gx = dense.gemm(gp, wt, passes=pb, n=K, k=N)
         if ctx.needs_input_grad[1]:
-            xk = _pad_cols(x, _r32(K))
+            xk = x if x.shape[1] == _r32(K) else pad_scale_mask(x, _r32(K))
             gw = dense.wgrad_matrix(gp, xk, passes=pw)[:N, :K].contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = colsum(gp, N)
@@ -86,7 +111,7 @@ def linear(x, weight, bias=None, relu=False):
 class _Layer(object):
     """Folded 1x1-conv (+BN eval) layer of the point decoder: y = relu?(x Wf^T + shift)."""
 
-    def __init__(self, w, cbias, bn, packed=False):
+    def __init__(self, w, cbias, bn, packed=False, plain=False):
         self.w = w.detach().reshape(w.shape[0], w.shape[1]).contiguous()
         self.cbias = cbias.detach().contiguous()
         self.O, self.I = self.w.shape
@@ -94,6 +119,16 @@ class _Layer(object):
         gamma, beta, mean, var = self.bn if self.bn is not None else (None, None, None, None)
         self.packed = packed
         self.shift, self.scale, self.rstd = _empty(self.O), _empty(self.O), _empty(self.O)
+        if plain:
+            # BatchNorm-folded weights in plain fp32, no data-gradient layout (the layer is evaluated outside the GEMMs)
+            self.ld = (self.I + 3) // 4 * 4
+            self.wf = _empty(self.O, self.ld)
+            self.wf_lo = self.wft = self.wft_lo = None
+            call("obman_fold_conv", ptr(self.w), ptr(self.cbias), ptr(gamma), ptr(beta), ptr(mean), ptr(var),
+                 BN_EPS, self.O, self.I, 1, 1, self.ld, 0, 0, ptr(self.wf), None, None, None,
+                 ptr(self.shift), ptr(self.scale), ptr(self.rstd), stream_ptr())
+            self.fw = self.bw = {}
+            return
         if packed:
             # folded weights in the packed bf16 hi|lo layout (3xBF16): wf (O, r32(I)), wft (I, r32(O))
             self.ld = _r32(self.I)
@@ -150,27 +185,33 @@ class _PointDecoderFn(torch.autograd.Function):
         N = grid.shape[-2]
         per_sample = grid.dim() == 3
         pk = pf == dense.BF16X3
-        l1 = _Layer(p[0], p[1], p[8:12])          # conv1 is split algebraically below: keep fp32 folded weights
+        l1 = _Layer(p[0], p[1], p[8:12], plain=True)   # conv1 is split algebraically below: fp32 folded weights
         l2 = _Layer(p[2], p[3], p[12:16], packed=pk)
         l3 = _Layer(p[4], p[5], p[16:20], packed=pk)
         l4 = _Layer(p[6], p[7], None, packed=pk)
         C1, C2, C3 = l1.O, l2.O, l3.O
-        # layer 1: grid part (K = 3, batch independent) + feature part (B x F GEMM) -> relu(G + F)
-        w1 = l1.wf + l1.wf_lo                                # full-precision folded conv1 weights
-        wg = w1[:, :3]                                       # (C1,3)
-        wfeat = w1[:, 3:3 + Fdim].contiguous()               # (C1,F)
-        G = (grid.unsqueeze(-2) * wg).sum(-1).contiguous()   # (N,C1) or (B,N,C1)
-        Fb = dense.gemm(feat, wfeat, bias=l1.shift, passes=pf)        # (B,C1)
+        # layer 1: grid part (K = 3, evaluated inside the layer-1 kernel) + feature part (B x F GEMM) -> relu(G + F)
+        wfeat = l1.wf[:, 3:3 + Fdim]                         # (C1,F) view of the folded conv1 weights
+        if pf == dense.BF16X3:
+            wpk = _empty(C1, _r32(Fdim))
+            call("obman_pack_bf16", ptr(wfeat), l1.wf.stride(0), C1, Fdim, ptr(wpk), wpk.stride(0), st)
+            Fb = dense.gemm(feat, wpk, bias=l1.shift, passes=pf, n=C1, k=Fdim, packed=True)        # (B,C1)
+        else:
+            Fb = dense.gemm(feat, wfeat.contiguous(), bias=l1.shift, passes=pf)
         ld1, ld2 = _r32(C1), _r32(C2)
         h1 = _empty(B * N, ld1)
-        call("obman_pointmlp_l1_fwd", ptr(G), N * C1 if per_sample else 0, ptr(Fb), B, N, C1, ld1, ptr(h1), st)
-        h2 = _zeros(B * N, ld2)
+        call("obman_pointmlp_l1_fwd", ptr(grid), N * 3 if per_sample else 0, ptr(l1.wf), l1.wf.stride(0), ptr(Fb), B, N,
+             C1, ld1, ptr(h1), st)
+        # padding columns of h2 (and of the gradient buffers below) are never read as data: GEMM A operands are fetched
+        # through tensor maps whose K extent is the true channel count (TMA zero-fills beyond it), and in the
+        # weight-gradient GEMMs a padding channel only produces a padding row / column of the raw gradient
+        h2 = _empty(B * N, ld2)
         dense.gemm(h1, l2.wf, out=h2, bias=l2.shift, relu=True, passes=pf, n=C2, k=C1, **l2.fw)
         h3 = dense.gemm(h2, l3.wf, bias=l3.shift, relu=True, passes=pf, n=C3, k=C2, **l3.fw)
         y = dense.gemm(h3, l4.wf, bias=l4.shift * out_factor, alpha=out_factor, passes=pf, n=3, k=C3, **l4.fw)
         ctx.layers = (l1, l2, l3, l4)
         ctx.param_shapes = [tuple(t.shape) for t in p]
-        ctx.saved = (feat, grid, wfeat, h1, h2, h3, B, N, per_sample, out_factor)
+        ctx.saved = (feat, grid, h1, h2, h3, B, N, per_sample, out_factor)
         return y.view(B, N, 3)
 
     @staticmethod
@@ -179,9 +220,10 @@ class _PointDecoderFn(torch.autograd.Function):
         pw = dense.PASSES[dense.get_precision()["wgrad"]]
         st = stream_ptr()
         l1, l2, l3, l4 = ctx.layers
-        feat, grid, wfeat, h1, h2, h3, B, N, per_sample, out_factor = ctx.saved
+        feat, grid, h1, h2, h3, B, N, per_sample, out_factor = ctx.saved
         C1, C2, C3 = l1.O, l2.O, l3.O
         M = B * N
+        Fdim = feat.shape[1]
         # data-gradient chain on the current stream, weight gradients / BN finishes on the auxiliary stream
         keep = []
 
@@ -191,35 +233,41 @@ class _PointDecoderFn(torch.autograd.Function):
             with streams.on_aux():
                 return layer.finish(dense.wgrad_matrix(g, h, passes=pw), colsum(g, C))
 
-        g4 = _zeros(M, 32)
-        g4[:, :3] = gy.reshape(M, 3) * out_factor
+        if not (gy.is_cuda and gy.dtype == torch.float32):
+            raise RuntimeError("point_decoder backward: expected a CUDA float32 gradient")
+        g4 = pad_scale_mask(gy.reshape(M, 3) if gy.is_contiguous() else gy.contiguous().view(M, 3), 32, alpha=out_factor)
         gw4, gb4, _, _ = side_layer(l4, g4, h3, 3)
         g3 = dense.gemm(g4, l4.wft, mask_src=h3, passes=pb, n=C3, k=3, **l4.bw)       # (M,C3)
         gw3, gb3, gg3, gbt3 = side_layer(l3, g3, h2, C3)
-        g2 = _zeros(M, h2.shape[1])
+        g2 = _empty(M, h2.shape[1])
         dense.gemm(g3, l3.wft, out=g2, mask_src=h2, passes=pb, n=C2, k=C3, **l3.bw)
         gw2, gb2, gg2, gbt2 = side_layer(l2, g2, h1, C2)
-        g1 = _zeros(M, h1.shape[1])
+        g1 = _empty(M, h1.shape[1])
         dense.gemm(g2, l2.wft, out=g1, mask_src=h1, passes=pb, n=C1, k=C2, **l2.bw)
-        gF = _zeros(B, _r32(C1))
         gFc = _empty(B, C1)
         gG = None if per_sample else _empty(N, C1)
         call("obman_pointmlp_l1_bwd", ptr(g1), B, N, C1, g1.shape[1], ptr(gFc), ptr(gG), st)
-        gF[:, :C1] = gFc
-        # raw weight gradient of conv1 = [grid part | feature part]
+        gF = pad_scale_mask(gFc, _r32(C1))
+        # raw weight gradient of conv1 = [grid part (C1,3) | feature part (C1,F)], written into one (C1, 3+F) buffer
+        dw1 = _empty(C1, 3 + Fdim)
         if per_sample:
-            gwg = torch.einsum("mc,mk->ck", g1[:, :C1], grid.reshape(M, 3))
+            call("obman_weighted_colsum", ptr(g1), M, C1, g1.stride(0), ptr(grid), 3, ptr(dw1), dw1.stride(0), st)
         else:
-            gwg = torch.einsum("nc,nk->ck", gG, grid)
-        Fdim = feat.shape[1]
-        gwf = dense.wgrad_matrix(gF, _pad_cols(feat, _r32(Fdim)), passes=pw)[:C1, :Fdim]
-        dw1 = torch.cat([gwg, gwf], dim=1).contiguous()                                      # (C1, 3+F)
+            call("obman_weighted_colsum", ptr(gG), N, C1, C1, ptr(grid), 3, ptr(dw1), dw1.stride(0), st)
+        featp = feat if Fdim == _r32(Fdim) else pad_scale_mask(feat, _r32(Fdim))
+        dw1[:, 3:] = dense.wgrad_matrix(gF, featp, passes=pw)[:C1, :Fdim]
         gw1, gb1, gg1, gbt1 = l1.finish(dw1, colsum(gF, C1))
         gfeat = None
         if ctx.needs_input_grad[0]:
-            wft = _zeros(Fdim, _r32(C1))
-            wft[:, :C1] = wfeat.t()
-            gfeat = dense.gemm(gF, wft, passes=pb, n=Fdim, k=C1)
+            wfeat = l1.wf[:, 3:3 + Fdim]
+            if pb == dense.BF16X3:
+                wft = _empty(Fdim, _r32(C1))
+                call("obman_pack_bf16_t", ptr(wfeat), l1.wf.stride(0), C1, Fdim, ptr(wft), wft.stride(0), st)
+                gfeat = dense.gemm(gF, wft, passes=pb, n=Fdim, k=C1, packed=True)
+            else:
+                wft = _zeros(Fdim, _r32(C1))
+                wft[:, :C1] = wfeat.t()
+                gfeat = dense.gemm(gF, wft, passes=pb, n=Fdim, k=C1)
         streams.join()
         del keep
         p = ctx.param_shapes

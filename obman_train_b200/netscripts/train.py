@@ -78,7 +78,9 @@ def run(args, model_kwargs=None, train_loader=None, val_loader=None, out=print):
     trainer = FlatAdamTrainer(model, lr=args.lr, weight_decay=args.weight_decay, world_size=world)
     start_epoch, best_score = 0, None
     if args.resume:
-        start_epoch, best_score = modelio.load_checkpoint(model, args.resume, optimizer=trainer, strict=False)
+        # the stored best score is dropped on resume, as the reference does (`start_epoch, _ = load_checkpoint`,
+        # traineval.py:160-166): it may be an AUC (higher is better) or a loss (lower is better) depending on who wrote it
+        start_epoch, _ = modelio.load_checkpoint(model, args.resume, optimizer=trainer, strict=False)
         trainer.lr = args.lr                      # "Override loaded learning rate" (traineval.py:168-171)
         trainer.set_lr_scale(1.0)
     n_gt = cfg.get("atlas_points_nb", 600)
@@ -98,8 +100,16 @@ def run(args, model_kwargs=None, train_loader=None, val_loader=None, out=print):
         val_meters, val_pck = epoch_pass(val_loader, model, epoch, train=False, world_size=world, rank=rank,
                                          log_every=0, out=out)
         val_total = val_meters.average_meters["total_loss"].avg
-        is_best = best_score is None or val_total < best_score
-        best_score = val_total if best_score is None else min(best_score, val_total)
+        # best-score bookkeeping of traineval.py:375-388: the validation AUC (higher is better) when joint errors were
+        # evaluated, else the validation loss (lower is better); "best_score" in the checkpoint is that number.  (The
+        # first evaluation counts as best here; the reference's strict comparison against itself never marks it.)
+        if "auc" in val_pck:
+            score = float(val_pck["auc"])
+            is_best = best_score is None or score > best_score
+            best_score = score if best_score is None else max(best_score, score)
+        else:
+            is_best = best_score is None or val_total < best_score
+            best_score = val_total if best_score is None else min(best_score, val_total)
         history.append({"epoch": epoch + 1, "train_total": train_meters.average_meters["total_loss"].avg,
                         "val_total": val_total, "val_auc": float(val_pck.get("auc", float("nan")))})
         if rank == 0:

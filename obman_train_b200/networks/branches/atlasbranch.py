@@ -94,15 +94,11 @@ class AtlasBranch(nn.Module):
             scales = self.decode_scale(img_features)
         dec_features = separate_encoder_features if self.separate_encoder else img_features
         verts = self.decoder.decode(dec_features, self.test_verts)
-        if self.predict_scale:
-            scaled_verts = scales.unsqueeze(1) * verts
-            if self.predict_trans:
-                objpoints3d = scaled_verts + translations.unsqueeze(1)
-        elif self.predict_trans:
-            objpoints3d = verts + translations.unsqueeze(1)
+        # per-sample similarity transform of the decoded sphere: one kernel per direction (losshead.affine_points)
         if not self.predict_scale and not self.predict_trans:
             results = {"objpoints3d": verts, "objfaces": self.test_faces}
         if self.predict_trans:
+            objpoints3d = losshead.affine_points(verts, scales if self.predict_scale else None, translations)
             results = {"objpoints3d": objpoints3d, "objtrans": translations,
                        "objpointscentered3d": verts, "objfaces": self.test_faces}
         if self.predict_scale:

@@ -426,6 +426,29 @@ def measure_train(wl, args, world, rank, local, full):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         res["in_sync"] = bool(torch.equal(lo, hi))
+    if world > 1:
+        # communication evidence (no nsys in this image): the exchange alone, and the same captured step with the
+        # exchange switched off - the difference is the exposed (non-overlapped) communication time.  Runs last: the
+        # replicas diverge once gradients are no longer summed.
+        nbytes = trainer.flat_g.numel() * 4
+        for _ in range(3):
+            dist.all_reduce(trainer.flat_g)
+        ms_ar = timed(10, lambda: dist.all_reduce(trainer.flat_g)) / 10
+        trainer.release_graph()
+        trainer.skip_allreduce = True
+        if use_graph:
+            trainer.capture(resident)
+        for _ in range(3):
+            step_resident()
+        ms_nc = timed(args.steps, step_resident) / args.steps
+        trainer.skip_allreduce = False
+        exposed = max(0.0, res["ms_per_step"] - ms_nc)
+        res["comm"] = {"allreduce_bytes": nbytes, "allreduce_alone_ms": ms_ar,
+                       "allreduce_bus_gbs": 2.0 * (world - 1) / world * nbytes / ms_ar / 1e6,
+                       "step_ms": res["ms_per_step"], "step_ms_without_exchange": ms_nc, "exposed_ms": exposed,
+                       "overlap_frac": max(0.0, 1.0 - exposed / ms_ar) if ms_ar > 0 else None,
+                       "how": "CUDA events, max over ranks; 'without exchange' = the same captured step with the "
+                              "all-reduce launches removed (replicas no longer in sync afterwards)"}
     res["trainer"] = trainer
     return res
 
@@ -488,6 +511,12 @@ def run_b200(args):
         raise RuntimeError(lib.obman_get_last_error().decode())
     dense.set_precision(args.precision, args.precision)
     wl = Workload(args.config or default_config(world))
+    scaling = "weak"
+    if args.strong:
+        wl = Workload(4)
+        wl.batch = 1024 // world
+        wl.name += " [strong scaling: global batch 1024, %d per GPU]" % wl.batch
+        scaling = "strong"
     if wl.hand_only:
         if rank == 0:
             print(json.dumps({"metric": "forward latency", "unit": "ms", "n_gpus": 1, "higher_is_better": False,
@@ -514,10 +543,11 @@ def run_b200(args):
     line = {
         "metric": "train-step images/sec", "value": res["value"], "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": res["warmup"], "ms_per_step": res["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
         "config": wl.describe(world, args.precision), "clocks": res["clocks"],
         "e2e": res["e2e"], "gpu_launches": res["kernels"], "replicas_in_sync": res["in_sync"],
+        "comm": res.get("comm"),
         "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel / wgrad_bf16_kernel (all conv/GEMM launches of a step)",
                      "achieved": prof["tflops"], "peak": tc_peak, "unit": "TFLOP/s",
                      "frac": prof["tflops"] / tc_peak,
@@ -594,6 +624,8 @@ def main():
     ap.add_argument("--config", type=int, default=0, choices=[0, 1, 2, 3, 4],
                     help="BASELINE.json configs index + 1; 0 (default) = configs[2] on one GPU, configs[3] under torchrun")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch tensor-core profile of one step here")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling of configs[3]: global batch fixed at 1024, per-GPU batch = 1024 / N")
     args = ap.parse_args()
     if args.quick:
         args.no_cpu_baseline = args.no_gpu_eager = args.no_secondary = True

@@ -147,11 +147,14 @@ int obman_conv_nhwc(const float* x, int n_img, int h_in, int w_in, int c_in, int
 
 /* obman_wgrad_nhwc: dw[co, t*c_in + ci] = sum_{n,h,w} dy[n,h,w,co] * xview_t[n, h+dh[t], w+dw[t], ci];
  * weight gradient of the convolution above and (h = 1) of obman_gemm, as ONE GEMM with the taps stacked
- * along N.  c_out, c_in multiples of 32.  dw (c_out, num_taps*c_in) is overwritten.  x_sN / x_sH / x_sW as above. */
+ * along N.  c_out, c_in multiples of 32.  dw (c_out, num_taps*c_in) is overwritten.  x_sN / x_sH / x_sW as above.
+ * dy_colsum (nullable, 3xBF16 path only): (c_out) receives sum_{n,h,w} dy[n,h,w,co] - the BatchNorm-beta / bias
+ * gradient, accumulated by the threads that split dy anyway (no separate pass over dy). */
 int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out, int c_out, const float* x,
                      int h_in, int w_in, int c_in, int in_step, long long x_sN, long long x_sH,
                      long long x_sW, int num_taps, const int* tap_dh,
-                     const int* tap_dw, const int* tap_phase, float* dw, int passes, void* stream);
+                     const int* tap_dw, const int* tap_phase, float* dw, float* dy_colsum, int passes,
+                     void* stream);
 
 /* ---- Encoder helpers (bandwidth-bound; mano_train/networks/bases/resnet.py:154-188) -----------------------
  * obman_stem_pack: x (B,3,H,W) NCHW -> out (B, H/2, W/2 + 4, 16) NHWC: 2x2 space-to-depth, channel

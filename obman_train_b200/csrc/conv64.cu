@@ -173,7 +173,7 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
       }
     }
     if (lane == 0) {
-      trace_put(epi, 6, w_conv); trace_put(epi, 7, w_accfree); trace_put(epi, 8, clock64() - t_loop);
+      trace_put(epi, 13, w_conv); trace_put(epi, 7, w_accfree); trace_put(epi, 8, clock64() - t_loop);
       trace_put(epi, 11, w_wfull); trace_put(epi, 12, ti);
     }
   } else if (warp < 2 + 4 * NS) {
@@ -289,6 +289,262 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ---- second generation: operand roles swapped ----------------------------------------------------------------------
+// Measured on the kernel above (scripts/trace_conv64.py, profiles/conv64_trace_r2.txt): with the A operand in tensor
+// memory every tap costs 16 KB of tcgen05.st plus 16 KB of A reads by the MMAs, and that tensor-memory traffic - not the
+// MMA rate - paces the loop (~650 clk per (tap, K block) against 248 clk of MMA work).  Here NOTHING is written per tap:
+//   * A operand (M = 128) = the resident stacked weight tile of a (tap, K block): rows 0-63 = bf16 hi, 64-127 = bf16 lo
+//     of the 64 output channels, read from shared memory (K-major, SW64) - the same bytes the first generation used as B;
+//   * B operand (N = a run of consecutive halo pixels) = the activations, read from shared memory through a NON-swizzled
+//     K-major descriptor.  The halo box is converted once, in place, from TMA's fp32 [pixel][32 ch] rows into eight
+//     "planes" [16-byte K chunk][pixel][8 bf16] (4 planes of hi, 4 of lo).  In that layout the 8-row x 16-byte core
+//     matrices of consecutive pixels are contiguous (stride-between-row-groups = 128 B), so ANY pixel offset is a valid
+//     descriptor start address: a tap is a different start address, nothing else.  The run covers the TH x TW output
+//     tile as flattened halo positions ((TH-1) * halo_w + TW columns, rounded up to 16); the halo columns in between are
+//     computed and discarded by the epilogue (89 % of the columns are used for the 8 x 16 tile of a 3x3 convolution).
+//   * two MMAs per K = 16 step, both with A = [w_hi; w_lo]: B = a_hi, then B = a_lo.  Accumulator lanes 0-63 hold
+//     w_hi * (a_hi + a_lo), lanes 64-127 hold w_lo * (a_hi + a_lo); the epilogue adds the two halves (all four bf16
+//     products, one more than the 3xBF16 scheme needs).
+// Warp roles (320 threads): 0 = TMA producer, 1 = MMA issuer, 2-5 = converters, 6-9 = epilogue.  Tensor memory: two
+// accumulators of N <= 256 columns.
+constexpr int P64V2_THREADS = 320;
+
+__global__ void __launch_bounds__(P64V2_THREADS, 1)
+conv64_v2_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, const GemmEpilogue epi, int total_tiles) {
+  const int RA = prog.halo_ring;
+  const int T = prog.num_taps, KB = prog.kblocks;
+  const int n_iters = T * KB;
+  const int NRUN = prog.run_cols;            // MMA N: columns of the accumulator (multiple of 16, <= 256)
+  const int P = prog.halo_pix;               // pixels of the halo box = rows of every plane
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wt = smem;
+  uint8_t* halo_base = smem + n_iters * P64_WT_TILE;
+  uint8_t* staging = halo_base + RA * prog.halo_stride;      // 2 x 4 KB: 16 pixels x 64 channels fp32, double-buffered
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 8192);
+  uint64_t* wfull = bars;                    // weights landed
+  uint64_t* afull = bars + 1;                // [RA] halo box landed (TMA)
+  uint64_t* bconv = afull + P64_RA_MAX;      // [RA] halo box converted to bf16 planes
+  uint64_t* afree = bconv + P64_RA_MAX;      // [RA] MMAs reading the box retired
+  uint64_t* accfull = afree + P64_RA_MAX;    // [2]  accumulator of a tile complete
+  uint64_t* accfree = accfull + 2;           // [2]  epilogue warps have drained the accumulator
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accfree + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(wfull, 1);
+    for (int i = 0; i < RA; ++i) { mbar_init(&afull[i], 1); mbar_init(&bconv[i], 128); mbar_init(&afree[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&accfull[i], 1); mbar_init(&accfree[i], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  auto halo = [&](int i) { return halo_base + i * prog.halo_stride; };
+
+  if (warp == 0) {
+    // ===== TMA producer: the weights once, then one halo box per (tile, K block) =====
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.a[0]);
+      tma_prefetch_desc(&maps.b);
+      mbar_arrive_expect_tx(wfull, (uint32_t)n_iters * P64_WT_TILE);
+      for (int kb = 0; kb < KB; ++kb)
+        for (int tap = 0; tap < T; ++tap) {
+          uint8_t* dst = wt + (kb * T + tap) * P64_WT_TILE;
+          const int kc = prog.tap_bk[tap] + kb * BK;
+          tma_load_2d(dst, &maps.b, wfull, kc, 0);             // 64 rows x 64 B of bf16 hi
+          tma_load_2d(dst + 4096, &maps.b, wfull, kc + 16, 0); // 64 rows x 64 B of bf16 lo
+        }
+      int g = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n_img0, h0, w0;
+        tile_coords(prog, tile, n_img0, h0, w0);
+        for (int kb = 0; kb < KB; ++kb, ++g) {
+          const int a = g % RA;
+          mbar_wait(&afree[a], ((g / RA) & 1) ^ 1);
+          mbar_arrive_expect_tx(&afull[a], (uint32_t)prog.halo_bytes);
+          tma_load_4d(halo(a), &maps.a[0], &afull[a], kb * BK, w0 + prog.halo_dw0, h0 + prog.halo_dh0, n_img0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = umma_idesc_bf16(BM, NRUN);
+    const uint32_t plane = (uint32_t)P * 16u;            // bytes between consecutive 16-byte K chunks of a pixel row
+    mbar_wait(wfull, 0);
+    int g = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int acc = ti & 1;
+      mbar_wait(&accfree[acc], ((ti >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)(acc * 256);
+      for (int kb = 0; kb < KB; ++kb, ++g) {
+        const int a = g % RA;
+        mbar_wait(&bconv[a], (g / RA) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t box = smem_u32(halo(a));
+          for (int tap = 0; tap < T; ++tap) {
+            const uint32_t w = smem_u32(wt + (kb * T + tap) * P64_WT_TILE);
+            const uint32_t brow = box + (uint32_t)prog.tap_delta[tap] * 16u;   // first pixel of the run for this tap
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              // A: 128 rows x 64 B, SW64, K-major: 8-row groups 512 B apart; k-th 32-byte K slice
+              const uint64_t da = umma_desc(w + k * 32, 16, 512, 4);
+              // B: no swizzle, K-major: core matrix = 8 pixels x 16 B contiguous; next 8 pixels +128 B (SBO),
+              // next 16-byte K chunk +plane (LBO); hi planes 0-3, lo planes 4-7; K = 16 -> chunks 2k, 2k+1
+              const uint64_t db_hi = umma_desc(brow + (uint32_t)(2 * k) * plane, plane, 128, 0);
+              const uint64_t db_lo = umma_desc(brow + (uint32_t)(4 + 2 * k) * plane, plane, 128, 0);
+              umma_f16_ss(d, da, db_hi, idesc, (kb > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              umma_f16_ss(d, da, db_lo, idesc, 1u);
+            }
+          }
+          umma_commit(&afree[a]);                       // the box may be overwritten once these MMAs have read it
+          if (kb == KB - 1) umma_commit(&accfull[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ===== converters: fp32 [pixel][32 ch] (SW128 rows as TMA wrote them) -> eight bf16 planes, in place =====
+    const int sid = threadIdx.x - 64;            // 0 .. 127
+    int g = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < KB; ++kb, ++g) {
+        const int a = g % RA;
+        mbar_wait(&afull[a], (g / RA) & 1);
+        const uint32_t box = smem_u32(halo(a));
+        uint32_t hi[2][16], lo[2][16];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int p = sid + 128 * e;
+          if (p < P) {
+            const uint32_t row = box + (uint32_t)p * 128u;
+            const int sw = p & 7;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 v = lds_v4(row + ((j ^ sw) << 4));
+              split_bf16x2(v.x, v.y, hi[e][2 * j], lo[e][2 * j]);
+              split_bf16x2(v.z, v.w, hi[e][2 * j + 1], lo[e][2 * j + 1]);
+            }
+          }
+        }
+        named_barrier_sync(1, 128);   // every row has been read before the planes overwrite the box
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int p = sid + 128 * e;
+          if (p < P) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              sts_v4(box + (uint32_t)(j * P + p) * 16u, hi[e][4 * j], hi[e][4 * j + 1], hi[e][4 * j + 2], hi[e][4 * j + 3]);
+              sts_v4(box + (uint32_t)((4 + j) * P + p) * 16u, lo[e][4 * j], lo[e][4 * j + 1], lo[e][4 * j + 2], lo[e][4 * j + 3]);
+            }
+          }
+        }
+        fence_proxy_async_smem();     // the planes are read by the tensor core (async proxy)
+        mbar_arrive(&bconv[a]);
+      }
+    }
+  } else {
+    // ===== epilogue: warps 6..9, TMEM lane quadrant = warp % 4 =====
+    // lanes 0-63 of the accumulator = w_hi part of channels 0-63, lanes 64-127 = w_lo part; 16 pixel columns per round
+    // go through a (16 pixels x 64 channels) fp32 staging tile: lo-part warps store, hi-part warps add, then all four
+    // warps walk the pixels with 16 lanes x float4 per pixel (256 contiguous bytes per store instruction and row)
+    const int q = warp & 3;
+    const int et = threadIdx.x - 192;            // 0 .. 127
+    const int part = q >> 1;                     // 0: lanes 0-63 (hi), 1: lanes 64-127 (lo)
+    const int ch = (q & 1) * 32 + lane;          // channel of this TMEM lane
+    const int px_sub = et >> 4;                  // pixel (of 8) this thread stores in each half round
+    const int c4 = (et & 15) * 4;                // its four channels
+    const bool ptr_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
+                          reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0;
+    float bias4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (epi.bias) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (c4 + e < prog.N) bias4[e] = __ldg(epi.bias + c4 + e);
+    }
+    int ti = 0, round_idx = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      int n_img0, h0, w0;
+      tile_coords(prog, tile, n_img0, h0, w0);
+      const int acc = ti & 1;
+      mbar_wait(&accfull[acc], (uint32_t)((ti >> 1) & 1));
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      for (int j0 = 0; j0 < NRUN; j0 += 16, ++round_idx) {
+        float* S = reinterpret_cast<float*>(staging + (round_idx & 1) * 4096);
+        // global row of the two pixels this thread will store (column j of the run = halo position (j / halo_w, j % halo_w))
+        long long roff[2];
+        float4 add4[2], msk4[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = j0 + px_sub + 8 * e;
+          const int hr = j / prog.halo_w, tw = j - hr * prog.halo_w;      // halo row (over all images of the box), column
+          const int tn = hr / prog.halo_h, th = hr - tn * prog.halo_h;
+          const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
+          const bool ok = tw < prog.TW && th < prog.TH && tn < prog.TN && n < prog.n_img && h < prog.h_out &&
+                          w < prog.w_out && c4 < prog.N;
+          roff[e] = ok ? n * epi.sN + h * epi.sH + w * epi.sW : -1;
+          epilogue_prefetch(epi, prog, roff[e], c4, ptr_ok, add4[e], msk4[e]);
+        }
+        uint32_t v[16];
+        tmem_ld_32x16(lane_addr + (uint32_t)j0, v);
+        tmem_ld_wait();
+        if (part == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) S[i * 64 + ch] = __uint_as_float(v[i]);
+        }
+        named_barrier_sync(2, 128);
+        if (part == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) S[i * 64 + ch] += __uint_as_float(v[i]);
+        }
+        named_barrier_sync(2, 128);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (roff[e] < 0) continue;
+          const float4 s4 = *reinterpret_cast<const float4*>(S + (px_sub + 8 * e) * 64 + c4);
+          float x[4] = {epi.alpha * s4.x + bias4[0], epi.alpha * s4.y + bias4[1], epi.alpha * s4.z + bias4[2],
+                        epi.alpha * s4.w + bias4[3]};
+          if (ptr_ok && (roff[e] & 3) == 0 && c4 + 3 < prog.N) {
+            x[0] += add4[e].x; x[1] += add4[e].y; x[2] += add4[e].z; x[3] += add4[e].w;
+            if (epi.relu) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) x[c] = fmaxf(x[c], 0.f);
+            }
+            x[0] = msk4[e].x > 0.f ? x[0] : 0.f; x[1] = msk4[e].y > 0.f ? x[1] : 0.f;
+            x[2] = msk4[e].z > 0.f ? x[2] : 0.f; x[3] = msk4[e].w > 0.f ? x[3] : 0.f;
+            *reinterpret_cast<float4*>(epi.out + roff[e] + c4) = make_float4(x[0], x[1], x[2], x[3]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c4 + c >= prog.N) break;
+              float y = x[c];
+              if (epi.addend) y += epi.addend[roff[e] + c4 + c];
+              if (epi.relu) y = fmaxf(y, 0.f);
+              if (epi.mask_src) y = epi.mask_src[roff[e] + c4 + c] > 0.f ? y : 0.f;
+              epi.out[roff[e] + c4 + c] = y;
+            }
+          }
+        }
+        // the other staging buffer is used by the next round; this one is rewritten two rounds from now, after the
+        // two barriers of the next round
+      }
+      tc_fence_before();
+      mbar_arrive(&accfree[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 static bool conv64_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -393,6 +649,34 @@ int try_conv64(const float* x, int n_img, int h_in, int w_in, int c_in, long lon
   epi.sN = o_sN; epi.sH = o_sH; epi.sW = o_sW;
   epi.trace = g_trace; epi.trace_cap = g_trace_cap;
   const int grid = (int)min((long long)num_sms(), total);
+  {
+    // second generation (operands swapped, no per-tap tensor-memory traffic) whenever the flattened run fits
+    static int gen = -1;
+    if (gen < 0) {
+      const char* e = getenv("OBMAN_CONV64_GEN");
+      gen = (e && e[0] == '1') ? 1 : 2;
+    }
+    const int run = (((TN - 1) * HH + TH - 1) * HW + TW + 15) / 16 * 16;
+    int ring2 = P64_RA_MAX;
+    auto smem2 = [&](int r) { return num_taps * KB * P64_WT_TILE + r * halo_stride + 8192 + 1024 + 512; };
+    while (ring2 > 2 && smem2(ring2) > P64_SMEM_LIMIT) --ring2;
+    if (gen == 2 && run <= 256 && halo_pix <= 256 && smem2(ring2) <= P64_SMEM_LIMIT) {
+      prog.run_cols = run;
+      prog.halo_ring = ring2;
+      static bool attr2 = false;
+      if (!attr2) {
+        cudaError_t err = cudaFuncSetAttribute(conv64_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P64_SMEM_LIMIT);
+        if (err != cudaSuccess) {
+          set_error("conv64: cudaFuncSetAttribute(%d bytes) failed: %s", P64_SMEM_LIMIT, cudaGetErrorString(err));
+          return OBMAN_ERR_CUDA;
+        }
+        attr2 = true;
+      }
+      conv64_v2_kernel<<<grid, P64V2_THREADS, smem2(ring2), st>>>(maps, prog, epi, (int)total);
+      int rc2 = check_launch("conv64_v2_kernel");
+      return rc2 ? rc2 : 1;
+    }
+  }
 #define OBMAN_P64_CASE(id, NS, EW)                                                                                    \
   if (cfg == id) {                                                                                                    \
     static int configured = 0;                                                                                        \

@@ -43,6 +43,7 @@ struct GemmProgram {
   // tile origin + (halo_dw0, halo_dh0); halo_pix = pixels of the whole box (all TN images)
   int halo_w, halo_h, halo_dw0, halo_dh0, halo_pix;
   int halo_stride, halo_ring;   // bytes between halo buffers (box rounded up to 1 KB), number of buffers
+  int run_cols;                 // conv64 second generation: accumulator columns = flattened halo run of a tile
   int raster_n;         // MODE 0: blockIdx.x = column tile, blockIdx.y = row tile
   int debug_skip;       // conv64.cu diagnostics (OBMAN_CONV64_DEBUG), 0 in normal operation
 };
@@ -57,6 +58,7 @@ struct GemmEpilogue {
   int accumulate;         // atomicAdd into out instead of store
   // row -> element offset: plain: row * ld ; spatial: n*sN + h*sH + w*sW  (+ column)
   long long ld, sN, sH, sW;
+  float* colsum;          // weight-gradient kernels: per-channel sum of dY over all pixels (atomicAdd), nullable
   // diagnostics (obman_debug_trace): 16 clock64 stamps per CTA, NULL in normal operation
   long long* trace;
   long long trace_cap;

@@ -615,6 +615,16 @@ __device__ __forceinline__ void split_column(uint32_t grp, int lane, uint32_t* h
 #pragma unroll
   for (int p = 0; p < 16; ++p) split_bf16x2(lds_f32(a + (2 * p) * 128), lds_f32(a + (2 * p + 1) * 128), hi[p], lo[p]);
 }
+// same, also adding the 32 raw values to `sum` (column sum of dY = the BatchNorm-beta / bias gradient, for free)
+__device__ __forceinline__ void split_column_sum(uint32_t grp, int lane, uint32_t* hi, uint32_t* lo, float& sum) {
+  const uint32_t a = grp + (uint32_t)lane * 4u;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const float v0 = lds_f32(a + (2 * p) * 128), v1 = lds_f32(a + (2 * p + 1) * 128);
+    sum += v0 + v1;
+    split_bf16x2(v0, v1, hi[p], lo[p]);
+  }
+}
 
 template <int BN, int SWAP, int OCC>
 __global__ void __launch_bounds__(WgradCfg<BN, SWAP, OCC>::THREADS, OCC)
@@ -749,6 +759,9 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
     const int r = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const int a_groups = SWAP ? valid_groups : BM / 32;
+    // dY is the A operand here: the CTAs of column tile 0 also accumulate its column sums (d beta / d bias)
+    const bool csum_on = !SWAP && epi.colsum != nullptr && (blockIdx.x % prog.n_tiles) == 0;
+    float csum = 0.f;
     for (int it = 0; it < n_iters; ++it) {
       const int rs = it % R, cs = it % C;
       mbar_wait(&full[rs], (it / R) & 1);
@@ -759,7 +772,8 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
       if (r == 0 && it == TRACE_IT) trace_stamp(epi, 11);
       uint32_t hi[16], lo[16];
       if (q < a_groups) {
-        split_column(smem_u32(raw_a(rs)) + q * 4096, lane, hi, lo);
+        if (!SWAP && csum_on) split_column_sum(smem_u32(raw_a(rs)) + q * 4096, lane, hi, lo, csum);
+        else split_column(smem_u32(raw_a(rs)) + q * 4096, lane, hi, lo);
       } else {
 #pragma unroll
         for (int p = 0; p < 16; ++p) hi[p] = lo[p] = 0u;
@@ -773,6 +787,7 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
       mbar_arrive(&conv[cs]);
       if (r == 0 && it == TRACE_IT) trace_stamp(epi, 12);
     }
+    if (csum_on && m0 + r < prog.M) atomicAdd(epi.colsum + m0 + r, csum);
     if (SWAP == 2) wgrad_epilogue_swapped_stacked<BN>(tmem_base, accum, prog, epi, m0, n0, q, r);
     else gemm_epilogue<BN, SWAP ? 2 : 1>(smem, tmem_base, accum, prog, epi, m0, n0, 0, 0, 0, q, lane, r);
   } else {
@@ -780,13 +795,17 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
     const int g = warp - 6;
     const int n = g * 32 + lane;
     const int b_groups = SWAP ? BN / 32 : valid_groups;
+    // roles swapped: dY is the B operand; the CTAs of row tile 0 accumulate its column sums
+    const bool csum_on = SWAP && epi.colsum != nullptr && m0 == 0;
+    float csum = 0.f;
     for (int it = 0; it < n_iters; ++it) {
       const int rs = it % R, cs = it % C;
       mbar_wait(&full[rs], (it / R) & 1);
       mbar_wait(&empty[cs], ((it / C) & 1) ^ 1);
       uint32_t hi[16], lo[16];
       if (g < b_groups) {
-        split_column(smem_u32(raw_b(rs)) + g * 4096, lane, hi, lo);
+        if (csum_on) split_column_sum(smem_u32(raw_b(rs)) + g * 4096, lane, hi, lo, csum);
+        else split_column(smem_u32(raw_b(rs)) + g * 4096, lane, hi, lo);
       } else {
 #pragma unroll
         for (int p = 0; p < 16; ++p) hi[p] = lo[p] = 0u;
@@ -811,6 +830,7 @@ wgrad_bf16_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog,
       fence_proxy_async_smem();
       mbar_arrive(&conv[cs]);
     }
+    if (csum_on && n0 + n < prog.N) atomicAdd(epi.colsum + n0 + n, csum);
   }
   tc_fence_before();
   __syncthreads();
@@ -1394,8 +1414,10 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
                                 const float* x, int h_in, int w_in, int c_in, int in_step, long long x_sN,
                                 long long x_sH, long long x_sW, int num_taps,
                                 const int* tap_dh, const int* tap_dw, const int* tap_phase, float* dw,
-                                int passes, void* stream) {
+                                float* dy_colsum, int passes, void* stream) {
   OBMAN_REQUIRE(dy && x && dw && tap_dh && tap_dw, "obman_wgrad_nhwc: null argument");
+  OBMAN_REQUIRE(dy_colsum == nullptr || passes == OBMAN_PREC_3XBF16,
+                "obman_wgrad_nhwc: the fused column sum of dy exists on the 3xBF16 path only");
   OBMAN_REQUIRE(n_img > 0 && h_out > 0 && w_out > 0 && h_in > 0 && w_in > 0, "obman_wgrad_nhwc: bad sizes");
   OBMAN_REQUIRE(c_out > 0 && c_in > 0 && c_out % 32 == 0 && c_in % 32 == 0,
                 "obman_wgrad_nhwc: c_out=%d and c_in=%d must be multiples of 32", c_out, c_in);
@@ -1493,6 +1515,8 @@ extern "C" int obman_wgrad_nhwc(const float* dy, int n_img, int h_out, int w_out
   GemmEpilogue epi;
   memset(&epi, 0, sizeof(epi));
   epi.out = dw;
+  epi.colsum = dy_colsum;
+  if (dy_colsum) cudaMemsetAsync(dy_colsum, 0, sizeof(float) * (size_t)c_out, st);
   epi.alpha = 1.f;
   epi.accumulate = splits > 1;
   epi.ld = ld;

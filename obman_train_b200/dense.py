@@ -185,9 +185,10 @@ def conv_nhwc(x, w, c_out, taps, in_step, out, h_out, w_out, out_strides=None, o
     return out
 
 
-def wgrad_nhwc(dy, x, taps, in_step, dw_out, passes=3, algo_k=None, x_geom=None):
+def wgrad_nhwc(dy, x, taps, in_step, dw_out, passes=3, algo_k=None, x_geom=None, dy_colsum=None):
     """dw_out (c_out, num_taps*c_in) = sum over pixels dy (N,Ho,Wo,c_out) x shifted x (N,H,W,c_in); the tap
-    order is the weight-slot order (taps = (dh, dw, phase, slot) with slot == position).  ``x_geom`` as in conv_nhwc."""
+    order is the weight-slot order (taps = (dh, dw, phase, slot) with slot == position).  ``x_geom`` as in conv_nhwc.
+    ``dy_colsum`` (c_out,), 3xBF16 only: also receives the per-channel sum of dy (fused into the operand split)."""
     _chk(dy, "dy"); _chk(x, "x"); _chk(dw_out, "dw")
     n_img, h_out, w_out, c_out = dy.shape
     if x_geom is None:
@@ -203,15 +204,16 @@ def wgrad_nhwc(dy, x, taps, in_step, dw_out, passes=3, algo_k=None, x_geom=None)
     _tc_call(2.0 * n_img * h_out * w_out * c_out * k_eff,
              "obman_wgrad_nhwc", ptr(dy), n_img, h_out, w_out, c_out, ptr(x), h_in, w_in, c_in,
              int(in_step), xs[0], xs[1], xs[2], len(dh), _ints(dh), _ints(dw),
-             _ints(phase) if phase is not None else None, ptr(dw_out), int(passes), stream_ptr(),
+             _ints(phase) if phase is not None else None, ptr(dw_out), ptr(dy_colsum), int(passes), stream_ptr(),
              tag="n%d %dx%d c%d->%d taps%d" % (n_img, h_out, w_out, c_in, c_out, len(dh)))
     return dw_out
 
 
-def wgrad_matrix(dy, x, dw_out=None, passes=3):
+def wgrad_matrix(dy, x, dw_out=None, passes=3, dy_colsum=None):
     """dw[N,K] = dy[M,N]^T @ x[M,K]; N and K (the padded row lengths) multiples of 32."""
     M, N = dy.shape
     K = x.shape[1]
     if dw_out is None:
         dw_out = torch.empty((N, K), device=dy.device, dtype=torch.float32)
-    return wgrad_nhwc(dy.view(1, 1, M, N), x.view(1, 1, M, K), ([0], [0], None, [0]), 1, dw_out, passes)
+    return wgrad_nhwc(dy.view(1, 1, M, N), x.view(1, 1, M, K), ([0], [0], None, [0]), 1, dw_out, passes,
+                      dy_colsum=dy_colsum)

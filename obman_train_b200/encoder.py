@@ -140,10 +140,13 @@ class _Unit(object):
             streams.join(streams.CHAIN)
         return gx
 
-    def wgrad(self, g, x, passes=3):
+    def wgrad(self, g, x, passes=3, colsum_out=None):
+        """Raw weight gradient; ``colsum_out`` (O,) additionally receives the per-channel sum of ``g`` (3xBF16 path:
+        accumulated by the threads that split ``g`` for the tensor cores, no separate pass over the gradient)."""
         dwraw = _empty(self.O, self.slots * self.Ip)
         dense.wgrad_nhwc(g, x, self.taps, self.in_step, dwraw, passes=passes,
-                         algo_k=147 if self.stem else None, x_geom=stem_view(x) if self.stem else None)
+                         algo_k=147 if self.stem else None, x_geom=stem_view(x) if self.stem else None,
+                         dy_colsum=colsum_out)
         return dwraw
 
     def finish(self, dwraw, gbeta_sum):
@@ -261,9 +264,14 @@ class _EncoderFn(torch.autograd.Function):
             keep.extend((g, x))
             streams.fork()  # g was produced on the current stream
             with streams.on_aux():
-                if gb is None:
-                    gb = colsum(rows, u.O, g)
-                grads[id(u)] = u.finish(u.wgrad(g, x, pw), gb)
+                if gb is None and pw == dense.BF16X3:
+                    gb = _empty(u.O)
+                    dwraw = u.wgrad(g, x, pw, colsum_out=gb)   # d beta comes out of the weight-gradient kernel
+                else:
+                    if gb is None:
+                        gb = colsum(rows, u.O, g)
+                    dwraw = u.wgrad(g, x, pw)
+                grads[id(u)] = u.finish(dwraw, gb)
             return gb
 
         for bidx, (u1, u2, ud, x, a, out, h, w_) in reversed(list(enumerate(blocks))):
@@ -302,7 +310,11 @@ class _EncoderFn(torch.autograd.Function):
             DEBUG["g_p"] = g2.clone()
             DEBUG["g_c1"] = gc1.clone()
         u0 = units[0]
-        grads[id(u0)] = u0.finish(u0.wgrad(gc1, xs, pw), colsum(B * (H // 2) * (W // 2), 64, gc1))
+        if pw == dense.BF16X3:
+            gb0 = _empty(64)
+            grads[id(u0)] = u0.finish(u0.wgrad(gc1, xs, pw, colsum_out=gb0), gb0)
+        else:
+            grads[id(u0)] = u0.finish(u0.wgrad(gc1, xs, pw), colsum(B * (H // 2) * (W // 2), 64, gc1))
         streams.join()
         del keep
         outs = [None]

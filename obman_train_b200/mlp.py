@@ -231,6 +231,9 @@ class _PointDecoderFn(torch.autograd.Function):
             keep.extend((g, h))
             streams.fork()
             with streams.on_aux():
+                if pw == dense.BF16X3:
+                    gsum = _empty(g.shape[1])       # over the padded width; finish reads the first C entries
+                    return layer.finish(dense.wgrad_matrix(g, h, passes=pw, dy_colsum=gsum), gsum)
                 return layer.finish(dense.wgrad_matrix(g, h, passes=pw), colsum(g, C))
 
         if not (gy.is_cuda and gy.dtype == torch.float32):

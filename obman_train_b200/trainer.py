@@ -59,6 +59,7 @@ class _GradSink(object):
         if a is None or b is None:
             return
         lo, hi = a[0], b[0] + b[1]
+        hi = min(t.numel, (hi + 63) // 64 * 64)   # up to the slot boundary (padding entries are zero and stay zero)
         # every parameter slot inside the range must have been written by the encoder
         for ptr_, (off, n, _) in self.by_ptr.items():
             if lo <= off < hi and ptr_ not in self.written:
@@ -68,7 +69,13 @@ class _GradSink(object):
         src = producer_stream if producer_stream is not None else torch.cuda.current_stream()
         self.comm_stream.wait_stream(src)
         with torch.cuda.stream(self.comm_stream):
-            dist.all_reduce(t.flat_g[lo:hi], op=dist.ReduceOp.SUM)
+            if not t.skip_allreduce:
+                dist.all_reduce(t.flat_g[lo:hi], op=dist.ReduceOp.SUM)
+            if t.adam_per_range:
+                # the optimiser step of this range follows its all-reduce on the communication stream, under the rest
+                # of the backward pass (nothing later in the step reads these parameters: the forward pass folded its
+                # own copies of the weights, and their gradients are complete)
+                t.adam_range(lo, hi)
         self.reduced.append((lo, hi))
 
 
@@ -110,6 +117,10 @@ class FlatAdamTrainer(object):
         # overlap_allreduce: the layer3 + layer4 range (94 % of an encoder) is all-reduced under the rest of backward
         self.direct_grads = direct_grads and dev.type == "cuda"
         self.overlap_allreduce = overlap_allreduce
+        # Adam per all-reduced range (bucketed optimiser): the early range is updated on the communication stream as
+        # soon as it is reduced, the rest after the backward pass; False = one Adam launch over the whole buffer
+        self.adam_per_range = True
+        self.skip_allreduce = False   # measurement knob (bench.py: step time without the exchange)
         self.offsets = offsets
         self._sink = _GradSink(self) if self.direct_grads else None
         self.step_count = 0
@@ -134,6 +145,7 @@ class FlatAdamTrainer(object):
         # an add kernel per parameter) and gathered into the flat buffer with one fused multi-tensor copy.
         for p in self.params:
             p.grad = None
+        self._begin_step()
         if self._sink is not None:
             from . import encoder
             self._sink.begin()
@@ -161,30 +173,53 @@ class FlatAdamTrainer(object):
         for v, p in zip(self.grad_views, self.params):
             p.grad = v
 
-    def all_reduce_grads(self):
-        """The only data-path collective of the step: one sum all-reduce of the flat gradient buffer."""
-        if self.world_size > 1:
-            done = self._sink.reduced if self._sink is not None else []
-            for lo, hi in complement_ranges(done, self.numel):
-                dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM)
-            if done:  # ranges that went out early on the communication stream
-                torch.cuda.current_stream().wait_stream(self._sink.comm_stream)
-                self._sink.reduced = []
-
-    def reduce_and_update(self):
-        self.all_reduce_grads()
-        self.adam_update()
-
-    def adam_update(self):
-        if not self.flat_p.is_cuda:
-            raise RuntimeError("FlatAdamTrainer.adam_update: the fused Adam kernel needs CUDA buffers (no CPU path)")
-        capturing = torch.cuda.is_current_stream_capturing()
-        if not capturing:
+    def _begin_step(self):
+        """The step number enters the Adam kernels through device memory; with per-range updates the first of them
+        runs in the middle of the backward pass, so the counter advances at the START of a step (a captured graph gets
+        it from ``replay``)."""
+        self._pending_ranges = None
+        if self.flat_p.is_cuda and not torch.cuda.is_current_stream_capturing():
             self.step_count += 1
             self._push_hyper()
-        call("obman_adam_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-             self.numel, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-             float(self.weight_decay), ptr(self._hyper_dev), 1.0 / float(self.world_size), stream_ptr())
+        self._stepped = True
+
+    def all_reduce_grads(self):
+        """The only data-path collective of the step: a sum all-reduce of the flat gradient buffer - the range that
+        went out early on the communication stream (see _GradSink.stage_done) plus one launch per remaining
+        contiguous range.  Returns the ranges reduced here."""
+        done = list(self._sink.reduced) if self._sink is not None else []
+        rest = complement_ranges(done, self.numel)
+        if self.world_size > 1 and not self.skip_allreduce:
+            for lo, hi in rest:
+                dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.SUM)
+        if done:  # ranges that went out early on the communication stream (and, per range, their Adam update)
+            torch.cuda.current_stream().wait_stream(self._sink.comm_stream)
+            self._sink.reduced = []
+        return rest, done
+
+    def reduce_and_update(self):
+        rest, done = self.all_reduce_grads()
+        if done and self.adam_per_range:
+            for lo, hi in rest:
+                self.adam_range(lo, hi)
+        else:
+            self.adam_range(0, self.numel)
+
+    def adam_range(self, lo, hi):
+        """Fused Adam on the slots [lo, hi) of the flat buffers (slot boundaries are 256-byte aligned)."""
+        call("obman_adam_step", ptr(self.flat_p) + 4 * lo, ptr(self.flat_g) + 4 * lo, ptr(self.exp_avg) + 4 * lo,
+             ptr(self.exp_avg_sq) + 4 * lo, hi - lo, float(self.lr), float(self.betas[0]), float(self.betas[1]),
+             float(self.eps), float(self.weight_decay), ptr(self._hyper_dev), 1.0 / float(self.world_size), stream_ptr())
+
+    def adam_update(self):
+        """One fused Adam step over the whole flat buffer (advances the step counter; ``step`` / ``replay`` use the
+        per-range form instead)."""
+        if not self.flat_p.is_cuda:
+            raise RuntimeError("FlatAdamTrainer.adam_update: the fused Adam kernel needs CUDA buffers (no CPU path)")
+        if not torch.cuda.is_current_stream_capturing():
+            self.step_count += 1
+            self._push_hyper()
+        self.adam_range(0, self.numel)
 
     def _push_hyper(self):
         # fill kernels carry the value as a launch argument: safe with many steps in flight (a pinned staging

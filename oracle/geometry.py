@@ -92,7 +92,7 @@ def contact_loss(hand, obj, obj_faces, zones=None, contact_thresh=5, contact_mod
     vertex ids (assets/contact_zones.pkl), required for contact_zones == "zones".
     Returns (missed_loss, penetr_loss, contact_info, metrics).
     """
-    faces = torch.as_tensor(np.asarray(obj_faces).astype(np.int64))
+    faces = torch.as_tensor(np.asarray(obj_faces).astype(np.int64)).to(obj.device)
     P = pairwise_sqdist(hand, obj)  # (B,778,N)
     mins12, idx12 = P.min(1)
     mins21, idx21 = P.min(2)
@@ -138,9 +138,9 @@ def contact_loss(hand, obj, obj_faces, zones=None, contact_thresh=5, contact_mod
     elif contact_zones == "zones":
         matching = torch.zeros_like(missed_mask)
         for _, zone_idxs in zones.items():
-            zone_idxs = torch.as_tensor(np.asarray(zone_idxs).astype(np.int64))
+            zone_idxs = torch.as_tensor(np.asarray(zone_idxs).astype(np.int64)).to(hand.device)
             _, arg = mins21[:, zone_idxs].min(1)
-            matching[torch.arange(hand.shape[0]), zone_idxs[arg]] = True
+            matching[torch.arange(hand.shape[0], device=hand.device), zone_idxs[arg]] = True
         missed_mask = missed_mask & matching
     elif contact_zones != "all":
         raise ValueError("contact_zones {} not in [tips|zones|all]".format(contact_zones))
@@ -158,7 +158,7 @@ def contact_loss(hand, obj, obj_faces, zones=None, contact_thresh=5, contact_mod
 
 def edge_loss(verts, faces):
     """edge_loss (atlasbranch.py:153-167): mean |e - mean_b(e)| over squared edge lengths."""
-    faces = torch.as_tensor(np.asarray(faces).astype(np.int64))
+    faces = torch.as_tensor(np.asarray(faces).astype(np.int64)).to(verts.device)
     a, b, c = verts[:, faces[:, 0]], verts[:, faces[:, 1]], verts[:, faces[:, 2]]
     la = ((b - a) ** 2).sum(2)
     lb = ((c - b) ** 2).sum(2)
@@ -192,7 +192,7 @@ def laplacian_loss(verts, L):
     """LaplacianLoss.__call__ (laplacianloss.py:36-41): mean over all B*N rows of ||(L V_b)_i||_2.
     ``L`` from laplacian_matrix (numpy or tensor); differentiable in ``verts`` (the reference's backward is
     L^T g = L g, :137-150, which is what autograd gives here)."""
-    Lt = torch.as_tensor(L, dtype=verts.dtype)
+    Lt = torch.as_tensor(L, dtype=verts.dtype).to(verts.device)
     lx = torch.einsum("ij,bjc->bic", Lt, verts)
     return torch.sqrt((lx ** 2).sum(2)).mean(), lx
 

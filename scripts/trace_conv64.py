@@ -13,7 +13,7 @@ from obman_train_b200._lib import call  # noqa: E402
 B = int(os.environ.get("PROF_B", "256"))
 NAMES = {0: "kernel body (thread 0)", 1: "producer: wait halo buffer free", 2: "splitter: wait halo landed",
          3: "splitter: wait A stage free", 4: "splitter: in-place split + barrier", 5: "splitter: loop total",
-         6: "MMA: wait A stage written", 7: "MMA: wait accumulator drained", 8: "MMA: loop total",
+         13: "MMA: wait A stage written", 7: "MMA: wait accumulator drained", 8: "MMA: loop total",
          9: "epilogue: wait accumulator complete", 10: "epilogue: loop total", 11: "MMA: wait weights", 12: "tiles per CTA"}
 
 

@@ -90,10 +90,16 @@ def test_two_gpu_shards_equal_one_gpu_batch(tmp_path, use_graph):
     print("gradient: L2 rel %.2e, max rel %.2e" % (rel, worst))
     assert rel < 1e-5 and worst < 1e-5
     assert abs(0.5 * (r0["loss"] + r1["loss"]).item() - loss.item()) <= 1e-5 * abs(loss.item())
-    # parameters: the first Adam step moves every entry by ~lr * sign(g); compare the UPDATE norm-wise (entries whose
-    # gradient is within rounding of zero may legitimately move the other way) and the parameters themselves tightly
+    # parameters: the first Adam step moves every entry by ~lr * g / (|g| + eps), i.e. by ~lr * sign(g): an entry whose
+    # gradient is within rounding of zero may legitimately move the other way (|difference| <= 2 lr), everything else
+    # moves identically.  Hence: an absolute bound of 2 lr everywhere, almost all entries equal to 1e-6 relative, and the
+    # update equal norm-wise.
     p1 = single.flat_p.cpu()
-    upd_rel = ((r0["p"] - p1).norm() / (p1 - p0).norm()).item()
-    par_rel = ((r0["p"] - p1).norm() / p1.norm()).item()
-    print("update rel %.2e, parameter rel %.2e" % (upd_rel, par_rel))
-    assert par_rel < 1e-6 and upd_rel < 2e-2
+    diff = (r0["p"] - p1).abs()
+    upd_rel = (diff.norm() / (p1 - p0).norm()).item()
+    moved = (p1 - p0).abs() > 0
+    off = (diff > 1e-6 * p1.abs() + 1e-9) & moved
+    frac_off = off.float().sum().item() / max(1.0, moved.float().sum().item())
+    print("update rel %.2e, max |dp| %.2e (lr 1e-4), entries off %.2e" % (upd_rel, diff.max().item(), frac_off))
+    assert diff.max().item() <= 2.1e-4
+    assert frac_off < 2e-2 and upd_rel < 5e-2

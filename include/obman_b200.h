@@ -183,6 +183,12 @@ int obman_maxpool_bwd(const float* gout, const unsigned char* idx, int B, int H,
 int obman_meanpool_fwd(const float* x, int B, int P, int C, float* out, void* stream);
 int obman_meanpool_bwd(const float* gout, const float* x, int B, int P, int C, float* gx,
                        void* stream);
+/* obman_fold_conv (packed bf16 layout, BatchNorm present, square filters K x K) for up to 24 units in ONE launch: every
+ * table is a HOST array of n_units entries (device pointers / sizes of unit u); wft[u] may be NULL. */
+int obman_fold_conv_batch(int n_units, const float* const* w, const float* const* gamma, const float* const* beta,
+                          const float* const* mean, const float* const* var, float eps, const int* O, const int* I,
+                          const int* K, const int* Ip, const int* stem, float* const* wf, float* const* wft,
+                          float* const* shift, float* const* scale, float* const* rstd, void* stream);
 /* out[c] = sum_r x[r*ld + c]  (bias / BatchNorm-beta gradients). */
 int obman_colsum(const float* x, long long rows, int C, long long ld, float* out, void* stream);
 /* Raw weight gradient dwraw (O rows of stride dw_ld, KH*KW*Ip used) -> gw (O,I,KH,KW) = scale*dwraw and
@@ -193,10 +199,11 @@ int obman_bn_wgrad_finish(const float* dwraw, long long dw_ld, const float* w, c
                           const float* gbeta_sum, int O, int I, int KH, int KW, int Ip, int stem,
                           float* gw, float* ggamma, float* gbeta, float* gcbias, void* stream);
 /* AtlasNet decoder layer 1 after the conv1 split (atlasbranch.py:117-131 + atlasutils.py:65-67):
- * out[b,n,c] = relu(sum_{k<3} grid[b*grid_bstride + 3n + k] * W1[c*ldw + k] + F[b*C + c]) (c < C), 0 (C <= c < ld);
+ * out[b,n,c] = [relu](sum_{k<3} grid[b*grid_bstride + 3n + k] * W1[c*ldw + k] + F[b*C + c]) (c < C), 0 (C <= c < ld);
+ * relu = 0 gives the pre-activation (BatchNorm with batch statistics normalises it afterwards);
  * W1 = BatchNorm-folded conv1 weights (C, ldw) in fp32 (its first three input channels are the grid point). */
 int obman_pointmlp_l1_fwd(const float* grid, long long grid_bstride, const float* W1, int ldw, const float* F,
-                          int B, int N, int C, int ld, float* out, void* stream);
+                          int B, int N, int C, int ld, int relu, float* out, void* stream);
 /* dst (rows, ld_dst) = alpha * src[:, :C] where mask > 0 (mask NULL = everywhere), zero in columns C .. ld_dst-1:
  * pad / scale / ReLU-mask glue of the Linear and decoder backward passes in one launch. */
 int obman_pad_scale_mask(const float* src, long long ld_src, const float* mask, long long ld_mask, long long rows,
@@ -230,6 +237,28 @@ int obman_edge_loss_bwd(const float* V, const int* faces, const int* vf, const f
  * over the batch of the per-sample IoU of the thresholded maps; auc[0] = their trapezoid over the thresholds. */
 int obman_contact_iou(const float* gt_dists, const float* pred_dists, int B, int P, const float* threshs,
                       int n_thresh, float* iou_ws, float* batch_ious, float* auc, void* stream);
+
+/* ---- BatchNorm with batch statistics (csrc/bn_train.cu) ---------------------------------------------------------
+ * Training WITHOUT --freeze_batchnorm (model.train(), epochpass3d.py:48-52): torch.nn.BatchNorm2d / BatchNorm1d in
+ * training mode around the convolutions of bases/resnet.py:25-54,154-171.  z = raw convolution output, (rows, C) with
+ * row stride ld (NHWC flattened), C % 4 == 0 and <= 1024.  partial: workspace of 2 * C * obman_bn_chunks(rows, C) floats.
+ *
+ * obman_bn_stats: mean / rstd (= 1 / sqrt(biased var + eps)) of z per channel, scale = gamma * rstd, shift = beta -
+ * mean * scale (gamma / beta nullable = 1 / 0), and when running_mean / running_var are given their update
+ * r = (1 - momentum) * r + momentum * {mean, unbiased var}. */
+int obman_bn_chunks(long long rows, int C);
+int obman_bn_stats(const float* z, long long rows, int C, long long ld, const float* gamma, const float* beta,
+                   float eps, float momentum, float* partial, float* mean, float* rstd, float* scale, float* shift,
+                   float* running_mean, float* running_var, void* stream);
+/* y = [relu](z * scale[c] + shift[c] [+ addend]) (addend: same layout as z, nullable). */
+int obman_bn_apply_fwd(const float* z, long long rows, int C, long long ld, const float* scale, const float* shift,
+                       const float* addend, int relu, float* y, void* stream);
+/* Backward through y = bn(z) for the incoming gradient g' = g where mask_src > 0 (the ReLU that follows; mask_src
+ * nullable): sum_g[c] = sum g' (d beta), sum_gz[c] = sum g' * zhat (d gamma), dz = scale * (g' - sum_g / rows -
+ * zhat * sum_gz / rows); gmasked (nullable) receives g' (gradient of a residual branch added before the ReLU). */
+int obman_bn_bwd(const float* g, const float* mask_src, const float* z, long long rows, int C, long long ld,
+                 const float* mean, const float* rstd, const float* scale, float* partial, float* sum_g,
+                 float* sum_gz, float* dz, float* gmasked, void* stream);
 
 /* ---- Scalar-loss stage (csrc/loss_head.cu) -------------------------------------------------------------------
  * Tables (a, b, ga, p, q, rows, width, ... slot, group) are HOST arrays of n_terms entries whose pointer entries are

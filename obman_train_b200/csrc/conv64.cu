@@ -305,9 +305,9 @@ conv64_persistent_kernel(const __grid_constant__ GemmMaps maps, const GemmProgra
 //   * two MMAs per K = 16 step, both with A = [w_hi; w_lo]: B = a_hi, then B = a_lo.  Accumulator lanes 0-63 hold
 //     w_hi * (a_hi + a_lo), lanes 64-127 hold w_lo * (a_hi + a_lo); the epilogue adds the two halves (all four bf16
 //     products, one more than the 3xBF16 scheme needs).
-// Warp roles (320 threads): 0 = TMA producer, 1 = MMA issuer, 2-5 = converters, 6-9 = epilogue.  Tensor memory: two
+// Warp roles (448 threads): 0 = TMA producer, 1 = MMA issuer, 2-5 = converters, 6-13 = epilogue (two groups of four).  Tensor memory: two
 // accumulators of N <= 256 columns.
-constexpr int P64V2_THREADS = 320;
+constexpr int P64V2_THREADS = 448;
 
 __global__ void __launch_bounds__(P64V2_THREADS, 1)
 conv64_v2_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, const GemmEpilogue epi, int total_tiles) {
@@ -320,8 +320,8 @@ conv64_v2_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wt = smem;
   uint8_t* halo_base = smem + n_iters * P64_WT_TILE;
-  uint8_t* staging = halo_base + RA * prog.halo_stride;      // 2 x 4 KB: 16 pixels x 64 channels fp32, double-buffered
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 8192);
+  uint8_t* staging = halo_base + RA * prog.halo_stride;      // 2 groups x [2 parts][16 pixels][64 channels] fp32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 16384);
   uint64_t* wfull = bars;                    // weights landed
   uint64_t* afull = bars + 1;                // [RA] halo box landed (TMA)
   uint64_t* bconv = afull + P64_RA_MAX;      // [RA] halo box converted to bf16 planes
@@ -335,7 +335,7 @@ conv64_v2_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, 
   if (threadIdx.x == 0) {
     mbar_init(wfull, 1);
     for (int i = 0; i < RA; ++i) { mbar_init(&afull[i], 1); mbar_init(&bconv[i], 128); mbar_init(&afree[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&accfull[i], 1); mbar_init(&accfree[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&accfull[i], 1); mbar_init(&accfree[i], 256); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -347,6 +347,8 @@ conv64_v2_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, 
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   auto halo = [&](int i) { return halo_base + i * prog.halo_stride; };
+  const bool timed = epi.trace != nullptr;
+  const long long t_start = clock64();
 
   if (warp == 0) {
     // ===== TMA producer: the weights once, then one halo box per (tile, K block) =====
@@ -362,16 +364,18 @@ conv64_v2_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, 
           tma_load_2d(dst + 4096, &maps.b, wfull, kc + 16, 0); // 64 rows x 64 B of bf16 lo
         }
       int g = 0;
+      long long w_afree = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int n_img0, h0, w0;
         tile_coords(prog, tile, n_img0, h0, w0);
         for (int kb = 0; kb < KB; ++kb, ++g) {
           const int a = g % RA;
-          mbar_wait(&afree[a], ((g / RA) & 1) ^ 1);
+          mbar_wait_timed(&afree[a], ((g / RA) & 1) ^ 1, timed, w_afree);
           mbar_arrive_expect_tx(&afull[a], (uint32_t)prog.halo_bytes);
           tma_load_4d(halo(a), &maps.a[0], &afull[a], kb * BK, w0 + prog.halo_dw0, h0 + prog.halo_dh0, n_img0);
         }
       }
+      trace_put(epi, 1, w_afree);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -379,14 +383,16 @@ conv64_v2_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, 
     const uint32_t plane = (uint32_t)P * 16u;            // bytes between consecutive 16-byte K chunks of a pixel row
     mbar_wait(wfull, 0);
     int g = 0, ti = 0;
+    long long w_bconv = 0, w_accfree = 0;
+    const long long t_loop = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int acc = ti & 1;
-      mbar_wait(&accfree[acc], ((ti >> 1) & 1) ^ 1);
+      mbar_wait_timed(&accfree[acc], ((ti >> 1) & 1) ^ 1, timed, w_accfree);
       tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)(acc * 256);
       for (int kb = 0; kb < KB; ++kb, ++g) {
         const int a = g % RA;
-        mbar_wait(&bconv[a], (g / RA) & 1);
+        mbar_wait_timed(&bconv[a], (g / RA) & 1, timed, w_bconv);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t box = smem_u32(halo(a));
@@ -411,14 +417,19 @@ conv64_v2_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, 
         __syncwarp();
       }
     }
+    if (lane == 0) {
+      trace_put(epi, 13, w_bconv); trace_put(epi, 7, w_accfree); trace_put(epi, 8, clock64() - t_loop); trace_put(epi, 12, ti);
+    }
   } else if (warp < 6) {
     // ===== converters: fp32 [pixel][32 ch] (SW128 rows as TMA wrote them) -> eight bf16 planes, in place =====
     const int sid = threadIdx.x - 64;            // 0 .. 127
     int g = 0;
+    long long w_afull = 0;
+    const long long t_loop = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < KB; ++kb, ++g) {
         const int a = g % RA;
-        mbar_wait(&afull[a], (g / RA) & 1);
+        mbar_wait_timed(&afull[a], (g / RA) & 1, timed, w_afull);
         const uint32_t box = smem_u32(halo(a));
         uint32_t hi[2][16], lo[2][16];
 #pragma unroll
@@ -451,17 +462,23 @@ conv64_v2_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, 
         mbar_arrive(&bconv[a]);
       }
     }
+    if (sid == 0) { trace_put(epi, 2, w_afull); trace_put(epi, 5, clock64() - t_loop); }
   } else {
-    // ===== epilogue: warps 6..9, TMEM lane quadrant = warp % 4 =====
-    // lanes 0-63 of the accumulator = w_hi part of channels 0-63, lanes 64-127 = w_lo part; 16 pixel columns per round
-    // go through a (16 pixels x 64 channels) fp32 staging tile: lo-part warps store, hi-part warps add, then all four
-    // warps walk the pixels with 16 lanes x float4 per pixel (256 contiguous bytes per store instruction and row)
+    // ===== epilogue: warps 6..13 = two groups of four (TMEM lane quadrant = warp % 4), alternating 16-column rounds =====
+    // lanes 0-63 of the accumulator = w_hi part of channels 0-63, lanes 64-127 = w_lo part.  In a round every warp
+    // stores its 32 channels x 16 pixel columns into the group's staging tile ([part][pixel][64 channels] fp32), one
+    // barrier later the four warps walk the pixels with 16 lanes x float4 per pixel, adding the two parts on the way
+    // (256 contiguous bytes per output row and store instruction).
+    constexpr int RW2 = 16;
     const int q = warp & 3;
-    const int et = threadIdx.x - 192;            // 0 .. 127
+    const int group = (warp - 6) >> 2;           // 0 | 1
+    const int et = (threadIdx.x - 192) & 127;    // 0 .. 127 inside the group
     const int part = q >> 1;                     // 0: lanes 0-63 (hi), 1: lanes 64-127 (lo)
     const int ch = (q & 1) * 32 + lane;          // channel of this TMEM lane
-    const int px_sub = et >> 4;                  // pixel (of 8) this thread stores in each half round
+    const int px_sub = et >> 4;                  // pixel (of 8) this thread stores in each half of a round
     const int c4 = (et & 15) * 4;                // its four channels
+    float* S = reinterpret_cast<float*>(staging + group * 8192);   // [2 parts][16 pixels][64 channels]
+    const float inv_hw = 1.f / (float)prog.halo_w, inv_hh = 1.f / (float)prog.halo_h;
     const bool ptr_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
                           reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0;
     float bias4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -469,77 +486,91 @@ conv64_v2_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, 
 #pragma unroll
       for (int e = 0; e < 4; ++e) if (c4 + e < prog.N) bias4[e] = __ldg(epi.bias + c4 + e);
     }
-    int ti = 0, round_idx = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    const int rounds = (NRUN + RW2 - 1) / RW2;
+    // addresses + residual / ReLU-mask operands of one round, fetched ONE ROUND AHEAD (a round is far shorter than a
+    // DRAM round trip; the first round of a tile is fetched before the wait for its accumulator)
+    struct RoundOps { long long roff[2]; float4 add4[2], msk4[2]; };
+    auto fetch = [&](int tile, int rr, RoundOps& o) {
       int n_img0, h0, w0;
       tile_coords(prog, tile, n_img0, h0, w0);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        // column j of the run = halo position (row j / halo_w over all images of the box, column j % halo_w);
+        // exact float reciprocals for j < 512
+        const int j = rr * RW2 + px_sub + 8 * e;
+        const int hr = (int)(((float)j + 0.5f) * inv_hw), tw = j - hr * prog.halo_w;
+        const int tn = (int)(((float)hr + 0.5f) * inv_hh), th = hr - tn * prog.halo_h;
+        const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
+        const bool ok = j < NRUN && tw < prog.TW && th < prog.TH && tn < prog.TN && n < prog.n_img && h < prog.h_out &&
+                        w < prog.w_out && c4 < prog.N;
+        o.roff[e] = ok ? n * epi.sN + h * epi.sH + w * epi.sW : -1;
+        epilogue_prefetch(epi, prog, o.roff[e], c4, ptr_ok, o.add4[e], o.msk4[e]);
+      }
+    };
+    int ti = 0;
+    long long w_accfull = 0;
+    const long long t_loop = clock64();
+    RoundOps cur, nxt;
+    if ((int)blockIdx.x < total_tiles) fetch(blockIdx.x, group & 1, cur);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int acc = ti & 1;
-      mbar_wait(&accfull[acc], (uint32_t)((ti >> 1) & 1));
+      mbar_wait_timed(&accfull[acc], (uint32_t)((ti >> 1) & 1), timed, w_accfull);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      for (int j0 = 0; j0 < NRUN; j0 += 16, ++round_idx) {
-        float* S = reinterpret_cast<float*>(staging + (round_idx & 1) * 4096);
-        // global row of the two pixels this thread will store (column j of the run = halo position (j / halo_w, j % halo_w))
-        long long roff[2];
-        float4 add4[2], msk4[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int j = j0 + px_sub + 8 * e;
-          const int hr = j / prog.halo_w, tw = j - hr * prog.halo_w;      // halo row (over all images of the box), column
-          const int tn = hr / prog.halo_h, th = hr - tn * prog.halo_h;
-          const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
-          const bool ok = tw < prog.TW && th < prog.TH && tn < prog.TN && n < prog.n_img && h < prog.h_out &&
-                          w < prog.w_out && c4 < prog.N;
-          roff[e] = ok ? n * epi.sN + h * epi.sH + w * epi.sW : -1;
-          epilogue_prefetch(epi, prog, roff[e], c4, ptr_ok, add4[e], msk4[e]);
-        }
-        uint32_t v[16];
+      // the groups take alternate rounds; which one starts alternates with the tile (odd round counts stay balanced)
+      for (int rr = (group + ti) & 1; rr < rounds; rr += 2) {
+        // next round of this group: in this tile, or the first one of the next tile
+        if (rr + 2 < rounds) fetch(tile, rr + 2, nxt);
+        else if (tile + (int)gridDim.x < total_tiles) fetch(tile + gridDim.x, (group + ti + 1) & 1, nxt);
+        const int j0 = rr * RW2;
+        uint32_t v[RW2];
         tmem_ld_32x16(lane_addr + (uint32_t)j0, v);
         tmem_ld_wait();
-        if (part == 1) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) S[i * 64 + ch] = __uint_as_float(v[i]);
-        }
-        named_barrier_sync(2, 128);
-        if (part == 0) {
+        for (int e = 0; e < 2; ++e)
+          asm volatile("" : "+f"(cur.msk4[e].x), "+f"(cur.msk4[e].y), "+f"(cur.msk4[e].z), "+f"(cur.msk4[e].w));
 #pragma unroll
-          for (int i = 0; i < 16; ++i) S[i * 64 + ch] += __uint_as_float(v[i]);
-        }
-        named_barrier_sync(2, 128);
+        for (int i = 0; i < RW2; ++i) S[(part * RW2 + i) * 64 + ch] = __uint_as_float(v[i]);
+        named_barrier_sync(2 + group, 128);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          if (roff[e] < 0) continue;
-          const float4 s4 = *reinterpret_cast<const float4*>(S + (px_sub + 8 * e) * 64 + c4);
-          float x[4] = {epi.alpha * s4.x + bias4[0], epi.alpha * s4.y + bias4[1], epi.alpha * s4.z + bias4[2],
-                        epi.alpha * s4.w + bias4[3]};
-          if (ptr_ok && (roff[e] & 3) == 0 && c4 + 3 < prog.N) {
-            x[0] += add4[e].x; x[1] += add4[e].y; x[2] += add4[e].z; x[3] += add4[e].w;
+          const long long roff = cur.roff[e];
+          if (roff < 0) continue;
+          const int px = px_sub + 8 * e;
+          const float4 s_hi = *reinterpret_cast<const float4*>(S + px * 64 + c4);
+          const float4 s_lo = *reinterpret_cast<const float4*>(S + (RW2 + px) * 64 + c4);
+          float x[4] = {epi.alpha * (s_hi.x + s_lo.x) + bias4[0], epi.alpha * (s_hi.y + s_lo.y) + bias4[1],
+                        epi.alpha * (s_hi.z + s_lo.z) + bias4[2], epi.alpha * (s_hi.w + s_lo.w) + bias4[3]};
+          if (ptr_ok && (roff & 3) == 0 && c4 + 3 < prog.N) {
+            x[0] += cur.add4[e].x; x[1] += cur.add4[e].y; x[2] += cur.add4[e].z; x[3] += cur.add4[e].w;
             if (epi.relu) {
 #pragma unroll
               for (int c = 0; c < 4; ++c) x[c] = fmaxf(x[c], 0.f);
             }
-            x[0] = msk4[e].x > 0.f ? x[0] : 0.f; x[1] = msk4[e].y > 0.f ? x[1] : 0.f;
-            x[2] = msk4[e].z > 0.f ? x[2] : 0.f; x[3] = msk4[e].w > 0.f ? x[3] : 0.f;
-            *reinterpret_cast<float4*>(epi.out + roff[e] + c4) = make_float4(x[0], x[1], x[2], x[3]);
+            x[0] = cur.msk4[e].x > 0.f ? x[0] : 0.f; x[1] = cur.msk4[e].y > 0.f ? x[1] : 0.f;
+            x[2] = cur.msk4[e].z > 0.f ? x[2] : 0.f; x[3] = cur.msk4[e].w > 0.f ? x[3] : 0.f;
+            *reinterpret_cast<float4*>(epi.out + roff + c4) = make_float4(x[0], x[1], x[2], x[3]);
           } else {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               if (c4 + c >= prog.N) break;
               float y = x[c];
-              if (epi.addend) y += epi.addend[roff[e] + c4 + c];
+              if (epi.addend) y += epi.addend[roff + c4 + c];
               if (epi.relu) y = fmaxf(y, 0.f);
-              if (epi.mask_src) y = epi.mask_src[roff[e] + c4 + c] > 0.f ? y : 0.f;
-              epi.out[roff[e] + c4 + c] = y;
+              if (epi.mask_src) y = epi.mask_src[roff + c4 + c] > 0.f ? y : 0.f;
+              epi.out[roff + c4 + c] = y;
             }
           }
         }
-        // the other staging buffer is used by the next round; this one is rewritten two rounds from now, after the
-        // two barriers of the next round
+        named_barrier_sync(2 + group, 128);   // the staging tile is rewritten by the group's next round
+        cur = nxt;
       }
       tc_fence_before();
       mbar_arrive(&accfree[acc]);
     }
+    if (et == 0) { trace_put(epi, 9 + 5 * group, w_accfull); trace_put(epi, 10 + 5 * group, clock64() - t_loop); }
   }
+  if (threadIdx.x == 0) trace_put(epi, 0, clock64() - t_start);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -657,10 +688,10 @@ int try_conv64(const float* x, int n_img, int h_in, int w_in, int c_in, long lon
       gen = (e && e[0] == '1') ? 1 : 2;
     }
     const int run = (((TN - 1) * HH + TH - 1) * HW + TW + 15) / 16 * 16;
+    auto smem2 = [&](int r) { return num_taps * KB * P64_WT_TILE + r * halo_stride + 16384 + 1024 + 512; };
     int ring2 = P64_RA_MAX;
-    auto smem2 = [&](int r) { return num_taps * KB * P64_WT_TILE + r * halo_stride + 8192 + 1024 + 512; };
     while (ring2 > 2 && smem2(ring2) > P64_SMEM_LIMIT) --ring2;
-    if (gen == 2 && run <= 256 && halo_pix <= 256 && smem2(ring2) <= P64_SMEM_LIMIT) {
+    if (gen == 2 && run >= 32 && run <= 256 && halo_pix <= 256 && smem2(ring2) <= P64_SMEM_LIMIT) {   // >= 2 epilogue rounds
       prog.run_cols = run;
       prog.halo_ring = ring2;
       static bool attr2 = false;

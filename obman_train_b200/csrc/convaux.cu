@@ -10,6 +10,7 @@
 //   bn_wgrad_finish  raw weight gradient -> gradients of conv weight (OIHW), gamma, beta
 //   adam             fused Adam step on a flat parameter buffer (torch.optim.Adam semantics, traineval.py:113-116)
 #include <cuda_bf16.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -75,15 +76,14 @@ __device__ __forceinline__ void store_packed_bf16(float* row, size_t k, float v)
   r16[blk * 64 + 32 + in] = l;
 }
 
-__global__ void __launch_bounds__(256)
-fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
-                 const float* __restrict__ gamma,
-                 const float* __restrict__ beta, const float* __restrict__ mean,
-                 const float* __restrict__ var, float eps, int O, int I, int KH, int KW, int Ip,
-                 int stem, int packed, float* __restrict__ wf, float* __restrict__ wf_lo, float* __restrict__ wft,
-                 float* __restrict__ wft_lo, float* __restrict__ shift, float* __restrict__ scale,
-                 float* __restrict__ rstd_out) {
-  const int o = blockIdx.x;
+__device__ __forceinline__ void
+fold_conv_row(int o, const float* __restrict__ w, const float* __restrict__ cbias,
+              const float* __restrict__ gamma,
+              const float* __restrict__ beta, const float* __restrict__ mean,
+              const float* __restrict__ var, float eps, int O, int I, int KH, int KW, int Ip,
+              int stem, int packed, float* __restrict__ wf, float* __restrict__ wf_lo, float* __restrict__ wft,
+              float* __restrict__ wft_lo, float* __restrict__ shift, float* __restrict__ scale,
+              float* __restrict__ rstd_out) {
   float s = 1.f, rs = 1.f;
   if (gamma) {
     rs = rsqrtf(var[o] + eps);
@@ -133,6 +133,43 @@ fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias,
     wf[(size_t)o * taps * Ip + k] = wf_lo ? h : v;
     if (wf_lo) wf_lo[(size_t)o * taps * Ip + k] = v - h;
   }
+}
+
+__global__ void __launch_bounds__(256)
+fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ cbias, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                 int O, int I, int KH, int KW, int Ip, int stem, int packed, float* __restrict__ wf,
+                 float* __restrict__ wf_lo, float* __restrict__ wft, float* __restrict__ wft_lo,
+                 float* __restrict__ shift, float* __restrict__ scale, float* __restrict__ rstd_out) {
+  fold_conv_row(blockIdx.x, w, cbias, gamma, beta, mean, var, eps, O, I, KH, KW, Ip, stem, packed, wf, wf_lo, wft, wft_lo,
+                shift, scale, rstd_out);
+}
+
+// All conv+BN units of an encoder in ONE launch (was one launch per unit, 20 per encoder and step): block b works on
+// output channel b - row0[u] of unit u, found through the prefix table.  Packed bf16 layout only.
+constexpr int FOLD_MAX_UNITS = 24;
+struct FoldBatch {
+  const float* w[FOLD_MAX_UNITS];
+  const float* gamma[FOLD_MAX_UNITS];
+  const float* beta[FOLD_MAX_UNITS];
+  const float* mean[FOLD_MAX_UNITS];
+  const float* var[FOLD_MAX_UNITS];
+  float* wf[FOLD_MAX_UNITS];
+  float* wft[FOLD_MAX_UNITS];     // nullable
+  float* shift[FOLD_MAX_UNITS];
+  float* scale[FOLD_MAX_UNITS];
+  float* rstd[FOLD_MAX_UNITS];
+  int row0[FOLD_MAX_UNITS + 1];   // first block of every unit (prefix sums of O)
+  int O[FOLD_MAX_UNITS], I[FOLD_MAX_UNITS], K[FOLD_MAX_UNITS], Ip[FOLD_MAX_UNITS], stem[FOLD_MAX_UNITS];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) fold_conv_batch_kernel(const __grid_constant__ FoldBatch t, float eps) {
+  int u = 0;
+  while (u + 1 < t.n && (int)blockIdx.x >= t.row0[u + 1]) ++u;
+  fold_conv_row((int)blockIdx.x - t.row0[u], t.w[u], nullptr, t.gamma[u], t.beta[u], t.mean[u], t.var[u], eps, t.O[u],
+                t.I[u], t.K[u], t.K[u], t.Ip[u], t.stem[u], 1, t.wf[u], nullptr, t.wft[u], nullptr, t.shift[u],
+                t.scale[u], t.rstd[u]);
 }
 
 // 3x3 stride-2 pad-1 max pooling, NHWC; idx = winning window position 0..8
@@ -385,7 +422,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // when grid_bstride != 0), F = feat * (s*W[:, 3:])^T + shift.
 __global__ void __launch_bounds__(256)
 pointmlp_l1_fwd_kernel(const float* __restrict__ grid, long long grid_bstride, const float* __restrict__ W1,
-                       int ldw, const float* __restrict__ F, int B, int N, int C, int ld,
+                       int ldw, const float* __restrict__ F, int B, int N, int C, int ld, int relu,
                        float* __restrict__ out) {
   const int ld4 = ld / 4;
   const size_t total = (size_t)B * N * ld4;
@@ -404,7 +441,8 @@ pointmlp_l1_fwd_kernel(const float* __restrict__ grid, long long grid_bstride, c
     float r = 0.f;
     if (cc < C) {
       const float* __restrict__ w = W1 + (size_t)cc * ldw;
-      r = fmaxf(fmaf(gz, w[2], fmaf(gy, w[1], fmaf(gx, w[0], F[(size_t)b * C + cc]))), 0.f);
+      r = fmaf(gz, w[2], fmaf(gy, w[1], fmaf(gx, w[0], F[(size_t)b * C + cc])));
+      if (relu) r = fmaxf(r, 0.f);
     }
     v[e] = r;
   }
@@ -516,12 +554,12 @@ weighted_colsum_kernel(const float* __restrict__ x, long long rows, int C, long 
 using namespace obman;
 
 extern "C" int obman_pointmlp_l1_fwd(const float* grid, long long grid_bstride, const float* W1, int ldw,
-                                     const float* F, int B, int N, int C, int ld, float* out, void* stream) {
+                                     const float* F, int B, int N, int C, int ld, int relu, float* out, void* stream) {
   OBMAN_REQUIRE(grid && W1 && F && out && B > 0 && N > 0 && C > 0 && ld >= C && ld % 4 == 0 && ldw >= 3,
                 "obman_pointmlp_l1_fwd: bad arguments");
   const size_t total = (size_t)B * N * (ld / 4);
   pointmlp_l1_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grid, grid_bstride, W1, ldw,
-                                                                                         F, B, N, C, ld, out);
+                                                                                         F, B, N, C, ld, relu, out);
   return check_launch("pointmlp_l1_fwd_kernel");
 }
 
@@ -588,6 +626,36 @@ extern "C" int obman_fold_conv(const float* w, const float* cbias, const float* 
   fold_conv_kernel<<<O, 256, 0, (cudaStream_t)stream>>>(w, cbias, gamma, beta, mean, var, eps, O, I, KH, KW, Ip, stem,
                                                         packed, wf, wf_lo, wft, wft_lo, shift, scale, rstd);
   return check_launch("fold_conv_kernel");
+}
+
+extern "C" int obman_fold_conv_batch(int n_units, const float* const* w, const float* const* gamma,
+                                     const float* const* beta, const float* const* mean, const float* const* var,
+                                     float eps, const int* O, const int* I, const int* K, const int* Ip, const int* stem,
+                                     float* const* wf, float* const* wft, float* const* shift, float* const* scale,
+                                     float* const* rstd, void* stream) {
+  OBMAN_REQUIRE(n_units >= 1 && n_units <= FOLD_MAX_UNITS, "obman_fold_conv_batch: n_units=%d out of [1,%d]", n_units,
+                FOLD_MAX_UNITS);
+  OBMAN_REQUIRE(w && gamma && beta && mean && var && O && I && K && Ip && stem && wf && wft && shift && scale && rstd,
+                "obman_fold_conv_batch: null table");
+  FoldBatch t;
+  memset(&t, 0, sizeof(t));
+  t.n = n_units;
+  int rows = 0;
+  for (int u = 0; u < n_units; ++u) {
+    OBMAN_REQUIRE(w[u] && gamma[u] && beta[u] && mean[u] && var[u] && wf[u] && shift[u] && scale[u] && rstd[u],
+                  "obman_fold_conv_batch: unit %d has a null pointer", u);
+    OBMAN_REQUIRE(O[u] > 0 && I[u] > 0 && K[u] > 0 && Ip[u] >= I[u] && Ip[u] % 32 == 0,
+                  "obman_fold_conv_batch: unit %d has bad sizes (packed layout needs Ip %% 32 == 0)", u);
+    OBMAN_REQUIRE(!stem[u] || (I[u] == 3 && K[u] == 7), "obman_fold_conv_batch: stem layout needs a (O,3,7,7) filter");
+    t.w[u] = w[u]; t.gamma[u] = gamma[u]; t.beta[u] = beta[u]; t.mean[u] = mean[u]; t.var[u] = var[u];
+    t.wf[u] = wf[u]; t.wft[u] = wft[u]; t.shift[u] = shift[u]; t.scale[u] = scale[u]; t.rstd[u] = rstd[u];
+    t.O[u] = O[u]; t.I[u] = I[u]; t.K[u] = K[u]; t.Ip[u] = Ip[u]; t.stem[u] = stem[u];
+    t.row0[u] = rows;
+    rows += O[u];
+  }
+  t.row0[n_units] = rows;
+  fold_conv_batch_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(t, eps);
+  return check_launch("fold_conv_batch_kernel");
 }
 
 extern "C" int obman_maxpool_fwd(const float* x, int B, int H, int W, int C, float* out,

@@ -69,8 +69,9 @@ class _NullCtx(object):
 class _Unit(object):
     """Per-step folded weights of one conv+BN unit."""
 
-    def __init__(self, w, gamma, beta, mean, var, ksize, stride, stem=False, need_dgrad=True, packed=False):
+    def __init__(self, w, gamma, beta, mean, var, ksize, stride, stem=False, need_dgrad=True, packed=False, fold=True):
         self.w, self.gamma, self.mean = w, gamma, mean
+        self.beta, self.var = beta, var
         self.beta_ptr = beta.data_ptr()
         self.O, self.I = w.shape[0], w.shape[1]
         self.k, self.stride, self.stem = ksize, stride, stem
@@ -86,9 +87,10 @@ class _Unit(object):
             self.wft = _empty(self.I, self.slots * self.O)
             self.wft_lo = None if packed else _empty(self.I, self.slots * self.O)
         self.shift, self.scale, self.rstd = _empty(self.O), _empty(self.O), _empty(self.O)
-        call("obman_fold_conv", ptr(w), None, ptr(gamma), ptr(beta), ptr(mean), ptr(var), BN_EPS, self.O, self.I,
-             ksize, ksize, self.Ip, int(stem), int(packed), ptr(self.wf), ptr(self.wf_lo), ptr(self.wft),
-             ptr(self.wft_lo), ptr(self.shift), ptr(self.scale), ptr(self.rstd), stream_ptr())
+        if fold:
+            call("obman_fold_conv", ptr(w), None, ptr(gamma), ptr(beta), ptr(mean), ptr(var), BN_EPS, self.O, self.I,
+                 ksize, ksize, self.Ip, int(stem), int(packed), ptr(self.wf), ptr(self.wf_lo), ptr(self.wft),
+                 ptr(self.wft_lo), ptr(self.shift), ptr(self.scale), ptr(self.rstd), stream_ptr())
         if stem:
             self.taps = ([-2, -1, 0, 1], [0, 0, 0, 0], [0] * 4, list(range(4)))
             self.in_step = 1
@@ -168,6 +170,24 @@ class _Unit(object):
         return gw, ggamma, gbeta
 
 
+def fold_units(units):
+    """BatchNorm folding + bf16 hi|lo packing of all units in ONE launch (obman_fold_conv_batch; packed layout only)."""
+    import ctypes
+
+    def ptrs(ts):
+        return (ctypes.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])
+
+    def ints(vs):
+        return (ctypes.c_int * len(vs))(*[int(v) for v in vs])
+
+    call("obman_fold_conv_batch", len(units), ptrs([u.w for u in units]), ptrs([u.gamma for u in units]),
+         ptrs([u.beta for u in units]), ptrs([u.mean for u in units]), ptrs([u.var for u in units]), BN_EPS,
+         ints([u.O for u in units]), ints([u.I for u in units]), ints([u.k for u in units]),
+         ints([u.Ip for u in units]), ints([int(u.stem) for u in units]), ptrs([u.wf for u in units]),
+         ptrs([u.wft for u in units]), ptrs([u.shift for u in units]), ptrs([u.scale for u in units]),
+         ptrs([u.rstd for u in units]), stream_ptr())
+
+
 def colsum(x2d_rows, C, t):
     out = _empty(C)
     call("obman_colsum", ptr(t), int(x2d_rows), int(C), int(C), ptr(out), stream_ptr())
@@ -190,20 +210,29 @@ class _EncoderFn(torch.autograd.Function):
         packed = pf == dense.BF16X3
         unit_params = [[p.detach().contiguous() for p in params[5 * i:5 * i + 5]] for i in range(len(specs))]
 
-        def make_unit(i):
+        def make_unit(i, fold=True):
             _, _, O, I, k, s = specs[i]
             w, gamma, beta, mean, var = unit_params[i]
-            return _Unit(w, gamma, beta, mean, var, k, s, stem=(i == 0), packed=packed)
+            return _Unit(w, gamma, beta, mean, var, k, s, stem=(i == 0), packed=packed, fold=fold)
 
         st = stream_ptr()
-        units = [make_unit(0)]
-        # the BN folding / weight packing of the 19 remaining units runs on the auxiliary stream underneath the
-        # HBM-bound front of the network (stem pack, stem convolution, max-pool)
-        streams.fork()
-        with streams.on_aux():
-            units.extend(make_unit(i) for i in range(1, len(specs)))
         xs = _empty(B, H // 2, W // 2 + 4, 16)
-        call("obman_stem_pack", ptr(images), B, H, W, ptr(xs), st)
+        if packed:
+            # BN folding + bf16 packing of all 20 units: one launch on the auxiliary stream, underneath the stem pack
+            streams.fork()
+            with streams.on_aux():
+                units = [make_unit(i, fold=False) for i in range(len(specs))]
+                fold_units(units)
+            call("obman_stem_pack", ptr(images), B, H, W, ptr(xs), st)
+            streams.join()
+        else:
+            units = [make_unit(0)]
+            # 3xTF32 layouts: one folding launch per unit; units 1..19 on the auxiliary stream underneath the HBM-bound
+            # front of the network (stem pack, stem convolution, max-pool)
+            streams.fork()
+            with streams.on_aux():
+                units.extend(make_unit(i) for i in range(1, len(specs)))
+            call("obman_stem_pack", ptr(images), B, H, W, ptr(xs), st)
         c1 = units[0].fprop(xs, H // 2, W // 2, relu=True, passes=pf)
         if DEBUG is not None:
             DEBUG["act_c1"] = c1
@@ -211,7 +240,8 @@ class _EncoderFn(torch.autograd.Function):
         p = _empty(B, hp, wp, 64)
         pidx = torch.empty((B, hp, wp, 64), device="cuda", dtype=torch.uint8)
         call("obman_maxpool_fwd", ptr(c1), B, H // 2, W // 2, 64, ptr(p), ptr(pidx), st)
-        streams.join()
+        if not packed:
+            streams.join()
         if DEBUG is not None:
             DEBUG["pool_idx"] = pidx
         x, h, w_ = p, hp, wp
@@ -322,6 +352,162 @@ class _EncoderFn(torch.autograd.Function):
             gw, gg, gbt = grads[id(u)]
             outs.extend([gw, gg, gbt, None, None])
         return tuple(outs)
+
+
+class _TrainUnit(_Unit):
+    """conv + BatchNorm with BATCH statistics (model.train(), i.e. training without --freeze_batchnorm): the raw
+    weights go to the tensor-core kernels (bf16 hi|lo packed, no folding), the statistics / normalisation / ReLU and
+    their gradients are the HBM-bound kernels of csrc/bn_train.cu."""
+
+    def __init__(self, w, gamma, beta, rmean, rvar, ksize, stride, stem=False, momentum=0.1, update_stats=True):
+        super(_TrainUnit, self).__init__(w, gamma, beta, rmean, rvar, ksize, stride, stem=stem, packed=True, fold=False)
+        self.rmean, self.rvar = rmean, rvar
+        self.momentum, self.update_stats = momentum, update_stats
+        self.mean_b = _empty(self.O)
+        # gamma = NULL: plain (unscaled) weights in the packed layouts, shift = 0
+        call("obman_fold_conv", ptr(w), None, None, None, None, None, BN_EPS, self.O, self.I, ksize, ksize, self.Ip,
+             int(stem), 1, ptr(self.wf), None, ptr(self.wft), None, ptr(self.shift), ptr(self.scale), ptr(self.rstd),
+             stream_ptr())
+
+    def _partial(self, rows):
+        chunks = _lib_load().obman_bn_chunks(int(rows), int(self.O))
+        return _empty(max(1, chunks) * self.O * 2)
+
+    def forward(self, x, h_out, w_out, addend=None, relu=True, passes=dense.BF16X3):
+        """-> (z raw convolution output, y = [relu](bn(z) [+ addend])), both (B, h_out, w_out, O)."""
+        z = _empty(x.shape[0], h_out, w_out, self.O)
+        dense.conv_nhwc(x, self.wf, self.O, self.taps, self.in_step, z, h_out, w_out, passes=passes, w_slots=self.slots,
+                        algo_k=147 if self.stem else None, x_geom=stem_view(x) if self.stem else None)
+        rows = z.shape[0] * h_out * w_out
+        upd = self.update_stats
+        call("obman_bn_stats", ptr(z), rows, self.O, self.O, ptr(self.gamma), ptr(self.beta), BN_EPS,
+             float(self.momentum), ptr(self._partial(rows)), ptr(self.mean_b), ptr(self.rstd), ptr(self.scale),
+             ptr(self.shift), ptr(self.rmean) if upd else None, ptr(self.rvar) if upd else None, stream_ptr())
+        y = torch.empty_like(z)
+        call("obman_bn_apply_fwd", ptr(z), rows, self.O, self.O, ptr(self.scale), ptr(self.shift), ptr(addend),
+             int(relu), ptr(y), stream_ptr())
+        return z, y
+
+    def bn_backward(self, g, mask_src, z, want_masked=False):
+        """g = gradient w.r.t. the unit's output (after the ReLU whose mask is ``mask_src > 0``; None = no ReLU) ->
+        (dz, d beta, d gamma, g masked or None)."""
+        rows = z.shape[0] * z.shape[1] * z.shape[2]
+        sum_g, sum_gz = _empty(self.O), _empty(self.O)
+        dz = torch.empty_like(z)
+        gm = torch.empty_like(z) if want_masked else None
+        call("obman_bn_bwd", ptr(g), ptr(mask_src), ptr(z), rows, self.O, self.O, ptr(self.mean_b), ptr(self.rstd),
+             ptr(self.scale), ptr(self._partial(rows)), ptr(sum_g), ptr(sum_gz), ptr(dz), ptr(gm), stream_ptr())
+        return dz, sum_g, sum_gz, gm
+
+    def weight_grad(self, dz, x, passes=dense.BF16X3):
+        """(O, I, k, k) weight gradient from the raw stacked-tap layout (bn_wgrad_finish with unit scale: a re-layout)."""
+        dwraw = self.wgrad(dz, x, passes)
+        gw = torch.empty_like(self.w)
+        ones = torch.ones(self.O, device=dz.device)   # (train mode is not the benchmarked path)
+        call("obman_bn_wgrad_finish", ptr(dwraw), dwraw.stride(0), ptr(self.w), None, ptr(ones), ptr(ones), None,
+             ptr(ones), self.O, self.I, self.k, self.k, self.Ip, int(self.stem), ptr(gw), None, None, None, stream_ptr())
+        return gw
+
+
+def _lib_load():
+    from . import _lib
+    return _lib.load()
+
+
+class _EncoderTrainFn(torch.autograd.Function):
+    """resnet18(images) with BatchNorm in TRAINING mode (batch statistics, running statistics updated with the modules'
+    momentum): bases/resnet.py:154-188 under model.train().  params = 5 tensors per unit (w, gamma, beta,
+    running_mean, running_var); ``momenta`` = one float per unit."""
+
+    @staticmethod
+    def forward(ctx, images, momenta, *params):
+        if not (images.is_cuda and images.dtype == torch.float32):
+            raise RuntimeError("encoder: expected CUDA float32 images (no CPU path)")
+        if dense.get_precision()["fwd"] != "bf16x3":
+            raise RuntimeError("encoder: batch-statistics BatchNorm runs on the 3xBF16 path only")
+        images = images.contiguous()
+        B, _, H, W = images.shape
+        if H % 32 or W % 32:
+            raise RuntimeError("encoder: image height/width must be multiples of 32")
+        specs = resnet18_units()
+        st = stream_ptr()
+        units = []
+        for i, (_, _, O, I, k, s) in enumerate(specs):
+            w, gamma, beta, rm, rv = [p.detach() for p in params[5 * i:5 * i + 5]]
+            units.append(_TrainUnit(w.contiguous(), gamma.contiguous(), beta.contiguous(), rm, rv, k, s, stem=(i == 0),
+                                    momentum=momenta[i]))
+        xs = _empty(B, H // 2, W // 2 + 4, 16)
+        call("obman_stem_pack", ptr(images), B, H, W, ptr(xs), st)
+        z0, c1 = units[0].forward(xs, H // 2, W // 2)
+        hp, wp = H // 4, W // 4
+        p = _empty(B, hp, wp, 64)
+        pidx = torch.empty((B, hp, wp, 64), device="cuda", dtype=torch.uint8)
+        call("obman_maxpool_fwd", ptr(c1), B, H // 2, W // 2, 64, ptr(p), ptr(pidx), st)
+        x, h, w_ = p, hp, wp
+        blocks = []
+        ui = 1
+        for li in range(4):
+            for bi in range(2):
+                u1, u2 = units[ui], units[ui + 1]
+                ud = None
+                nxt = ui + 2
+                if nxt < len(specs) and "downsample" in specs[nxt][0] and specs[nxt][0].startswith("layer{}.{}.".format(li + 1, bi)):
+                    ud = units[nxt]
+                    nxt += 1
+                ho, wo = h // u1.stride, w_ // u1.stride
+                z1, a = u1.forward(x, ho, wo)
+                zd, r = ud.forward(x, ho, wo, relu=False) if ud is not None else (None, x)
+                z2, out = u2.forward(a, ho, wo, addend=r)
+                blocks.append((u1, u2, ud, x, z1, a, zd, z2, out, h, w_))
+                x, h, w_ = out, ho, wo
+                ui = nxt
+        feats = _empty(B, 512)
+        call("obman_meanpool_fwd", ptr(x), B, h * w_, 512, ptr(feats), st)
+        ctx.units, ctx.blocks = units, blocks
+        ctx.saved = (xs, z0, c1, pidx, H, W)
+        return feats
+
+    @staticmethod
+    def backward(ctx, gfeat):
+        units, blocks = ctx.units, ctx.blocks
+        xs, z0, c1, pidx, H, W = ctx.saved
+        st = stream_ptr()
+        gfeat = gfeat.contiguous()
+        B = gfeat.shape[0]
+        last = blocks[-1][8]
+        g2 = torch.empty_like(last)
+        call("obman_meanpool_bwd", ptr(gfeat), ptr(last), B, last.shape[1] * last.shape[2], 512, ptr(g2), st)
+        grads = {}
+        for (u1, u2, ud, x, z1, a, zd, z2, out, h, w_) in reversed(blocks):
+            ho, wo = out.shape[1], out.shape[2]
+            # out = relu(bn2(conv2(a)) + r): the ReLU mask comes from ``out``; its masked gradient also feeds the residual
+            dz2, gb2, gg2, gmask = u2.bn_backward(g2, out, z2, want_masked=True)
+            grads[id(u2)] = (u2.weight_grad(dz2, a), gg2, gb2)
+            ga = u2.dgrad(dz2, ho, wo, passes=dense.BF16X3)
+            if ud is not None:
+                dzd, gbd, ggd, _ = ud.bn_backward(gmask, None, zd)
+                grads[id(ud)] = (ud.weight_grad(dzd, x), ggd, gbd)
+                gres = ud.dgrad(dzd, h, w_, passes=dense.BF16X3)
+            else:
+                gres = gmask
+            dz1, gb1, gg1, _ = u1.bn_backward(ga, a, z1)
+            grads[id(u1)] = (u1.weight_grad(dz1, x), gg1, gb1)
+            g2 = u1.dgrad(dz1, h, w_, addend=gres, passes=dense.BF16X3)
+        gc1 = _empty(B, H // 2, W // 2, 64)
+        call("obman_maxpool_bwd", ptr(g2), ptr(pidx), B, H // 2, W // 2, 64, ptr(gc1), st)
+        u0 = units[0]
+        dz0, gb0, gg0, _ = u0.bn_backward(gc1, c1, z0)
+        grads[id(u0)] = (u0.weight_grad(dz0, xs), gg0, gb0)
+        outs = [None, None]
+        for u in units:
+            gw, gg, gbt = grads[id(u)]
+            outs.extend([gw, gg, gbt, None, None])
+        return tuple(outs)
+
+
+def resnet18_features_train(images, params, momenta):
+    """Batch-statistics BatchNorm (the module is in training mode)."""
+    return _EncoderTrainFn.apply(images, list(momenta), *params)
 
 
 def resnet18_features(images, params):

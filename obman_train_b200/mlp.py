@@ -201,7 +201,7 @@ class _PointDecoderFn(torch.autograd.Function):
         ld1, ld2 = _r32(C1), _r32(C2)
         h1 = _empty(B * N, ld1)
         call("obman_pointmlp_l1_fwd", ptr(grid), N * 3 if per_sample else 0, ptr(l1.wf), l1.wf.stride(0), ptr(Fb), B, N,
-             C1, ld1, ptr(h1), st)
+             C1, ld1, 1, ptr(h1), st)
         # padding columns of h2 (and of the gradient buffers below) are never read as data: GEMM A operands are fetched
         # through tensor maps whose K extent is the true channel count (TMA zero-fills beyond it), and in the
         # weight-gradient GEMMs a padding channel only produces a padding row / column of the raw gradient
@@ -277,6 +277,153 @@ class _PointDecoderFn(torch.autograd.Function):
         return (gfeat, None, None,
                 gw1.view(p[0]), gb1, gw2.view(p[2]), gb2, gw3.view(p[4]), gb3, gw4.view(p[6]), gb4,
                 gg1, gbt1, None, None, gg2, gbt2, None, None, gg3, gbt3, None, None)
+
+
+class _BatchStatBN(object):
+    """BatchNorm1d with batch statistics on a (rows, ld) activation whose first C columns are real (csrc/bn_train.cu works
+    on the padded width; padded channels get gamma = beta = 0 and come out as zeros)."""
+
+    def __init__(self, gamma, beta, rmean, rvar, ld, momentum):
+        from . import _lib
+        self.C, self.ld = gamma.shape[0], ld
+        self.gamma = pad_scale_mask(gamma.detach().view(1, -1), ld).view(-1)
+        self.beta = pad_scale_mask(beta.detach().view(1, -1), ld).view(-1)
+        self.rmean_mod, self.rvar_mod = rmean, rvar
+        self.rmean = pad_scale_mask(rmean.detach().view(1, -1), ld).view(-1)
+        self.rvar = pad_scale_mask(rvar.detach().view(1, -1), ld).view(-1)
+        self.momentum = momentum
+        self.mean, self.rstd, self.scale, self.shift = _empty(ld), _empty(ld), _empty(ld), _empty(ld)
+        self._chunks = _lib.load().obman_bn_chunks
+
+    def _partial(self, rows):
+        return _empty(max(1, self._chunks(int(rows), int(self.ld))) * self.ld * 2)
+
+    def forward(self, z, relu=True):
+        rows = z.shape[0]
+        call("obman_bn_stats", ptr(z), rows, self.ld, self.ld, ptr(self.gamma), ptr(self.beta), BN_EPS,
+             float(self.momentum), ptr(self._partial(rows)), ptr(self.mean), ptr(self.rstd), ptr(self.scale),
+             ptr(self.shift), ptr(self.rmean), ptr(self.rvar), stream_ptr())
+        with torch.no_grad():   # the module's running statistics (state-dict entries) follow the padded copies
+            self.rmean_mod.copy_(self.rmean[:self.C])
+            self.rvar_mod.copy_(self.rvar[:self.C])
+        y = torch.empty_like(z)
+        call("obman_bn_apply_fwd", ptr(z), rows, self.ld, self.ld, ptr(self.scale), ptr(self.shift), None, int(relu),
+             ptr(y), stream_ptr())
+        return y
+
+    def backward(self, g, y, z):
+        """-> (dz (rows, ld), d gamma (C,), d beta (C,)) for g = gradient w.r.t. y = relu(bn(z))."""
+        rows = z.shape[0]
+        sum_g, sum_gz = _empty(self.ld), _empty(self.ld)
+        dz = torch.empty_like(z)
+        call("obman_bn_bwd", ptr(g), ptr(y), ptr(z), rows, self.ld, self.ld, ptr(self.mean), ptr(self.rstd),
+             ptr(self.scale), ptr(self._partial(rows)), ptr(sum_g), ptr(sum_gz), ptr(dz), None, stream_ptr())
+        return dz, sum_gz[:self.C].contiguous(), sum_g[:self.C].contiguous()
+
+
+class _PointDecoderTrainFn(torch.autograd.Function):
+    """PointGenCon with its three BatchNorm1d layers in TRAINING mode (batch statistics over all B*N points,
+    running statistics updated): atlasutils.py:65-75 under model.train().  Same argument list as _PointDecoderFn plus
+    the three momenta.  3xBF16 path only; not the benchmarked configuration (the README recipe freezes BatchNorm)."""
+
+    @staticmethod
+    def forward(ctx, feat, grid, out_factor, momenta, *p):
+        if dense.get_precision()["fwd"] != "bf16x3":
+            raise RuntimeError("point_decoder: batch-statistics BatchNorm runs on the 3xBF16 path only")
+        pf = dense.BF16X3
+        st = stream_ptr()
+        feat = feat.contiguous()
+        grid = grid.detach().contiguous()
+        B, Fdim = feat.shape
+        N = grid.shape[-2]
+        per_sample = grid.dim() == 3
+        # plain (unfolded) weights: layer 1 in fp32 (split algebraically), layers 2-4 packed for the tensor cores
+        l1 = _Layer(p[0], p[1], None, plain=True)
+        l2 = _Layer(p[2], p[3], None, packed=True)
+        l3 = _Layer(p[4], p[5], None, packed=True)
+        l4 = _Layer(p[6], p[7], None, packed=True)
+        C1, C2, C3 = l1.O, l2.O, l3.O
+        ld1, ld2, ld3 = _r32(C1), _r32(C2), _r32(C3)
+        bn1 = _BatchStatBN(p[8], p[9], p[10], p[11], ld1, momenta[0])
+        bn2 = _BatchStatBN(p[12], p[13], p[14], p[15], ld2, momenta[1])
+        bn3 = _BatchStatBN(p[16], p[17], p[18], p[19], ld3, momenta[2])
+        wfeat = l1.wf[:, 3:3 + Fdim]
+        wpk = _empty(C1, _r32(Fdim))
+        call("obman_pack_bf16", ptr(wfeat), l1.wf.stride(0), C1, Fdim, ptr(wpk), wpk.stride(0), st)
+        Fb = dense.gemm(feat, wpk, bias=l1.shift, passes=pf, n=C1, k=Fdim, packed=True)     # (B,C1) incl. the conv bias
+        z1 = _empty(B * N, ld1)     # the layer-1 kernel writes the padding columns as zeros
+        call("obman_pointmlp_l1_fwd", ptr(grid), N * 3 if per_sample else 0, ptr(l1.wf), l1.wf.stride(0), ptr(Fb), B, N,
+             C1, ld1, 0, ptr(z1), st)
+        y1 = bn1.forward(z1)
+        z2 = _zeros(B * N, ld2)
+        dense.gemm(y1, l2.wf, out=z2, bias=l2.shift, passes=pf, n=C2, k=C1, packed=True)
+        y2 = bn2.forward(z2)
+        z3 = _zeros(B * N, ld3)
+        dense.gemm(y2, l3.wf, out=z3, bias=l3.shift, passes=pf, n=C3, k=C2, packed=True)
+        y3 = bn3.forward(z3)
+        y = dense.gemm(y3, l4.wf, bias=l4.shift * out_factor, alpha=out_factor, passes=pf, n=3, k=C3, packed=True)
+        ctx.layers, ctx.bns = (l1, l2, l3, l4), (bn1, bn2, bn3)
+        ctx.param_shapes = [tuple(t.shape) for t in p]
+        ctx.saved = (feat, grid, z1, y1, z2, y2, z3, y3, B, N, per_sample, out_factor)
+        return y.view(B, N, 3)
+
+    @staticmethod
+    def backward(ctx, gy):
+        pb = pw = dense.BF16X3
+        st = stream_ptr()
+        l1, l2, l3, l4 = ctx.layers
+        bn1, bn2, bn3 = ctx.bns
+        feat, grid, z1, y1, z2, y2, z3, y3, B, N, per_sample, out_factor = ctx.saved
+        C1, C2, C3 = l1.O, l2.O, l3.O
+        M = B * N
+        Fdim = feat.shape[1]
+
+        def conv_grads(layer, dz, x, C):
+            """weight (O, I) and bias gradients of a plain 1x1 convolution from its output gradient dz and input x."""
+            gsum = _empty(dz.shape[1])
+            dw = dense.wgrad_matrix(dz, x, passes=pw, dy_colsum=gsum)
+            return dw[:layer.O, :layer.I].contiguous(), gsum[:C].contiguous()
+
+        g4 = pad_scale_mask(gy.reshape(M, 3) if gy.is_contiguous() else gy.contiguous().view(M, 3), 32, alpha=out_factor)
+        gw4, gb4 = conv_grads(l4, g4, y3, 3)
+        gy3 = _zeros(M, z3.shape[1])
+        dense.gemm(g4, l4.wft, out=gy3, passes=pb, n=C3, k=3, packed=True)
+        dz3, gg3, gbt3 = bn3.backward(gy3, y3, z3)
+        gw3, gb3 = conv_grads(l3, dz3, y2, C3)
+        gy2 = _zeros(M, z2.shape[1])
+        dense.gemm(dz3, l3.wft, out=gy2, passes=pb, n=C2, k=C3, packed=True)
+        dz2, gg2, gbt2 = bn2.backward(gy2, y2, z2)
+        gw2, gb2 = conv_grads(l2, dz2, y1, C2)
+        gy1 = _zeros(M, z1.shape[1])
+        dense.gemm(dz2, l2.wft, out=gy1, passes=pb, n=C1, k=C2, packed=True)
+        dz1, gg1, gbt1 = bn1.backward(gy1, y1, z1)
+        gFc = _empty(B, C1)
+        gG = None if per_sample else _empty(N, C1)
+        call("obman_pointmlp_l1_bwd", ptr(dz1), B, N, C1, dz1.shape[1], ptr(gFc), ptr(gG), st)
+        gF = pad_scale_mask(gFc, _r32(C1))
+        dw1 = _empty(C1, 3 + Fdim)
+        if per_sample:
+            call("obman_weighted_colsum", ptr(dz1), M, C1, dz1.stride(0), ptr(grid), 3, ptr(dw1), dw1.stride(0), st)
+        else:
+            call("obman_weighted_colsum", ptr(gG), N, C1, C1, ptr(grid), 3, ptr(dw1), dw1.stride(0), st)
+        featp = feat if Fdim == _r32(Fdim) else pad_scale_mask(feat, _r32(Fdim))
+        dw1[:, 3:] = dense.wgrad_matrix(gF, featp, passes=pw)[:C1, :Fdim]
+        gb1 = colsum(gF, C1)
+        gfeat = None
+        if ctx.needs_input_grad[0]:
+            wfeat = l1.wf[:, 3:3 + Fdim]
+            wft = _empty(Fdim, _r32(C1))
+            call("obman_pack_bf16_t", ptr(wfeat), l1.wf.stride(0), C1, Fdim, ptr(wft), wft.stride(0), st)
+            gfeat = dense.gemm(gF, wft, passes=pb, n=Fdim, k=C1, packed=True)
+        ps = ctx.param_shapes
+        return (gfeat, None, None, None,
+                dw1.view(ps[0]), gb1, gw2.view(ps[2]), gb2, gw3.view(ps[4]), gb3, gw4.view(ps[6]), gb4,
+                gg1, gbt1, None, None, gg2, gbt2, None, None, gg3, gbt3, None, None)
+
+
+def point_decoder_train(feat, grid, out_factor, conv_params, bn_params, momenta):
+    """point_decoder with the BatchNorm1d layers in training mode (batch statistics)."""
+    return _PointDecoderTrainFn.apply(feat, grid, out_factor, list(momenta), *(list(conv_params) + list(bn_params)))
 
 
 def point_decoder(feat, grid, out_factor, conv_params, bn_params):

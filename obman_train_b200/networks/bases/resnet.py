@@ -76,19 +76,26 @@ class ResNet(nn.Module):
         return nn.Sequential(*layers)
 
     def _unit_params(self):
+        """(params, momenta, training): 5 tensors per conv+BN unit; all BatchNorm layers must be in the same mode."""
         mods = dict(self.named_modules())
-        params = []
+        params, momenta, modes = [], [], set()
         for conv_name, bn_name, _, _, _, _ in encoder.resnet18_units():
             conv, bn = mods[conv_name], mods[bn_name]
-            if bn.training:
-                raise NotImplementedError(
-                    "BatchNorm with batch statistics is not on the B200 hot path; put the model in eval() "
-                    "mode as the reference does with --freeze_batchnorm (epochpass3d.py:48-50)")
+            modes.add(bool(bn.training))
+            momenta.append(0.1 if bn.momentum is None else float(bn.momentum))
             params.extend([conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var])
-        return params
+        if len(modes) != 1:
+            raise NotImplementedError("ResNet: BatchNorm layers in mixed train / eval mode are not supported")
+        return params, momenta, modes.pop()
 
     def forward(self, x):
-        feats = encoder.resnet18_features(x, self._unit_params())
+        params, momenta, training = self._unit_params()
+        if training:
+            # batch statistics (training without --freeze_batchnorm, epochpass3d.py:48-52)
+            feats = encoder.resnet18_features_train(x, params, momenta)
+        else:
+            # fixed running statistics, trainable gamma / beta (--freeze_batchnorm: eval() during training)
+            feats = encoder.resnet18_features(x, params)
         return feats, {}
 
 

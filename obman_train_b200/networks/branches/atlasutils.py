@@ -44,22 +44,27 @@ class PointGenCon(nn.Module):
         self.bn3 = torch.nn.BatchNorm1d(int(self.bottleneck_size / 4))
 
     def _params(self):
-        for bn in (self.bn1, self.bn2, self.bn3):
-            if bn.training:
-                raise NotImplementedError(
-                    "BatchNorm with batch statistics is not on the B200 hot path; put the model in eval() "
-                    "mode as the reference does with --freeze_batchnorm (epochpass3d.py:48-50)")
+        """(conv tensors, bn tensors, momenta, training); the three BatchNorm1d layers must be in the same mode."""
+        bn_mods = (self.bn1, self.bn2, self.bn3)
+        modes = {bool(bn.training) for bn in bn_mods}
+        if len(modes) != 1:
+            raise NotImplementedError("PointGenCon: BatchNorm layers in mixed train / eval mode are not supported")
         convs = [self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
                  self.conv3.weight, self.conv3.bias, self.conv4.weight, self.conv4.bias]
         bns = []
-        for bn in (self.bn1, self.bn2, self.bn3):
+        for bn in bn_mods:
             bns.extend([bn.weight, bn.bias, bn.running_mean, bn.running_var])
-        return convs, bns
+        momenta = [0.1 if bn.momentum is None else float(bn.momentum) for bn in bn_mods]
+        return convs, bns, momenta, modes.pop()
 
     def decode(self, features, grid):
-        """features (B,F), grid (N,3) or (B,N,3) -> (B,N,3) = out_factor * decoder(cat(grid, features))."""
+        """features (B,F), grid (N,3) or (B,N,3) -> (B,N,3) = out_factor * decoder(cat(grid, features)).  BatchNorm in
+        eval mode (the README recipe, --freeze_batchnorm) is folded into the tensor-core GEMMs; in training mode the
+        batch statistics run as separate kernels (mlp.point_decoder_train)."""
         from ... import mlp
-        convs, bns = self._params()
+        convs, bns, momenta, training = self._params()
+        if training:
+            return mlp.point_decoder_train(features, grid, float(self.out_factor), convs, bns, momenta)
         return mlp.point_decoder(features, grid, float(self.out_factor), convs, bns)
 
     def forward(self, x):

@@ -11,6 +11,10 @@ from obman_train_b200 import dense  # noqa: E402
 from obman_train_b200._lib import call  # noqa: E402
 
 B = int(os.environ.get("PROF_B", "256"))
+NAMES_V2 = {0: "kernel body (thread 0)", 1: "producer: wait halo buffer free", 2: "converter: wait halo landed",
+            5: "converter: loop total", 13: "MMA: wait box converted", 7: "MMA: wait accumulator drained", 8: "MMA: loop total",
+            9: "epilogue group 0: wait accumulator", 10: "epilogue group 0: loop total",
+            14: "epilogue group 1: wait accumulator", 15: "epilogue group 1: loop total", 12: "tiles per CTA"}
 NAMES = {0: "kernel body (thread 0)", 1: "producer: wait halo buffer free", 2: "splitter: wait halo landed",
          3: "splitter: wait A stage free", 4: "splitter: in-place split + barrier", 5: "splitter: loop total",
          13: "MMA: wait A stage written", 7: "MMA: wait accumulator drained", 8: "MMA: loop total",
@@ -41,8 +45,9 @@ def run(h, cin, cout, variant):
     call("obman_debug_trace", None, 0)
     t = buf.view(148, 16).double()
     print("conv3x3 %dx%d c%d->%d %s, B=%d: %.4f ms (traced launch)" % (h, h, cin, cout, variant, B, e0.elapsed_time(e1)))
-    for k in sorted(NAMES):
-        print("   %-40s %12.0f" % (NAMES[k], t[:, k].mean().item()))
+    names = NAMES if os.environ.get("OBMAN_CONV64_GEN") == "1" else NAMES_V2
+    for k in sorted(names):
+        print("   %-40s %12.0f" % (names[k], t[:, k].mean().item()))
 
 
 for variant in ("plain", "mask+add"):

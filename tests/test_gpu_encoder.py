@@ -86,8 +86,10 @@ def test_resnet18_fwd_bwd_vs_oracle(B, H, precision, tol, grad_tol):
     assert l2s[0][0] < grad_tol, l2s[:5]
 
 
-def test_resnet18_train_mode_bn_is_rejected():
+def test_resnet18_mixed_bn_modes_are_rejected():
+    """All BatchNorm layers train or all evaluate (tests/test_gpu_bn_train.py covers the training mode)."""
     from obman_train_b200.networks.bases.resnet import resnet18
-    model = resnet18().cuda().train()
+    model = resnet18().cuda().eval()
+    model.layer3[0].bn1.train()
     with pytest.raises(NotImplementedError):
         model(torch.zeros(1, 3, 64, 64, device="cuda"))

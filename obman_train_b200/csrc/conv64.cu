@@ -320,8 +320,8 @@ conv64_v2_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wt = smem;
   uint8_t* halo_base = smem + n_iters * P64_WT_TILE;
-  uint8_t* staging = halo_base + RA * prog.halo_stride;      // 2 groups x [2 parts][16 pixels][64 channels] fp32
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 16384);
+  uint8_t* staging = halo_base + RA * prog.halo_stride;      // 2 groups x [2 parts][32 pixels][64 channels] fp32 + column table
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 32768 + 2048);
   uint64_t* wfull = bars;                    // weights landed
   uint64_t* afull = bars + 1;                // [RA] halo box landed (TMA)
   uint64_t* bconv = afull + P64_RA_MAX;      // [RA] halo box converted to bf16 planes
@@ -464,111 +464,150 @@ conv64_v2_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, 
     }
     if (sid == 0) { trace_put(epi, 2, w_afull); trace_put(epi, 5, clock64() - t_loop); }
   } else {
-    // ===== epilogue: warps 6..13 = two groups of four (TMEM lane quadrant = warp % 4), alternating 16-column rounds =====
+    // ===== epilogue: warps 6..13 = two groups of four (TMEM lane quadrant = warp % 4), alternating 32-column rounds =====
     // lanes 0-63 of the accumulator = w_hi part of channels 0-63, lanes 64-127 = w_lo part.  In a round every warp
-    // stores its 32 channels x 16 pixel columns into the group's staging tile ([part][pixel][64 channels] fp32), one
+    // stores its 32 channels x 32 pixel columns into the group's staging tile ([part][pixel][64 channels] fp32), one
     // barrier later the four warps walk the pixels with 16 lanes x float4 per pixel, adding the two parts on the way
-    // (256 contiguous bytes per output row and store instruction).
-    constexpr int RW2 = 16;
+    // (256 contiguous bytes per output row and store instruction; four independent pixels per thread).  The column ->
+    // pixel mapping does not depend on the tile: it is tabulated once in shared memory, so a round costs one table
+    // read per pixel instead of a chain of integer divisions (a lone warp per scheduler runs dependent ALU chains at
+    // ~4 clk per instruction: the divisions alone were 800 clk per round, scripts/trace_conv64.py).
+    constexpr int RW2 = 32, PE = RW2 / 8;
     const int q = warp & 3;
     const int group = (warp - 6) >> 2;           // 0 | 1
     const int et = (threadIdx.x - 192) & 127;    // 0 .. 127 inside the group
     const int part = q >> 1;                     // 0: lanes 0-63 (hi), 1: lanes 64-127 (lo)
     const int ch = (q & 1) * 32 + lane;          // channel of this TMEM lane
-    const int px_sub = et >> 4;                  // pixel (of 8) this thread stores in each half of a round
+    const int px_sub = et >> 4;                  // pixel (of 8) this thread stores in each eighth of a round
     const int c4 = (et & 15) * 4;                // its four channels
-    float* S = reinterpret_cast<float*>(staging + group * 8192);   // [2 parts][16 pixels][64 channels]
-    const float inv_hw = 1.f / (float)prog.halo_w, inv_hh = 1.f / (float)prog.halo_h;
+    float* S = reinterpret_cast<float*>(staging + group * 16384);   // [2 parts][32 pixels][64 channels]
+    int2* tab = reinterpret_cast<int2*>(staging + 32768);           // [256] column -> {relative offset, th | tw<<8 | tn<<16}
+    for (int j = threadIdx.x - 192; j < 256; j += 256) {
+      const int hr = j / prog.halo_w, tw = j - hr * prog.halo_w;    // halo row (over all images of the box), column
+      const int tn = hr / prog.halo_h, th = hr - tn * prog.halo_h;
+      const bool ok = j < NRUN && tw < prog.TW && th < prog.TH && tn < prog.TN;
+      tab[j] = make_int2((int)(tn * epi.sN + th * epi.sH + tw * epi.sW), ok ? (th | (tw << 8) | (tn << 16)) : -1);
+    }
+    named_barrier_sync(4, 256);                  // both groups: the table is complete
     const bool ptr_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
                           reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0;
+    // vector path: 16-byte aligned rows (pointers and strides) and four whole channels for this thread
+    const bool fast = ptr_ok && ((epi.sN | epi.sH | epi.sW) & 3) == 0 && c4 + 3 < prog.N;
+    const float relu_floor = epi.relu ? 0.f : -3.0e38f;
     float bias4[4] = {0.f, 0.f, 0.f, 0.f};
     if (epi.bias) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) if (c4 + e < prog.N) bias4[e] = __ldg(epi.bias + c4 + e);
     }
     const int rounds = (NRUN + RW2 - 1) / RW2;
-    // addresses + residual / ReLU-mask operands of one round, fetched ONE ROUND AHEAD (a round is far shorter than a
-    // DRAM round trip; the first round of a tile is fetched before the wait for its accumulator)
-    struct RoundOps { long long roff[2]; float4 add4[2], msk4[2]; };
-    auto fetch = [&](int tile, int rr, RoundOps& o) {
-      int n_img0, h0, w0;
-      tile_coords(prog, tile, n_img0, h0, w0);
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        // column j of the run = halo position (row j / halo_w over all images of the box, column j % halo_w);
-        // exact float reciprocals for j < 512
-        const int j = rr * RW2 + px_sub + 8 * e;
-        const int hr = (int)(((float)j + 0.5f) * inv_hw), tw = j - hr * prog.halo_w;
-        const int tn = (int)(((float)hr + 0.5f) * inv_hh), th = hr - tn * prog.halo_h;
-        const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
-        const bool ok = j < NRUN && tw < prog.TW && th < prog.TH && tn < prog.TN && n < prog.n_img && h < prog.h_out &&
-                        w < prog.w_out && c4 < prog.N;
-        o.roff[e] = ok ? n * epi.sN + h * epi.sH + w * epi.sW : -1;
-        epilogue_prefetch(epi, prog, o.roff[e], c4, ptr_ok, o.add4[e], o.msk4[e]);
-      }
-    };
     int ti = 0;
     long long w_accfull = 0;
     const long long t_loop = clock64();
-    RoundOps cur, nxt;
-    if ((int)blockIdx.x < total_tiles) fetch(blockIdx.x, group & 1, cur);
+    long long t_phase[5] = {0, 0, 0, 0, 0};
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      int n_img0, h0, w0;
+      tile_coords(prog, tile, n_img0, h0, w0);
+      const long long base = n_img0 * epi.sN + h0 * epi.sH + w0 * epi.sW;
+      const int lim_n = prog.n_img - n_img0, lim_h = prog.h_out - h0, lim_w = prog.w_out - w0;
       const int acc = ti & 1;
+      // operands of this group's first round: independent of the accumulator, fetched before waiting for it
+      const int rr0 = (group + ti) & 1;
+      long long roff[PE];
+      bool okp[PE];
+      float4 add4[PE], msk4[PE];
+      // branch-free per pixel (the four pixels of a thread are independent chains the scheduler can interleave):
+      // validity from the tabulated tile coordinates, operand loads predicated
+      auto fetch = [&](int rr) {
+#pragma unroll
+        for (int e = 0; e < PE; ++e) {
+          const int2 t = tab[rr * RW2 + px_sub + 8 * e];
+          okp[e] = (t.y >= 0) & ((t.y & 255) < lim_h) & (((t.y >> 8) & 255) < lim_w) & ((t.y >> 16) < lim_n) & (c4 < prog.N);
+          roff[e] = base + t.x;
+        }
+        if (fast) {
+#pragma unroll
+          for (int e = 0; e < PE; ++e) {
+            add4[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            msk4[e] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (epi.addend && okp[e]) add4[e] = __ldg(reinterpret_cast<const float4*>(epi.addend + roff[e] + c4));
+            if (epi.mask_src && okp[e]) msk4[e] = __ldg(reinterpret_cast<const float4*>(epi.mask_src + roff[e] + c4));
+          }
+        }
+      };
+      fetch(rr0);
       mbar_wait_timed(&accfull[acc], (uint32_t)((ti >> 1) & 1), timed, w_accfull);
       tc_fence_after();
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
       // the groups take alternate rounds; which one starts alternates with the tile (odd round counts stay balanced)
-      for (int rr = (group + ti) & 1; rr < rounds; rr += 2) {
-        // next round of this group: in this tile, or the first one of the next tile
-        if (rr + 2 < rounds) fetch(tile, rr + 2, nxt);
-        else if (tile + (int)gridDim.x < total_tiles) fetch(tile + gridDim.x, (group + ti + 1) & 1, nxt);
-        const int j0 = rr * RW2;
+      for (int rr = rr0; rr < rounds; rr += 2) {
+        const long long tp0 = timed ? clock64() : 0;
+        if (rr != rr0) fetch(rr);
+        const long long tp1 = timed ? clock64() : 0;
         uint32_t v[RW2];
-        tmem_ld_32x16(lane_addr + (uint32_t)j0, v);
+        tmem_ld_32x32(lane_addr + (uint32_t)(rr * RW2), v);
         tmem_ld_wait();
+        if (fast) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e)
-          asm volatile("" : "+f"(cur.msk4[e].x), "+f"(cur.msk4[e].y), "+f"(cur.msk4[e].z), "+f"(cur.msk4[e].w));
+          for (int e = 0; e < PE; ++e)
+            asm volatile("" : "+f"(msk4[e].x), "+f"(msk4[e].y), "+f"(msk4[e].z), "+f"(msk4[e].w));
+        }
 #pragma unroll
         for (int i = 0; i < RW2; ++i) S[(part * RW2 + i) * 64 + ch] = __uint_as_float(v[i]);
+        const long long tp2 = timed ? clock64() : 0;
         named_barrier_sync(2 + group, 128);
+        const long long tp3 = timed ? clock64() : 0;
+        if (fast) {
+          float4 s_hi[PE], s_lo[PE], o4[PE];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const long long roff = cur.roff[e];
-          if (roff < 0) continue;
-          const int px = px_sub + 8 * e;
-          const float4 s_hi = *reinterpret_cast<const float4*>(S + px * 64 + c4);
-          const float4 s_lo = *reinterpret_cast<const float4*>(S + (RW2 + px) * 64 + c4);
-          float x[4] = {epi.alpha * (s_hi.x + s_lo.x) + bias4[0], epi.alpha * (s_hi.y + s_lo.y) + bias4[1],
-                        epi.alpha * (s_hi.z + s_lo.z) + bias4[2], epi.alpha * (s_hi.w + s_lo.w) + bias4[3]};
-          if (ptr_ok && (roff & 3) == 0 && c4 + 3 < prog.N) {
-            x[0] += cur.add4[e].x; x[1] += cur.add4[e].y; x[2] += cur.add4[e].z; x[3] += cur.add4[e].w;
-            if (epi.relu) {
+          for (int e = 0; e < PE; ++e) {
+            s_hi[e] = *reinterpret_cast<const float4*>(S + (px_sub + 8 * e) * 64 + c4);
+            s_lo[e] = *reinterpret_cast<const float4*>(S + (RW2 + px_sub + 8 * e) * 64 + c4);
+          }
 #pragma unroll
-              for (int c = 0; c < 4; ++c) x[c] = fmaxf(x[c], 0.f);
-            }
-            x[0] = cur.msk4[e].x > 0.f ? x[0] : 0.f; x[1] = cur.msk4[e].y > 0.f ? x[1] : 0.f;
-            x[2] = cur.msk4[e].z > 0.f ? x[2] : 0.f; x[3] = cur.msk4[e].w > 0.f ? x[3] : 0.f;
-            *reinterpret_cast<float4*>(epi.out + roff + c4) = make_float4(x[0], x[1], x[2], x[3]);
-          } else {
+          for (int e = 0; e < PE; ++e) {
+            float x[4] = {epi.alpha * (s_hi[e].x + s_lo[e].x) + bias4[0] + add4[e].x,
+                          epi.alpha * (s_hi[e].y + s_lo[e].y) + bias4[1] + add4[e].y,
+                          epi.alpha * (s_hi[e].z + s_lo[e].z) + bias4[2] + add4[e].z,
+                          epi.alpha * (s_hi[e].w + s_lo[e].w) + bias4[3] + add4[e].w};
 #pragma unroll
+            for (int c = 0; c < 4; ++c) x[c] = fmaxf(x[c], relu_floor);
+            o4[e].x = msk4[e].x > 0.f ? x[0] : 0.f; o4[e].y = msk4[e].y > 0.f ? x[1] : 0.f;
+            o4[e].z = msk4[e].z > 0.f ? x[2] : 0.f; o4[e].w = msk4[e].w > 0.f ? x[3] : 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < PE; ++e)
+            if (okp[e]) *reinterpret_cast<float4*>(epi.out + roff[e] + c4) = o4[e];
+        } else {
+#pragma unroll 1
+          for (int e = 0; e < PE; ++e) {
+            if (!okp[e]) continue;
+            const long long ro = roff[e];
+            const int px = px_sub + 8 * e;
             for (int c = 0; c < 4; ++c) {
               if (c4 + c >= prog.N) break;
-              float y = x[c];
-              if (epi.addend) y += epi.addend[roff + c4 + c];
+              float y = epi.alpha * (S[px * 64 + c4 + c] + S[(RW2 + px) * 64 + c4 + c]) + bias4[c];
+              if (epi.addend) y += epi.addend[ro + c4 + c];
               if (epi.relu) y = fmaxf(y, 0.f);
-              if (epi.mask_src) y = epi.mask_src[roff + c4 + c] > 0.f ? y : 0.f;
-              epi.out[roff + c4 + c] = y;
+              if (epi.mask_src) y = epi.mask_src[ro + c4 + c] > 0.f ? y : 0.f;
+              epi.out[ro + c4 + c] = y;
             }
           }
         }
+        const long long tp4 = timed ? clock64() : 0;
         named_barrier_sync(2 + group, 128);   // the staging tile is rewritten by the group's next round
-        cur = nxt;
+        if (timed) {
+          t_phase[0] += tp1 - tp0; t_phase[1] += tp2 - tp1; t_phase[2] += tp3 - tp2; t_phase[3] += tp4 - tp3;
+          t_phase[4] += clock64() - tp4;
+        }
       }
       tc_fence_before();
       mbar_arrive(&accfree[acc]);
     }
     if (et == 0) { trace_put(epi, 9 + 5 * group, w_accfull); trace_put(epi, 10 + 5 * group, clock64() - t_loop); }
+    if (et == 0 && group == 0) {
+      trace_put(epi, 3, t_phase[0]); trace_put(epi, 4, t_phase[1]); trace_put(epi, 6, t_phase[2]);
+      trace_put(epi, 11, t_phase[3] + t_phase[4]);
+    }
   }
   if (threadIdx.x == 0) trace_put(epi, 0, clock64() - t_start);
   tc_fence_before();
@@ -688,7 +727,7 @@ int try_conv64(const float* x, int n_img, int h_in, int w_in, int c_in, long lon
       gen = (e && e[0] == '1') ? 1 : 2;
     }
     const int run = (((TN - 1) * HH + TH - 1) * HW + TW + 15) / 16 * 16;
-    auto smem2 = [&](int r) { return num_taps * KB * P64_WT_TILE + r * halo_stride + 16384 + 1024 + 512; };
+    auto smem2 = [&](int r) { return num_taps * KB * P64_WT_TILE + r * halo_stride + 32768 + 2048 + 1024 + 512; };
     int ring2 = P64_RA_MAX;
     while (ring2 > 2 && smem2(ring2) > P64_SMEM_LIMIT) --ring2;
     if (gen == 2 && run >= 32 && run <= 256 && halo_pix <= 256 && smem2(ring2) <= P64_SMEM_LIMIT) {   // >= 2 epilogue rounds

@@ -35,9 +35,15 @@ nn_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int M
   int* __restrict__ oidx = (dir == 0 ? idxx : idxy) + (size_t)b * nq;
 
   __shared__ float4 sc[NN_CHUNK];
+  // fminf drops NaNs, so a NaN coordinate would come out as a huge finite (or an arbitrary neighbour's) distance; the
+  // reference's torch.min over the distance matrix gives NaN for the NaN query itself and - a NaN candidate poisons
+  // every row - for all queries of the sample.  Detected at load time (outside the inner loop) and applied at the end.
+  __shared__ int s_nan;
+  if (threadIdx.x == 0) s_nan = 0;
 
   float qx[Q], qy[Q], qz[Q], best[Q];
   int bi[Q];
+  bool nan_seen[Q];
 #pragma unroll
   for (int k = 0; k < Q; ++k) {
     int j = q0 + k * NN_THREADS + threadIdx.x;
@@ -47,6 +53,7 @@ nn_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int M
     qz[k] = ok ? __ldg(qp + 3 * j + 2) : 0.f;
     best[k] = 3.0e38f;
     bi[k] = 0;
+    nan_seen[k] = (qx[k] != qx[k]) | (qy[k] != qy[k]) | (qz[k] != qz[k]);
   }
 
   for (int c0 = 0; c0 < nc; c0 += NN_CHUNK) {
@@ -58,6 +65,7 @@ nn_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int M
       float v = __ldg(src + e);
       int p = e / 3;
       reinterpret_cast<float*>(sc)[p * 4 + (e - 3 * p)] = v;
+      if (v != v) s_nan = 1;
     }
     for (int p = n + threadIdx.x; p < n4; p += NN_THREADS)
       sc[p] = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);  // never the minimum
@@ -89,7 +97,7 @@ nn_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int M
   for (int k = 0; k < Q; ++k) {
     int j = q0 + k * NN_THREADS + threadIdx.x;
     if (j < nq) {
-      omin[j] = best[k];
+      omin[j] = (nan_seen[k] || s_nan) ? __int_as_float(0x7fc00000) : best[k];
       oidx[j] = bi[k];
     }
   }

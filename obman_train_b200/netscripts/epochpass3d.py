@@ -69,7 +69,7 @@ def epoch_pass(loader, model, epoch, optimizer=None, debug=False, freeze_batchno
         out("epoch: {}".format(epoch))
     idxs = list(range(21)) if idxs is None else list(idxs)
     if train and not freeze_batchnorm:
-        model.train()   # rejected downstream: batch-statistics BatchNorm is not on the hot path
+        model.train()   # BatchNorm on batch statistics (csrc/bn_train.cu)
     else:
         model.eval()    # the README recipe (--freeze_batchnorm): eval-mode BN with trainable gamma / beta
     log = _DeviceLossLog()
@@ -80,14 +80,16 @@ def epoch_pass(loader, model, epoch, optimizer=None, debug=False, freeze_batchno
     for batch_idx, sample in enumerate(loader):
         time_meters.add_loss_value("data_time", time.time() - end)
         if train:
-            if use_graph:
-                if getattr(optimizer, "_graph", None) is None:
-                    optimizer.capture(dict(sample))   # the first batch's tensors become the static input buffers
+            if use_graph and getattr(optimizer, "_graph", None) is None:
+                optimizer.capture(dict(sample))       # the first batch's tensors become the static input buffers
+            if use_graph and optimizer.matches_captured(sample):
                 optimizer.replay(sample)              # copies this batch (and its left/right mask) into them
                 _, results, losses = optimizer.static_outputs()
                 if "joints" in results:               # static output: the next replay overwrites it
                     results = dict(results, joints=results["joints"].clone())
             else:
+                # eager launches: no graph, or a batch the captured step was not built for (a partial last batch, a
+                # key that appears / disappears)
                 _, results, losses = optimizer.step(sample, return_all=True)
         else:
             with torch.no_grad():

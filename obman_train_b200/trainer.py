@@ -120,6 +120,8 @@ class FlatAdamTrainer(object):
         # Adam per all-reduced range (bucketed optimiser): the early range is updated on the communication stream as
         # soon as it is reduced, the rest after the backward pass; False = one Adam launch over the whole buffer
         self.adam_per_range = True
+        self._skipped = []            # parameter indices without a gradient in the current step
+        self._ever_updated = set()    # parameter indices that have received a gradient at least once
         self.skip_allreduce = False   # measurement knob (bench.py: step time without the exchange)
         self.offsets = offsets
         self._sink = _GradSink(self) if self.direct_grads else None
@@ -167,6 +169,12 @@ class FlatAdamTrainer(object):
         have = [(v, p.grad) for v, p in zip(self.grad_views, self.params) if p.grad is not None]
         missing = [v for v, p in zip(self.grad_views, self.params)
                    if p.grad is None and p.data_ptr() not in written]
+        # torch.optim.Adam SKIPS a parameter whose .grad is None (no moment decay, no weight decay, no step): remember
+        # which slots those are; reduce_and_update puts their parameter / moment values back after the fused kernel
+        self._skipped = [i for i, p in enumerate(self.params) if p.grad is None and p.data_ptr() not in written]
+        for i, p in enumerate(self.params):
+            if p.grad is not None or p.data_ptr() in written:
+                self._ever_updated.add(i)
         if missing:
             torch._foreach_zero_(missing)
         torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
@@ -198,6 +206,18 @@ class FlatAdamTrainer(object):
         return rest, done
 
     def reduce_and_update(self):
+        keep = None
+        if self._skipped:
+            sl = [slice(self.offsets[i], self.offsets[i] + self.params[i].numel()) for i in self._skipped]
+            keep = [(s_, self.flat_p[s_].clone(), self.exp_avg[s_].clone(), self.exp_avg_sq[s_].clone()) for s_ in sl]
+        self._reduce_and_update()
+        if keep is not None:
+            for s_, p_, m_, v_ in keep:
+                self.flat_p[s_].copy_(p_)
+                self.exp_avg[s_].copy_(m_)
+                self.exp_avg_sq[s_].copy_(v_)
+
+    def _reduce_and_update(self):
         rest, done = self.all_reduce_grads()
         if done and self.adam_per_range:
             for lo, hi in rest:
@@ -242,6 +262,11 @@ class FlatAdamTrainer(object):
         if self.world_size > 1:
             # NCCL inside a captured graph needs the communicator warmed up outside of capture
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+        # the captured step reads OWNED device buffers: host tensors of the loader's collate (the reference's DataLoader
+        # contract) are moved once here, replay() copies every later batch into the same buffers
+        for k, v in list(sample.items()):
+            if torch.is_tensor(v) and not v.is_cuda:
+                sample[k] = v.cuda()
         sides = self._sides_of(sample)
         if sides is not None and "sides_mask" not in sample:
             # graph mode: the left/right pattern enters through a device mask instead of the launch sequence
@@ -279,6 +304,9 @@ class FlatAdamTrainer(object):
     def replay(self, sample=None):
         """Run the captured step; ``sample`` tensors (if given) are copied into the static input buffers."""
         if sample is not None and sample is not self._static_sample:
+            if not self.matches_captured(sample):
+                raise RuntimeError("FlatAdamTrainer.replay: the batch does not have the tensor keys / shapes of the "
+                                   "captured step (a partial last batch?); run it through step() instead")
             for k, v in sample.items():
                 if torch.is_tensor(v):
                     self._static_sample[k].copy_(v, non_blocking=True)
@@ -287,6 +315,17 @@ class FlatAdamTrainer(object):
         self._push_hyper()
         self._graph.replay()
         return self._static_loss
+
+    def matches_captured(self, sample):
+        """True when ``sample`` can be copied into the captured step's static buffers (same tensor keys and shapes)."""
+        if self._graph is None:
+            return False
+        static = self._static_sample
+        keys = {k for k, v in sample.items() if torch.is_tensor(v)}
+        skeys = {k for k, v in static.items() if torch.is_tensor(v) and k != "sides_mask"}
+        if keys - {"sides_mask"} != skeys:
+            return False
+        return all(tuple(sample[k].shape) == tuple(static[k].shape) for k in skeys)
 
     def release_graph(self):
         """Drop the captured step (graph, static inputs / outputs).  Must run before the NCCL process group is
@@ -301,7 +340,9 @@ class FlatAdamTrainer(object):
         checkpoint written here resumes under the reference's traineval.py and vice versa."""
         state = {}
         if self.step_count > 0:
-            for p, off, idx in zip(self.params, self.offsets, self.optim_index):
+            for i, (p, off, idx) in enumerate(zip(self.params, self.offsets, self.optim_index)):
+                if self._ever_updated and i not in self._ever_updated:
+                    continue   # never received a gradient: torch.optim.Adam holds no state for it
                 n = p.numel()
                 state[idx] = {"step": torch.tensor(float(self.step_count)),
                               "exp_avg": self.exp_avg[off:off + n].view_as(p).clone(),
@@ -332,10 +373,12 @@ class FlatAdamTrainer(object):
         steps = set()
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
-        for p, off, idx in zip(self.params, self.offsets, self.optim_index):
+        self._ever_updated = set()
+        for i, (p, off, idx) in enumerate(zip(self.params, self.offsets, self.optim_index)):
             st = state.get(idx)
             if st is None:
                 continue
+            self._ever_updated.add(i)
             n = p.numel()
             if st["exp_avg"].numel() != n:
                 raise ValueError("FlatAdamTrainer: optimizer state %d has %d elements, parameter has %d" % (

@@ -28,9 +28,9 @@ FULL_METRICS = [
     "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size",
     "sm__inst_executed.avg.per_cycle_elapsed", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"]
-KERNEL_LABELS = ["conv3x3 64x64 64->64", "conv3x3 32x32 128->128", "conv3x3 16x16 256->256", "conv3x3 8x8 512->512",
+KERNEL_LABELS = ["conv3x3 64x64 64->64 (conv64_v2)", "conv3x3 32x32 128->128", "conv3x3 16x16 256->256", "conv3x3 8x8 512->512",
                  "wgrad3x3 64x64 64->64", "wgrad3x3 32x32 128->128", "wgrad3x3 16x16 256->256",
-                 "wgrad3x3 8x8 512->512", "gemm 41088x257x515"]
+                 "wgrad3x3 8x8 512->512", "gemm (B*642)x257x515"]
 
 
 def launch_list(tag):
@@ -45,16 +45,17 @@ def launch_list(tag):
     for row in rows:
         per.setdefault(row["ID"], {"name": row["Kernel Name"]})[row["Metric Name"]] = float(row["Metric Value"].replace(",", ""))
     ids = list(per.keys())
-    stems = [i for i, k in enumerate(ids) if "stem_pack" in per[k]["name"]]
-    if len(stems) < 3:
-        print("launch list too short to contain a full step:", len(ids), "launches,", len(stems), "stem_pack")
+    # one training step = the launches between two consecutive fused-Adam launches (N = 1: one Adam per step)
+    adams = [i for i, k in enumerate(ids) if "adam_kernel" in per[k]["name"]]
+    if len(adams) < 2:
+        print("launch list too short to contain a full step:", len(ids), "launches,", len(adams), "adam_kernel")
         return
-    a, b = stems[1], stems[2]
+    a, b = adams[-2] + 1, adams[-1] + 1
     keep = set(ids[a:b])
     with open(os.path.join(PROF, "launches_%s_bench_step.csv" % tag), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv "
-                "python bench.py --steps 2 --warmup 1 --no-graph --no-cpu-baseline\n")
-        f.write("# one full training step (launch IDs %s..%s: stem_pack to stem_pack); times are cold-cache and serialised\n" % (ids[a], ids[b - 1]))
+                "python bench.py --config 3 --steps 1 --warmup 1 --no-graph --quick\n")
+        f.write("# one full training step (launch IDs %s..%s: Adam to Adam); times are cold-cache and serialised\n" % (ids[a], ids[b - 1]))
         f.write(lines[0])
         for l, row in zip(lines[1:], rows):
             if row["ID"] in keep:
@@ -69,21 +70,26 @@ def launch_list(tag):
         x[2] += v.get("dram__bytes_read.sum", 0)
         x[3] += v.get("dram__bytes_write.sum", 0)
     tot = sum(x[1] for x in agg.values())
-    tc = [x for n, x in agg.items() if "gemm_tc_kernel" in n or "wgrad_bf16_kernel" in n]
+    tc = [x for n, x in agg.items() if "gemm_tc_kernel" in n or "wgrad_bf16_kernel" in n or "conv64_" in n]
     n_tc, us_tc, by = sum(x[0] for x in tc), sum(x[1] for x in tc), sum(x[2] + x[3] for x in tc)
     with open(os.path.join(PROF, "launches_%s_bench_step_summary.txt" % tag), "w") as f:
-        f.write("# per-kernel totals of ONE training step (B=64, configs[1], bf16x3, eager launches, ncu serialises all streams) from "
+        f.write("# per-kernel totals of ONE training step (B=256, configs[2], bf16x3, eager launches, ncu serialises all streams) from "
                 "profiles/launches_%s_bench_step.csv\n" % tag)
         f.write("# %d launches, %.1f us serialised under ncu\n" % (b - a, tot))
         f.write("%-66s %5s %10s %6s %10s %10s\n" % ("kernel", "n", "us", "share", "dram rd MB", "dram wr MB"))
         for n, x in sorted(agg.items(), key=lambda q: -q[1][1]):
             f.write("%-66s %5d %10.1f %5.1f%% %10.1f %10.1f\n" % (n, x[0], x[1], 100 * x[1] / tot, x[2] / 1e6, x[3] / 1e6))
-        f.write("\n# tensor-core kernels (gemm_tc_kernel + wgrad_bf16_kernel): %d launches, %.1f us = %.1f%% of the step, DRAM "
+        f.write("\n# tensor-core kernels (gemm_tc_kernel + wgrad_bf16_kernel + conv64_*): %d launches, %.1f us = %.1f%% of the step, DRAM "
                 "traffic %.1f MB per step = %.2f MB per launch\n" % (n_tc, us_tc, 100 * us_tc / tot, by / 1e6, by / 1e6 / n_tc))
-    json.dump({"source": "profiles/launches_%s_bench_step.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, one B=64 step)" % tag,
-               "tensor_core_launches_per_step": n_tc, "dram_bytes_per_step": by, "dram_bytes_per_launch": by / n_tc,
-               "tensor_core_share_of_step_under_ncu": us_tc / tot, "step_us_under_ncu": tot, "launches_per_step": b - a},
-              open(os.path.join(PROF, "gemm_traffic_%s.json" % tag), "w"), indent=1)
+    sys.path.insert(0, ROOT)
+    import bench
+    rec = {"source": "profiles/launches_%s_bench_step.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, one B=256 "
+                     "configs[2] step)" % tag,
+           "precision": "bf16x3", "kernel_source_sha256": bench.kernel_source_hash(),
+           "tensor_core_launches_per_step": n_tc, "dram_bytes_per_step": by, "dram_bytes_per_launch": by / n_tc,
+           "tensor_core_share_of_step_under_ncu": us_tc / tot, "step_us_under_ncu": tot, "launches_per_step": b - a}
+    json.dump(rec, open(os.path.join(PROF, "gemm_traffic_%s.json" % tag), "w"), indent=1)
+    json.dump(rec, open(os.path.join(PROF, "gemm_traffic_current.json"), "w"), indent=1)
     print("launch list: %d launches / step, %.1f us, tensor-core share %.1f%%, %.2f MB DRAM per tensor-core launch" % (
         b - a, tot, 100 * us_tc / tot, by / 1e6 / n_tc))
 
@@ -98,8 +104,9 @@ def full_capture(tag):
     head, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(head)}
     with open(os.path.join(PROF, "ncu_full_%s_bf16x3_summary.txt" % tag), "w") as f:
-        f.write("# ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_kernel|wgrad_bf16_kernel' -c 10, "
-                "scripts/prof_kernels.py (B=64 layer shapes), PROF_PASSES=2 PROF_WG_PASSES=2 (3xBF16)\n")
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_kernel|wgrad_bf16_kernel|conv64_|"
+                "chamfer_bwd' -c 12, scripts/prof_kernels.py (PROF_B layer shapes in launch order: see the script's CASES), "
+                "PROF_PASSES=2 PROF_WG_PASSES=2 (3xBF16)\n")
         f.write("# source: gpurun_out/prof_%s.ncu-rep (not committed); extracted with ncu -i ... --page raw --csv\n" % tag)
         for k, row in enumerate(data):
             f.write("%s   [%s]\n" % (row[idx["Kernel Name"]][:70], KERNEL_LABELS[k] if k < len(KERNEL_LABELS) else ""))

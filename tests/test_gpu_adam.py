@@ -105,3 +105,39 @@ def test_flat_trainer_adam_update_matches_torch_adam():
             _close(p.data, q.data, 1e-6, "step %d" % step)
     sd = tr.state_dict()
     assert int(sd["state"][0]["step"]) == 5
+
+
+def test_parameters_without_gradient_are_skipped_like_torch_adam():
+    """torch.optim.Adam skips a parameter whose .grad is None (no moment decay, no weight decay, no state); the fused flat
+    kernel updates every slot, so the trainer restores such slots afterwards and leaves them out of its state dict
+    (with weight decay an unused parameter would otherwise drift)."""
+    from obman_train_b200.trainer import FlatAdamTrainer
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.used = torch.nn.Linear(8, 8)
+            self.unused = torch.nn.Linear(8, 8)
+
+        def forward(self, sample):
+            loss = self.used(sample["x"]).pow(2).sum().view(1)
+            return loss, {}, {"total_loss": loss}
+
+    torch.manual_seed(0)
+    model, twin = Net().cuda(), Net().cuda()
+    twin.load_state_dict(model.state_dict())
+    tr = FlatAdamTrainer(model, lr=1e-2, weight_decay=0.1, direct_grads=False)
+    opt = torch.optim.Adam(twin.parameters(), lr=1e-2, weight_decay=0.1)
+    x = torch.randn(4, 8, device="cuda")
+    unused0 = model.unused.weight.detach().clone()
+    for _ in range(3):
+        tr.step({"x": x})
+        opt.zero_grad(set_to_none=True)
+        twin({"x": x})[0].backward()
+        opt.step()
+    assert torch.equal(model.unused.weight.detach(), unused0)
+    for p, q in zip(model.parameters(), twin.parameters()):
+        assert torch.allclose(p.detach(), q.detach(), rtol=1e-5, atol=1e-7)
+    sd = tr.state_dict()
+    assert sorted(sd["state"].keys()) == [0, 1]          # used.weight, used.bias only
+    assert sorted(opt.state_dict()["state"].keys()) == [0, 1]

@@ -141,7 +141,8 @@ def test_handnet_in_training_mode_matches_oracle():
             continue
         d = p.grad.cpu().double() - og
         if og.norm().item() < 1e-9:   # biases in front of a batch-statistics BatchNorm: exact gradient zero
-            assert p.grad.abs().max().item() < 1e-3, (name, p.grad.abs().max().item())
+            wgrad = dict(model.named_parameters())[name.replace("bias", "weight")].grad
+            assert p.grad.abs().max().item() <= 1e-4 * wgrad.abs().max().item() + 1e-3, (name, p.grad.abs().max().item())
             continue
         rels.append((d.norm().item() / (og.norm().item() + 1e-12), name))
     rels.sort(reverse=True)

@@ -214,3 +214,21 @@ def test_mano_layer_large_batch_matches_small_batches(mano_tables_np):
     v_all, j_all = layer(pose, betas)
     v_part, j_part = layer(pose[300:307].contiguous(), betas[300:307].contiguous())
     assert torch.equal(v_all[300:307], v_part) and torch.equal(j_all[300:307], j_part)
+
+
+def test_nearest_neighbours_propagate_nan_like_torch_min():
+    """A NaN coordinate must give NaN distances (the reference's torch.min over the distance matrix does), not a huge
+    finite value with an arbitrary neighbour: the NaN query's own row, and - for a NaN candidate - every row of that
+    sample.  Other samples of the batch are unaffected."""
+    import torch
+    from obman_train_b200 import functional as Fb
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 700, 3, generator=g).cuda() * 40
+    y = torch.randn(3, 650, 3, generator=g).cuda() * 40
+    x[1, 5, 2] = float("nan")
+    minx, _, miny, _ = Fb.nearest_neighbours(x, y)
+    assert torch.isnan(minx[1, 5]) and torch.isfinite(minx[1, :5]).all() and torch.isfinite(minx[1, 6:]).all()
+    assert torch.isnan(miny[1]).all()                      # x[1] is the candidate cloud of the y -> x direction
+    assert torch.isfinite(minx[0]).all() and torch.isfinite(miny[0]).all() and torch.isfinite(minx[2]).all()
+    l1, l2 = Fb.chamfer(x, y)
+    assert torch.isnan(l1[1]) and torch.isnan(l2[1]) and torch.isfinite(l1[0]) and torch.isfinite(l2[2])

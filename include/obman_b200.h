@@ -50,7 +50,7 @@ int obman_chamfer_fwd(const float* preds, const float* gts, int B, int N, int M,
  * are (B) vectors; g_stride 0: each points to ONE float that applies to every sample (the gradient of
  * torch.mean(loss_1 + loss_2), atlasbranch.py:235,243, without materialising the expanded vector).  Scatter-free:
  * the inverse of the nearest-neighbour index is built per sample in shared memory, every output element is written
- * once in a fixed order (bit-reproducible); clouds beyond ~18 k points take a float-atomic fallback. */
+ * once in a fixed order (bit-reproducible); clouds beyond ~33 k points take a float-atomic fallback. */
 int obman_chamfer_bwd(const float* preds, const float* gts, const int* idx1, const int* idx2,
                       const float* gloss1, const float* gloss2, int g_stride, int B, int N, int M, float* gpreds,
                       float* ggts, void* stream);
@@ -199,10 +199,10 @@ int obman_bn_wgrad_finish(const float* dwraw, long long dw_ld, const float* w, c
                           const float* gbeta_sum, int O, int I, int KH, int KW, int Ip, int stem,
                           float* gw, float* ggamma, float* gbeta, float* gcbias, void* stream);
 /* AtlasNet decoder layer 1 after the conv1 split (atlasbranch.py:117-131 + atlasutils.py:65-67):
- * out[b,n,c] = [relu](sum_{k<3} grid[b*grid_bstride + 3n + k] * W1[c*ldw + k] + F[b*C + c]) (c < C), 0 (C <= c < ld);
- * relu = 0 gives the pre-activation (BatchNorm with batch statistics normalises it afterwards);
- * W1 = BatchNorm-folded conv1 weights (C, ldw) in fp32 (its first three input channels are the grid point). */
-int obman_pointmlp_l1_fwd(const float* grid, long long grid_bstride, const float* W1, int ldw, const float* F,
+ * out[b,n,c] = [relu](sum_{k<3} grid[b*grid_bstride + 3n + k] * Wg4[4c + k] + F[b*C + c]) (c < C), 0 (C <= c < ld);
+ * Wg4 (C, 4) = the first three input channels (the grid point) of the BatchNorm-folded conv1 weights, zero-padded to 4
+ * (16-byte aligned).  relu = 0 gives the pre-activation (BatchNorm with batch statistics normalises it afterwards). */
+int obman_pointmlp_l1_fwd(const float* grid, long long grid_bstride, const float* Wg4, const float* F,
                           int B, int N, int C, int ld, int relu, float* out, void* stream);
 /* dst (rows, ld_dst) = alpha * src[:, :C] where mask > 0 (mask NULL = everywhere), zero in columns C .. ld_dst-1:
  * pad / scale / ReLU-mask glue of the Linear and decoder backward passes in one launch. */

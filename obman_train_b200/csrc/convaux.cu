@@ -418,11 +418,12 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 // AtlasNet decoder, first layer after the algebraic split of conv1 (atlasutils.py:65-67 on the input of
 // atlasbranch.py:117-131): h1[b,n,c] = relu(sum_k grid[n,k] * W1[c,k] + F[b,c]) for c < C, 0 for C <= c < ld.
-// W1 = folded conv1 weights (C, ldw), columns 0..2 multiply the grid point (batch-independent grid, or per-sample
-// when grid_bstride != 0), F = feat * (s*W[:, 3:])^T + shift.
+// Wg = the three grid columns of the folded conv1 weights, compacted to (C, 4) rows {w0, w1, w2, 0} (one coalesced float4
+// per channel; reading them out of the (C, 516) weight rows made the kernel 4x slower), the grid is batch-independent
+// or per-sample (grid_bstride != 0), F = feat * (s*W[:, 3:])^T + shift.
 __global__ void __launch_bounds__(256)
-pointmlp_l1_fwd_kernel(const float* __restrict__ grid, long long grid_bstride, const float* __restrict__ W1,
-                       int ldw, const float* __restrict__ F, int B, int N, int C, int ld, int relu,
+pointmlp_l1_fwd_kernel(const float* __restrict__ grid, long long grid_bstride, const float4* __restrict__ Wg,
+                       const float* __restrict__ F, int B, int N, int C, int ld, int relu,
                        float* __restrict__ out) {
   const int ld4 = ld / 4;
   const size_t total = (size_t)B * N * ld4;
@@ -440,8 +441,8 @@ pointmlp_l1_fwd_kernel(const float* __restrict__ grid, long long grid_bstride, c
     const int cc = c + e;
     float r = 0.f;
     if (cc < C) {
-      const float* __restrict__ w = W1 + (size_t)cc * ldw;
-      r = fmaf(gz, w[2], fmaf(gy, w[1], fmaf(gx, w[0], F[(size_t)b * C + cc])));
+      const float4 w = __ldg(Wg + cc);
+      r = fmaf(gz, w.z, fmaf(gy, w.y, fmaf(gx, w.x, F[(size_t)b * C + cc])));
       if (relu) r = fmaxf(r, 0.f);
     }
     v[e] = r;
@@ -553,13 +554,13 @@ weighted_colsum_kernel(const float* __restrict__ x, long long rows, int C, long 
 
 using namespace obman;
 
-extern "C" int obman_pointmlp_l1_fwd(const float* grid, long long grid_bstride, const float* W1, int ldw,
+extern "C" int obman_pointmlp_l1_fwd(const float* grid, long long grid_bstride, const float* Wg4,
                                      const float* F, int B, int N, int C, int ld, int relu, float* out, void* stream) {
-  OBMAN_REQUIRE(grid && W1 && F && out && B > 0 && N > 0 && C > 0 && ld >= C && ld % 4 == 0 && ldw >= 3,
+  OBMAN_REQUIRE(grid && Wg4 && F && out && B > 0 && N > 0 && C > 0 && ld >= C && ld % 4 == 0 && (((uintptr_t)Wg4) & 15) == 0,
                 "obman_pointmlp_l1_fwd: bad arguments");
   const size_t total = (size_t)B * N * (ld / 4);
-  pointmlp_l1_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(grid, grid_bstride, W1, ldw,
-                                                                                         F, B, N, C, ld, relu, out);
+  pointmlp_l1_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      grid, grid_bstride, reinterpret_cast<const float4*>(Wg4), F, B, N, C, ld, relu, out);
   return check_launch("pointmlp_l1_fwd_kernel");
 }
 

@@ -129,15 +129,32 @@ chamfer_mean_kernel(const float* __restrict__ minx, const float* __restrict__ mi
 // written.  Shared memory: (2 A + 2 + O) ints.
 constexpr int CH_BWD_THREADS = 512;
 
+// index arrays in shared memory: 32-bit, or 16-bit (clouds below 65 536 points: half the shared memory, up to three
+// CTAs per SM at 10^4 points - the kernel is latency-bound on its random gathers, so residency is what counts)
+template <typename IT> struct IdxOps;
+template <> struct IdxOps<int> {
+  static __device__ __forceinline__ int add(int* arr, int j) { return atomicAdd(&arr[j], 1); }
+};
+template <> struct IdxOps<unsigned short> {
+  // 16-bit atomic increment on the containing 32-bit word (counts stay below 65 536: no carry into the neighbour)
+  static __device__ __forceinline__ int add(unsigned short* arr, int j) {
+    unsigned* word = reinterpret_cast<unsigned*>(arr) + (j >> 1);
+    const unsigned old = atomicAdd(word, (j & 1) ? 0x10000u : 1u);
+    return (int)((j & 1) ? (old >> 16) : (old & 0xffffu));
+  }
+};
+
+template <typename IT>
 __global__ void __launch_bounds__(CH_BWD_THREADS)
 chamfer_bwd_gather_kernel(const float* __restrict__ a, const float* __restrict__ o,
                           const int* __restrict__ idx_a, const int* __restrict__ idx_o,
                           const float* __restrict__ g_a, const float* __restrict__ g_o, int g_stride,
                           int A, int O, float* __restrict__ ga) {
-  extern __shared__ int sh[];
-  int* offs = sh;              // [A + 1] bucket offsets (exclusive scan of the counts)
-  int* cursor = sh + A + 1;    // [A]     counts, then fill cursors
-  int* list = sh + 2 * A + 1;  // [O]     indices of the other cloud, grouped by the point of `a` they map to
+  extern __shared__ int sh_raw[];
+  const int A2 = (A + 2) & ~1;                       // even lengths keep every array 4-byte aligned
+  IT* offs = reinterpret_cast<IT*>(sh_raw);          // [A + 1] bucket offsets (exclusive scan of the counts)
+  IT* cursor = offs + A2;                            // [A]     counts, then fill cursors
+  IT* list = cursor + A2;                            // [O]     indices of the other cloud, grouped by the point of `a` they map to
   __shared__ int warp_tot[CH_BWD_THREADS / 32];
   __shared__ int carry;
   const int b = blockIdx.x;
@@ -146,15 +163,15 @@ chamfer_bwd_gather_kernel(const float* __restrict__ a, const float* __restrict__
   const float* __restrict__ ob = o + (size_t)b * O * 3;
   const int* __restrict__ ia = idx_a + (size_t)b * A;
   const int* __restrict__ io = idx_o + (size_t)b * O;
-  for (int t = tid; t < A; t += CH_BWD_THREADS) cursor[t] = 0;
+  for (int t = tid; t < A2; t += CH_BWD_THREADS) cursor[t] = 0;
   if (tid == 0) carry = 0;
   __syncthreads();
-  for (int i = tid; i < O; i += CH_BWD_THREADS) atomicAdd(&cursor[io[i]], 1);
+  for (int i = tid; i < O; i += CH_BWD_THREADS) IdxOps<IT>::add(cursor, io[i]);
   __syncthreads();
   // exclusive scan of the counts, CH_BWD_THREADS entries per round
   for (int base = 0; base < A; base += CH_BWD_THREADS) {
     const int t = base + tid;
-    const int c = t < A ? cursor[t] : 0;
+    const int c = t < A ? (int)cursor[t] : 0;
     int incl = c;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -165,17 +182,17 @@ chamfer_bwd_gather_kernel(const float* __restrict__ a, const float* __restrict__
     __syncthreads();
     int before = carry;
     for (int w = 0; w < (tid >> 5); ++w) before += warp_tot[w];
-    if (t < A) offs[t] = before + incl - c;
+    if (t < A) offs[t] = (IT)(before + incl - c);
     __syncthreads();
     if (tid == CH_BWD_THREADS - 1) carry = before + incl;
     __syncthreads();
   }
-  if (tid == 0) offs[A] = carry;
-  for (int t = tid; t < A; t += CH_BWD_THREADS) cursor[t] = 0;
+  if (tid == 0) offs[A] = (IT)carry;
+  for (int t = tid; t < A2; t += CH_BWD_THREADS) cursor[t] = 0;
   __syncthreads();
   for (int i = tid; i < O; i += CH_BWD_THREADS) {
     const int j = io[i];
-    list[offs[j] + atomicAdd(&cursor[j], 1)] = i;
+    list[(int)offs[j] + IdxOps<IT>::add(cursor, j)] = (IT)i;
   }
   __syncthreads();
   const float sa = 2.f * g_a[(size_t)b * g_stride] / (float)A;
@@ -185,13 +202,13 @@ chamfer_bwd_gather_kernel(const float* __restrict__ a, const float* __restrict__
     const float x = ab[3 * t], y = ab[3 * t + 1], z = ab[3 * t + 2];
     const int n1 = ia[t];
     float gx = sa * (x - ob[3 * n1]), gy = sa * (y - ob[3 * n1 + 1]), gz = sa * (z - ob[3 * n1 + 2]);
-    const int lo = offs[t], hi = offs[t + 1];
+    const int lo = offs[t], hi = (t + 1 <= A) ? (int)offs[t + 1] : lo;
     // ascending order of the bucket's indices whatever order the fill left them in (buckets hold ~O/A entries)
     int prev = -1;
     for (int e = lo; e < hi; ++e) {
       int best = 0x7fffffff;
       for (int f = lo; f < hi; ++f) {
-        const int v = list[f];
+        const int v = (int)list[f];
         if (v > prev && v < best) best = v;
       }
       prev = best;
@@ -281,20 +298,32 @@ extern "C" int obman_chamfer_fwd(const float* preds, const float* gts, int B, in
   return check_launch("chamfer_mean_kernel");
 }
 
+static size_t chamfer_bwd_smem(int A, int O, bool narrow) {
+  const size_t A2 = (size_t)((A + 2) & ~1);
+  return (narrow ? sizeof(unsigned short) : sizeof(int)) * (2 * A2 + (size_t)((O + 1) & ~1)) + 16;
+}
+
 static int chamfer_bwd_side(const float* a, const float* o, const int* idx_a, const int* idx_o, const float* g_a,
                             const float* g_o, int g_stride, int B, int A, int O, float* ga, cudaStream_t st) {
-  const size_t smem = sizeof(int) * (size_t)(2 * A + 2 + O);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(chamfer_bwd_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(smem > 48 * 1024 ? smem : 48 * 1024));
+  const bool narrow = A < 65535 && O < 65535;
+  const size_t smem = chamfer_bwd_smem(A, O, narrow);
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[narrow]) {
+    const int want = (int)(smem > 48 * 1024 ? smem : 48 * 1024);
+    cudaError_t e = narrow ? cudaFuncSetAttribute(chamfer_bwd_gather_kernel<unsigned short>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, want)
+                           : cudaFuncSetAttribute(chamfer_bwd_gather_kernel<int>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, want);
     if (e != cudaSuccess) {
       set_error("chamfer_bwd: cudaFuncSetAttribute(%zu bytes) failed: %s", smem, cudaGetErrorString(e));
       return OBMAN_ERR_CUDA;
     }
-    configured = smem > 48 * 1024 ? smem : 48 * 1024;
+    configured[narrow] = (size_t)want;
   }
-  chamfer_bwd_gather_kernel<<<B, CH_BWD_THREADS, smem, st>>>(a, o, idx_a, idx_o, g_a, g_o, g_stride, A, O, ga);
+  if (narrow)
+    chamfer_bwd_gather_kernel<unsigned short><<<B, CH_BWD_THREADS, smem, st>>>(a, o, idx_a, idx_o, g_a, g_o, g_stride, A, O, ga);
+  else
+    chamfer_bwd_gather_kernel<int><<<B, CH_BWD_THREADS, smem, st>>>(a, o, idx_a, idx_o, g_a, g_o, g_stride, A, O, ga);
   return check_launch("chamfer_bwd_gather_kernel");
 }
 
@@ -307,7 +336,8 @@ extern "C" int obman_chamfer_bwd(const float* preds, const float* gts, const int
   OBMAN_REQUIRE(g_stride == 0 || g_stride == 1, "obman_chamfer_bwd: g_stride must be 0 (one scalar) or 1 (per sample)");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem_max = 200 * 1024;
-  if (sizeof(int) * (size_t)(2 * N + 2 + M) <= smem_max && sizeof(int) * (size_t)(2 * M + 2 + N) <= smem_max) {
+  const bool narrow = N < 65535 && M < 65535;
+  if (chamfer_bwd_smem(N, M, narrow) <= smem_max && chamfer_bwd_smem(M, N, narrow) <= smem_max) {
     int rc = chamfer_bwd_side(preds, gts, idx1, idx2, gloss1, gloss2, g_stride, B, N, M, gpreds, st);
     if (rc || !ggts) return rc;
     return chamfer_bwd_side(gts, preds, idx2, idx1, gloss2, gloss1, g_stride, B, M, N, ggts, st);

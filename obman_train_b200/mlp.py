@@ -200,7 +200,8 @@ class _PointDecoderFn(torch.autograd.Function):
             Fb = dense.gemm(feat, wfeat.contiguous(), bias=l1.shift, passes=pf)
         ld1, ld2 = _r32(C1), _r32(C2)
         h1 = _empty(B * N, ld1)
-        call("obman_pointmlp_l1_fwd", ptr(grid), N * 3 if per_sample else 0, ptr(l1.wf), l1.wf.stride(0), ptr(Fb), B, N,
+        wg4 = pad_scale_mask(l1.wf, 4, cols=3)               # (C1, 4): the grid columns, one float4 per channel
+        call("obman_pointmlp_l1_fwd", ptr(grid), N * 3 if per_sample else 0, ptr(wg4), ptr(Fb), B, N,
              C1, ld1, 1, ptr(h1), st)
         # padding columns of h2 (and of the gradient buffers below) are never read as data: GEMM A operands are fetched
         # through tensor maps whose K extent is the true channel count (TMA zero-fills beyond it), and in the
@@ -352,7 +353,8 @@ class _PointDecoderTrainFn(torch.autograd.Function):
         call("obman_pack_bf16", ptr(wfeat), l1.wf.stride(0), C1, Fdim, ptr(wpk), wpk.stride(0), st)
         Fb = dense.gemm(feat, wpk, bias=l1.shift, passes=pf, n=C1, k=Fdim, packed=True)     # (B,C1) incl. the conv bias
         z1 = _empty(B * N, ld1)     # the layer-1 kernel writes the padding columns as zeros
-        call("obman_pointmlp_l1_fwd", ptr(grid), N * 3 if per_sample else 0, ptr(l1.wf), l1.wf.stride(0), ptr(Fb), B, N,
+        wg4 = pad_scale_mask(l1.wf, 4, cols=3)
+        call("obman_pointmlp_l1_fwd", ptr(grid), N * 3 if per_sample else 0, ptr(wg4), ptr(Fb), B, N,
              C1, ld1, 0, ptr(z1), st)
         y1 = bn1.forward(z1)
         z2 = _zeros(B * N, ld2)

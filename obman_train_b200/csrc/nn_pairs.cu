@@ -198,25 +198,50 @@ chamfer_bwd_gather_kernel(const float* __restrict__ a, const float* __restrict__
   const float sa = 2.f * g_a[(size_t)b * g_stride] / (float)A;
   const float so = 2.f * g_o[(size_t)b * g_stride] / (float)O;
   float* __restrict__ gab = ga + (size_t)b * A * 3;
-  for (int t = tid; t < A; t += CH_BWD_THREADS) {
-    const float x = ab[3 * t], y = ab[3 * t + 1], z = ab[3 * t + 2];
-    const int n1 = ia[t];
-    float gx = sa * (x - ob[3 * n1]), gy = sa * (y - ob[3 * n1 + 1]), gz = sa * (z - ob[3 * n1 + 2]);
-    const int lo = offs[t], hi = (t + 1 <= A) ? (int)offs[t + 1] : lo;
-    // ascending order of the bucket's indices whatever order the fill left them in (buckets hold ~O/A entries)
-    int prev = -1;
-    for (int e = lo; e < hi; ++e) {
-      int best = 0x7fffffff;
-      for (int f = lo; f < hi; ++f) {
-        const int v = (int)list[f];
-        if (v > prev && v < best) best = v;
-      }
-      prev = best;
-      gx = fmaf(so, x - ob[3 * best], gx);
-      gy = fmaf(so, y - ob[3 * best + 1], gy);
-      gz = fmaf(so, z - ob[3 * best + 2], gz);
+  // four output points per thread and iteration: their (dependent) index -> coordinate gathers are issued together, the
+  // kernel is bound by the latency of those random reads, not by bandwidth
+  constexpr int U = 4;
+  for (int t0 = tid; t0 < A; t0 += U * CH_BWD_THREADS) {
+    int n1[U], lo[U], hi[U];
+    float px[U], py[U], pz[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u * CH_BWD_THREADS;
+      const bool in = t < A;
+      const int tc = in ? t : 0;
+      n1[u] = ia[tc];
+      px[u] = ab[3 * tc]; py[u] = ab[3 * tc + 1]; pz[u] = ab[3 * tc + 2];
+      lo[u] = in ? (int)offs[tc] : 0;
+      hi[u] = in ? (int)offs[tc + 1] : 0;
     }
-    gab[3 * t] = gx; gab[3 * t + 1] = gy; gab[3 * t + 2] = gz;
+    float gx[U], gy[U], gz[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      gx[u] = sa * (px[u] - ob[3 * n1[u]]);
+      gy[u] = sa * (py[u] - ob[3 * n1[u] + 1]);
+      gz[u] = sa * (pz[u] - ob[3 * n1[u] + 2]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      // ascending order of the bucket's indices whatever order the fill left them in (buckets hold ~O/A entries)
+      int prev = -1;
+      for (int e = lo[u]; e < hi[u]; ++e) {
+        int best = 0x7fffffff;
+        for (int f = lo[u]; f < hi[u]; ++f) {
+          const int v = (int)list[f];
+          if (v > prev && v < best) best = v;
+        }
+        prev = best;
+        gx[u] = fmaf(so, px[u] - ob[3 * best], gx[u]);
+        gy[u] = fmaf(so, py[u] - ob[3 * best + 1], gy[u]);
+        gz[u] = fmaf(so, pz[u] - ob[3 * best + 2], gz[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u * CH_BWD_THREADS;
+      if (t < A) { gab[3 * t] = gx[u]; gab[3 * t + 1] = gy[u]; gab[3 * t + 2] = gz[u]; }
+    }
   }
 }
 

@@ -90,3 +90,31 @@ def test_maxpool_and_stem_pack_vs_torch(B, H, C):
         for pw in range(2):
             for c in range(3):
                 assert torch.equal(xs[:, :, 2:-2, (ph * 2 + pw) * 3 + c], img[:, c, ph::2, pw::2])
+
+
+@pytest.mark.parametrize("env", [{"OBMAN_GEMM_STACK64": "1", "OBMAN_CONV64": "0"}, {"OBMAN_WGRAD_STACK64": "1"},
+                                 {"OBMAN_CONV64_GEN": "1"}, {"OBMAN_CONV64_GEN": "1", "OBMAN_CONV64_CFG": "18"},
+                                 {"OBMAN_CONV64": "0"}])
+def test_alternative_kernel_variants_in_a_subprocess(env):
+    """Kernel variants that are selected by environment switches read once per process (the stacked-N variants of the
+    generic kernels, the first generation of the persistent 64-channel kernel, the generic kernel on 64-channel layers)
+    ship in the library: each runs its 64-channel cases here, in a process of its own, against the fp64 references."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import importlib.util\n"
+        "spec = importlib.util.spec_from_file_location('probe_dense', %r)\n"
+        "m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)\n"
+        "names = ['conv3x3_s1_16_64_64_b3_epi', 'conv3x3_s1_50_64_64_b3_epi_ragged', 'dgrad3x3_s1_16_64_64_b3',\n"
+        "         'dgrad3x3_s2_32_64_128_b3', 'wgrad3x3_s1_16_64_64_b3', 'stemlike_wgrad_4x4_128_32_64_b3', 'gemm_64x33x256_b3']\n"
+        "for n in names:\n"
+        "    r = m.CASES[n]()\n"
+        "    assert not r['nan'] and r['rel'] < 5e-5, (n, r)\n"
+        "print('variants ok')\n" % (root, os.path.join(root, "scripts", "probe_dense.py")))
+    full_env = dict(os.environ)
+    full_env.update(env)
+    out = subprocess.run([sys.executable, "-c", code], env=full_env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "variants ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -93,3 +93,39 @@ def test_resnet18_mixed_bn_modes_are_rejected():
     model.layer3[0].bn1.train()
     with pytest.raises(NotImplementedError):
         model(torch.zeros(1, 3, 64, 64, device="cuda"))
+
+
+def test_resnet18_full_size_gradients_without_mask_injection():
+    """256x256 images (the benchmark's tile shapes: 128x128 stem, 64x64 layer1), B=2, against the PLAIN fp64 oracle: no
+    ReLU-mask or arg-max injection.  With ~10^4-10^5 pixels per channel the handful of pre-activations that fall on the
+    other side of zero than in fp64 no longer dominates any parameter gradient."""
+    from obman_train_b200.networks.bases.resnet import resnet18
+    torch.manual_seed(0)
+    model = resnet18()
+    _randomise_bn(model, 1)
+    model.eval()
+    state64 = {"base_net." + k: v.detach().double().clone() for k, v in model.state_dict().items()}
+    for k, v in state64.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    g = torch.Generator().manual_seed(2)
+    images = torch.rand(2, 3, 256, 256, generator=g) - 0.5
+    wts = torch.randn(2, 512, generator=g)
+    ref = nets.resnet18_features(state64, images.double(), "base_net", False)
+    (ref * wts.double()).sum().backward()
+    model = model.cuda()
+    feats, _ = model(images.cuda())
+    (feats * wts.cuda()).sum().backward()
+    scale = ref.abs().max().item()
+    err = (feats.detach().cpu().double() - ref.detach()).abs().max().item()
+    assert err < 2e-4 * scale, (err, scale)
+    l2s = []
+    for name, p in model.named_parameters():
+        if name.startswith("fc."):
+            continue
+        gref = state64["base_net." + name].grad
+        l2s.append((((p.grad.cpu().double() - gref).norm() / (gref.norm() + 1e-30)).item(), name))
+    l2s.sort(reverse=True)
+    print("full size, no injection: features rel err %.2e; worst gradients (L2 rel): %s" % (
+        err / scale, ["%s %.2e" % (n, r) for r, n in l2s[:4]]))
+    assert l2s[0][0] < 1e-2, l2s[:5]

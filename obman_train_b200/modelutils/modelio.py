@@ -92,46 +92,65 @@ def load_checkpoints(model, resume_paths, strict=True):
     return max(epochs), None
 
 
+def _best_score(checkpoint):
+    """The score stored next to the weights: "best_auc" / the deprecated "best_acc" (with the reference's warning) /
+    "best_score" (modelio.py:76-83)."""
+    for key, deprecated in (("best_auc", False), ("best_acc", True), ("best_score", False)):
+        if key in checkpoint:
+            if deprecated:
+                warnings.warn("Using deprecated best_acc instead of best_auc")
+            return checkpoint[key]
+    raise KeyError("checkpoint holds none of best_auc / best_acc / best_score")
+
+
+def _restore_optimizer(optimizer, checkpoint, resume_path):
+    """Optimizer state is best effort, as in the reference (modelio.py:60-73): a parameter-group mismatch is reported
+    and training continues with a fresh optimizer state."""
+    stored = checkpoint["optimizer"]
+    absent = set(optimizer.state_dict().keys()) - set(stored.keys())
+    if absent:
+        warnings.warn("Missing keys in optimizer ! : {}".format(absent))
+    try:
+        optimizer.load_state_dict(stored)
+    except ValueError:
+        traceback.print_exc()
+        warnings.warn("Couldn' load optimizer from {}".format(resume_path))
+
+
 def load_checkpoint(model, resume_path, optimizer=None, strict=True, load_atlas=False):
+    """-> (epoch, best score).  Same arguments, warnings and errors as modelio.py:31-84; the weights are copied IN PLACE
+    into ``model`` whatever prefix convention (``module.`` or none) either side uses."""
     if not os.path.isfile(resume_path):
         raise ValueError("=> no checkpoint found at '{}'".format(resume_path))
     print("=> loading checkpoint '{}'".format(resume_path))
     checkpoint = _read(resume_path)
-    state_dict = checkpoint["state_dict"]
+    weights = checkpoint["state_dict"]
     if load_atlas:
-        state_dict = _to_atlas_encoder(state_dict)
-    state_dict = _match_prefix(state_dict, model)
-    missing = set(model.state_dict().keys()) - set(state_dict.keys())
-    if len(missing) > 0:
-        warnings.warn("Missing keys ! : {}".format(missing))
-    _load_in_place(model, state_dict, strict)
+        weights = _to_atlas_encoder(weights)
+    weights = _match_prefix(weights, model)
+    absent = set(model.state_dict().keys()) - set(weights.keys())
+    if absent:
+        warnings.warn("Missing keys ! : {}".format(absent))
+    _load_in_place(model, weights, strict)
     print("=> loaded checkpoint '{}' (epoch {})".format(resume_path, checkpoint["epoch"]))
     if optimizer is not None:
-        try:
-            missing = set(optimizer.state_dict().keys()) - set(checkpoint["optimizer"].keys())
-            if len(missing) > 0:
-                warnings.warn("Missing keys in optimizer ! : {}".format(missing))
-            optimizer.load_state_dict(checkpoint["optimizer"])
-        except ValueError:
-            traceback.print_exc()
-            warnings.warn("Couldn' load optimizer from {}".format(resume_path))
-    if "best_auc" in checkpoint:
-        best = checkpoint["best_auc"]
-    elif "best_acc" in checkpoint:
-        warnings.warn("Using deprecated best_acc instead of best_auc")
-        best = checkpoint["best_acc"]
-    else:
-        best = checkpoint["best_score"]
-    return checkpoint["epoch"], best
+        _restore_optimizer(optimizer, checkpoint, resume_path)
+    return checkpoint["epoch"], _best_score(checkpoint)
 
 
 def save_checkpoint(state, is_best, checkpoint="checkpoint", filename="checkpoint.pth.tar", snapshot=None):
-    """``state`` is the dict traineval.py:374-384 builds: ``{"epoch", "network", "state_dict", "best_auc",
-    "optimizer"}``.  Keys are written with the ``module.`` prefix the reference expects (its loader also accepts
-    them without)."""
-    filepath = os.path.join(checkpoint, filename)
-    torch.save(state, filepath)
+    """Write ``state`` (the dict traineval.py:374-384 builds: epoch, network, state_dict, best score, optimizer) to
+    ``checkpoint/filename``; every ``snapshot``-th epoch also as ``checkpoint_<epoch>.pth.tar``, and as
+    ``model_best.pth.tar`` when ``is_best`` (same files as modelio.py:87-104).  The main file is written to a temporary
+    name first and renamed, so a job killed mid-write never leaves a truncated checkpoint behind."""
+    target = os.path.join(checkpoint, filename)
+    partial = target + ".tmp"
+    torch.save(state, partial)
+    os.replace(partial, target)
+    copies = []
     if snapshot and state["epoch"] % snapshot == 0:
-        shutil.copyfile(filepath, os.path.join(checkpoint, "checkpoint_{}.pth.tar".format(state["epoch"])))
+        copies.append("checkpoint_{}.pth.tar".format(state["epoch"]))
     if is_best:
-        shutil.copyfile(filepath, os.path.join(checkpoint, "model_best.pth.tar"))
+        copies.append("model_best.pth.tar")
+    for name in copies:
+        shutil.copyfile(target, os.path.join(checkpoint, name))

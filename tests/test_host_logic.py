@@ -148,3 +148,57 @@ def test_streams_module_is_a_no_op_when_disabled():
         assert (streams.WGRAD, streams.CHAIN, streams.BRANCH) == (0, 1, 2)
     finally:
         assert streams.set_enabled(prev) is False
+
+
+def test_loss_weights_host_mirror_and_slots():
+    """losshead.LossWeights: named slots, None / 0 stored as 0, host values readable without a device."""
+    from obman_train_b200.losshead import LossWeights
+    w = LossWeights(["a", "b", "one"])
+    w["a"], w["b"], w["one"] = 0.167, None, 1
+    assert w.slot == {"a": 0, "b": 1, "one": 2}
+    assert w["a"] == pytest.approx(0.167) and w["b"] == 0.0 and w["one"] == 1.0
+    w["a"] = 0.167 * 0.5
+    assert w.host[0] == pytest.approx(0.0835)
+    with pytest.raises(KeyError):
+        w["missing"] = 1.0
+
+
+def test_bench_workloads_follow_baseline_configs():
+    """bench.Workload: --config k = BASELINE.json configs[k-1]; default = configs[2] on one GPU, configs[3] under torchrun."""
+    import json
+    import os
+    import bench
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    configs = json.load(open(os.path.join(root, "BASELINE.json")))["configs"]
+    assert bench.default_config(1) == 3 and bench.default_config(8) == 4
+    w1, w2, w3, w4 = (bench.Workload(k) for k in (1, 2, 3, 4))
+    assert w1.hand_only and w1.batch == 1 and "single 256" in configs[0]
+    assert (w2.batch, w2.n_obj, w2.n_gt) == (64, 642, 600) and "batch 64" in configs[1]
+    assert (w3.batch, w3.n_obj, w3.n_gt) == (256, 2562, 2500) and "batch 256" in configs[2]
+    assert w3.cfg["atlas_separate_encoder"] and w3.cfg["contact_zones"] == "zones" and w3.cfg["contact_lambda"]
+    assert w4.batch == 128 and w4.cfg["atlas_lambda_regul_edges"] > 0 and "batch 1024" in configs[3]
+    for k, name in ((2, "configs[1]"), (3, "configs[2]"), (4, "configs[3]")):
+        assert name in bench.Workload(k).name
+    s = w3.sample(2, 0)
+    assert s["images"].shape == (2, 3, 256, 256) and s["objpoints3d"].shape == (2, 2500, 3) and s["verts3d"].shape == (2, 778, 3)
+    assert sorted(w1.sample(1, 0).keys()) == ["images", "joints3d", "root", "sides"]
+
+
+def test_bench_traffic_record_goes_stale_with_the_kernel_sources(tmp_path, monkeypatch):
+    """roofline.traffic is only reported while csrc/ hashes to the profiled build (it used to be a constant)."""
+    import json
+    import os
+    import bench
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    monkeypatch.setattr(bench, "kernel_source_hash", lambda: "abc")
+    rec = {"source": "x", "precision": "bf16x3", "kernel_source_sha256": "abc", "dram_bytes_per_launch": 1.0}
+    (prof / "gemm_traffic_current.json").write_text(json.dumps(rec))
+    tr, src = bench.traffic_record("bf16x3")
+    assert tr["dram_bytes_per_launch"] == 1.0 and src == "x"
+    rec["kernel_source_sha256"] = "other"
+    (prof / "gemm_traffic_current.json").write_text(json.dumps(rec))
+    tr, src = bench.traffic_record("bf16x3")
+    assert tr is None and "stale" in src
+    assert bench.traffic_record("tf32") == (None, None) or bench.traffic_record("tf32")[0] is None

@@ -210,12 +210,10 @@ int obman_pad_scale_mask(const float* src, long long ld_src, const float* mask, 
                          int C, float alpha, float* dst, int ld_dst, void* stream);
 /* out (K, ld_out) = transpose of w (N, K) in the obman_pack_bf16 layout (B operand of a Linear data gradient). */
 int obman_pack_bf16_t(const float* w, long long ldw, int N, int K, float* out, long long ld_out, void* stream);
-/* out[c * ld_out + k] = sum_r x[r * ld + c] * w[r * K + k], K <= 4: grid part of the decoder's conv1 weight gradient. */
-int obman_weighted_colsum(const float* x, long long rows, int C, long long ld, const float* w, int K, float* out,
-                          long long ld_out, void* stream);
-/* g (B,N, ld) -> gF[b,c] = sum_n g, gG[n,c] = sum_b g (gG may be NULL). */
-int obman_pointmlp_l1_bwd(const float* g, int B, int N, int C, int ld, float* gF, float* gG,
-                          void* stream);
+/* One pass over g (B,N, ld): gF[b,c] = sum_n g[b,n,c]; dw[c * ld_dw + k] = sum_{b,n} g[b,n,c] * grid[n,k], k < 3 (the grid
+ * columns of the conv1 weight gradient).  grid (N,3), or (B,N,3) with grid_bstride = 3 N.  gW: scratch of 3 B C floats. */
+int obman_pointmlp_l1_bwd(const float* g, const float* grid, long long grid_bstride, int B, int N, int C, int ld,
+                          float* gF, float* gW, float* dw, long long ld_dw, void* stream);
 /* Cotangent-Laplacian regulariser (laplacianloss.py:24-41: loss = mean_{b,i} ||(L V_b)_i||_2; L built once from the
  * unit icosphere, laplacianloss.py:100-131).  L is passed in ELL form: nbr (N,K) int32 neighbour ids, w (N,K) the
  * off-diagonal entries L_ij (rows padded with w = 0); the diagonal is -sum_j L_ij by construction.

@@ -26,18 +26,6 @@ namespace obman {
 extern long long* g_trace;
 extern long long g_trace_cap;
 
-// wait-time accounting (obman_debug_trace): a timed mbarrier wait adds the cycles it blocked to `acc`
-__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, bool timed, long long& acc) {
-  if (!timed) { mbar_wait(bar, parity); return; }
-  const long long t0 = clock64();
-  mbar_wait(bar, parity);
-  acc += clock64() - t0;
-}
-__device__ __forceinline__ void trace_put(const GemmEpilogue& epi, int k, long long v) {
-  if (epi.trace == nullptr || ((long long)blockIdx.x + 1) * 16 > epi.trace_cap) return;
-  epi.trace[(long long)blockIdx.x * 16 + k] = v;
-}
-
 constexpr int P64_HALO_BYTES = 25600;   // up to 200 halo pixels x 32 channels fp32
 constexpr int P64_RA_MAX = 6;           // halo boxes in flight (as many as fit next to the resident weights, >= 2)
 constexpr int P64_WT_TILE = 8192;       // 128 rows (64 hi + 64 lo) x 64 B

@@ -216,6 +216,8 @@ maxpool_bwd_kernel(const float* __restrict__ gout, const unsigned char* __restri
   const int c4 = u % C4, w = u / C4;
   const int h = blockIdx.y, b = blockIdx.z;
   const size_t t = ((size_t)b * H + h) * (size_t)(W * C4) + u;
+  // (two restructurings that put the loads of all candidate windows in flight together - unconditional with clamped
+  // addresses, and predicated without a loop - were measured 13 % and 30 % SLOWER than this loop, gpurun r2w / r2aa)
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int i = (h + 1) / 2 - 1; i <= (h + 1) / 2; ++i) {
     if (i < 0 || i >= Ho) continue;
@@ -421,65 +423,110 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 // Wg = the three grid columns of the folded conv1 weights, compacted to (C, 4) rows {w0, w1, w2, 0} (one coalesced float4
 // per channel; reading them out of the (C, 516) weight rows made the kernel 4x slower), the grid is batch-independent
 // or per-sample (grid_bstride != 0), F = feat * (s*W[:, 3:])^T + shift.
+constexpr int L1F_ROWS = 4;   // points per thread: the weights / feature part of a channel quad are loaded once for all of them
+
 __global__ void __launch_bounds__(256)
 pointmlp_l1_fwd_kernel(const float* __restrict__ grid, long long grid_bstride, const float4* __restrict__ Wg,
                        const float* __restrict__ F, int B, int N, int C, int ld, int relu,
                        float* __restrict__ out) {
+  // grid (ceil(ceil(N/4) * ld/4 / 256), B): thread = (group of 4 consecutive points, 4 consecutive channels); 32-bit
+  // index arithmetic per sample
   const int ld4 = ld / 4;
-  const size_t total = (size_t)B * N * ld4;
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total) return;
-  const int c = (int)(t % ld4) * 4;
-  const size_t row = t / ld4;
-  const int n = (int)(row % N);
-  const int b = (int)(row / N);
-  const float* __restrict__ gp = grid + (size_t)b * grid_bstride + (size_t)n * 3;
-  const float gx = gp[0], gy = gp[1], gz = gp[2];
-  float v[4];
+  const int groups = (N + L1F_ROWS - 1) / L1F_ROWS;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= groups * ld4) return;
+  const int b = blockIdx.y;
+  const int ng = t / ld4;
+  const int c4 = t - ng * ld4;
+  const int c = c4 * 4;
+  const float* __restrict__ Fb = F + (size_t)b * C;
+  float4 w[4];
+  float f[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const int cc = c + e;
-    float r = 0.f;
-    if (cc < C) {
-      const float4 w = __ldg(Wg + cc);
-      r = fmaf(gz, w.z, fmaf(gy, w.y, fmaf(gx, w.x, F[(size_t)b * C + cc])));
-      if (relu) r = fmaxf(r, 0.f);
-    }
-    v[e] = r;
+    const bool ok = c + e < C;
+    w[e] = ok ? __ldg(Wg + c + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    f[e] = ok ? __ldg(Fb + c + e) : 0.f;
   }
-  reinterpret_cast<float4*>(out)[t] = make_float4(v[0], v[1], v[2], v[3]);
-}
-
-// gF[b,c] = sum_n g[b,n,c]   (g has row stride ld); grid (ceil(C/32), B)
-__global__ void __launch_bounds__(256)
-pointmlp_l1_bwd_f_kernel(const float* __restrict__ g, int N, int C, int ld, float* __restrict__ gF) {
-  __shared__ float red[8][33];
-  const int b = blockIdx.y;
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int ry = threadIdx.x >> 5;
-  float s = 0.f;
-  if (c < C)
-    for (int n = ry; n < N; n += 8) s += g[((size_t)b * N + n) * ld + c];
-  red[ry][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (ry == 0 && c < C) {
-    float tot = 0.f;
+  const float* __restrict__ gp = grid + (size_t)b * grid_bstride;
+  float4* __restrict__ ob = reinterpret_cast<float4*>(out) + (size_t)b * N * ld4 + c4;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) tot += red[k][threadIdx.x & 31];
-    gF[(size_t)b * C + c] = tot;
+  for (int j = 0; j < L1F_ROWS; ++j) {
+    const int n = ng * L1F_ROWS + j;
+    if (n >= N) break;
+    const float gx = __ldg(gp + 3 * n), gy = __ldg(gp + 3 * n + 1), gz = __ldg(gp + 3 * n + 2);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float r = fmaf(gz, w[e].z, fmaf(gy, w[e].y, fmaf(gx, w[e].x, f[e])));   // padding channels: all-zero operands
+      if (relu) r = fmaxf(r, 0.f);
+      v[e] = r;
+    }
+    ob[(size_t)n * ld4] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
-// gG[n,c] = sum_b g[b,n,c]
+// Backward of the split first decoder layer, one pass over g = d loss / d (pre-activation of layer 1), row stride ld:
+//   gF[b,c]   = sum_n g[b,n,c]                   gradient of the per-sample feature part F (and, summed over b, of the shift)
+//   gW[b,k,c] = sum_n g[b,n,c] * grid[b?,n,k]    per-sample partial of the grid columns of the conv1 weight gradient
+// grid (ceil(C/32), B); fixed summation order.  (Was two kernels that each read g: a per-sample column sum and a sum over
+// the batch per point followed by a weighted column sum.)
 __global__ void __launch_bounds__(256)
-pointmlp_l1_bwd_g_kernel(const float* __restrict__ g, int B, int N, int C, int ld, float* __restrict__ gG) {
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (size_t)N * C) return;
-  const int c = (int)(t % C);
-  const int n = (int)(t / C);
+pointmlp_l1_bwd_kernel(const float* __restrict__ g, const float* __restrict__ grid, long long grid_bstride, int N, int C,
+                       int ld, float* __restrict__ gF, float* __restrict__ gW) {
+  // grid (ceil(ld / 128), B): a warp covers 128 consecutive columns (one float4 per lane) of one row, the 8 warps of the
+  // CTA take every 8th row; the three grid coordinates of a row are one broadcast load per 4 columns.  Columns >= C of
+  // the padded rows may hold anything: they are summed but never written.
+  __shared__ float4 red[8][4][32];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const int ry = threadIdx.x >> 5;
+  const float* __restrict__ gp = grid + (size_t)b * grid_bstride;
+  float4 acc[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < ld) {
+    const float* __restrict__ gb = g + (size_t)b * N * ld + c;
+#pragma unroll 4
+    for (int n = ry; n < N; n += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(gb + (size_t)n * ld));
+      const float w0 = __ldg(gp + 3 * n + 0), w1 = __ldg(gp + 3 * n + 1), w2 = __ldg(gp + 3 * n + 2);
+      acc[0].x += v.x; acc[0].y += v.y; acc[0].z += v.z; acc[0].w += v.w;
+      acc[1].x = fmaf(v.x, w0, acc[1].x); acc[1].y = fmaf(v.y, w0, acc[1].y);
+      acc[1].z = fmaf(v.z, w0, acc[1].z); acc[1].w = fmaf(v.w, w0, acc[1].w);
+      acc[2].x = fmaf(v.x, w1, acc[2].x); acc[2].y = fmaf(v.y, w1, acc[2].y);
+      acc[2].z = fmaf(v.z, w1, acc[2].z); acc[2].w = fmaf(v.w, w1, acc[2].w);
+      acc[3].x = fmaf(v.x, w2, acc[3].x); acc[3].y = fmaf(v.y, w2, acc[3].y);
+      acc[3].z = fmaf(v.z, w2, acc[3].z); acc[3].w = fmaf(v.w, w2, acc[3].w);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) red[ry][k][lane] = acc[k];
+  __syncthreads();
+  if (ry < 4) {
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      const float4 t = red[y][ry][lane];
+      tot.x += t.x; tot.y += t.y; tot.z += t.z; tot.w += t.w;
+    }
+    float* dst = ry == 0 ? gF + (size_t)b * C : gW + ((size_t)b * 3 + (ry - 1)) * C;
+    const float tv[4] = {tot.x, tot.y, tot.z, tot.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) if (c + e < C) dst[c + e] = tv[e];
+  }
+}
+
+// dw[c * ld_dw + k] = sum_b gW[b,k,c]
+__global__ void __launch_bounds__(256)
+pointmlp_l1_bwd_finish_kernel(const float* __restrict__ gW, int B, int C, float* __restrict__ dw, long long ld_dw) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * C) return;
+  const int k = t / C, c = t - k * C;
   float s = 0.f;
-  for (int b = 0; b < B; ++b) s += g[((size_t)b * N + n) * ld + c];
-  gG[t] = s;
+  for (int b = 0; b < B; ++b) s += gW[((size_t)b * 3 + k) * C + c];
+  dw[(size_t)c * ld_dw + k] = s;
 }
 
 // dst (rows, ld_dst) <- alpha * src[:, :C] (row stride ld_src), entries whose mask value is <= 0 zeroed (mask nullable, row
@@ -521,35 +568,6 @@ pack_bf16_t_kernel(const float* __restrict__ w, long long ldw, int N, int K, uin
   out[k * ld_out + blk * 32 + 16 + in] = lo;
 }
 
-// out[c * ld_out + k] = sum_r x[r, c] * w[r, k]  (x (rows, ld), w (rows, K), K <= 4): the grid part of the decoder's conv1
-// weight gradient (the reference's conv1 sees cat(grid, feature): its first three input channels are the grid point).
-// One CTA per 32 columns, fixed summation order.
-__global__ void __launch_bounds__(256)
-weighted_colsum_kernel(const float* __restrict__ x, long long rows, int C, long long ld, const float* __restrict__ w,
-                       int K, float* __restrict__ out, long long ld_out) {
-  __shared__ float red[8][32][4];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int ry = threadIdx.x >> 5;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (c < C) {
-    for (long long r = ry; r < rows; r += 8) {
-      const float v = x[r * ld + c];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) if (k < K) acc[k] = fmaf(v, w[r * K + k], acc[k]);
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) red[ry][threadIdx.x & 31][k] = acc[k];
-  __syncthreads();
-  if (ry == 0 && c < C) {
-    for (int k = 0; k < K; ++k) {
-      float s = 0.f;
-      for (int y = 0; y < 8; ++y) s += red[y][threadIdx.x][k];
-      out[(size_t)c * ld_out + k] = s;
-    }
-  }
-}
-
 }  // namespace obman
 
 using namespace obman;
@@ -558,8 +576,9 @@ extern "C" int obman_pointmlp_l1_fwd(const float* grid, long long grid_bstride, 
                                      const float* F, int B, int N, int C, int ld, int relu, float* out, void* stream) {
   OBMAN_REQUIRE(grid && Wg4 && F && out && B > 0 && N > 0 && C > 0 && ld >= C && ld % 4 == 0 && (((uintptr_t)Wg4) & 15) == 0,
                 "obman_pointmlp_l1_fwd: bad arguments");
-  const size_t total = (size_t)B * N * (ld / 4);
-  pointmlp_l1_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  OBMAN_REQUIRE(B <= 65535 && (long long)N * (ld / 4) < 0x7fffffffLL, "obman_pointmlp_l1_fwd: batch / cloud too large for the grid");
+  const unsigned per_sample = (unsigned)(((long long)((N + L1F_ROWS - 1) / L1F_ROWS) * (ld / 4) + 255) / 256);
+  pointmlp_l1_fwd_kernel<<<dim3(per_sample, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
       grid, grid_bstride, reinterpret_cast<const float4*>(Wg4), F, B, N, C, ld, relu, out);
   return check_launch("pointmlp_l1_fwd_kernel");
 }
@@ -584,24 +603,17 @@ extern "C" int obman_pack_bf16_t(const float* w, long long ldw, int N, int K, fl
   return check_launch("pack_bf16_t_kernel");
 }
 
-extern "C" int obman_weighted_colsum(const float* x, long long rows, int C, long long ld, const float* w, int K,
-                                     float* out, long long ld_out, void* stream) {
-  OBMAN_REQUIRE(x && w && out && rows > 0 && C > 0 && ld >= C && K >= 1 && K <= 4 && ld_out >= K,
-                "obman_weighted_colsum: bad arguments");
-  weighted_colsum_kernel<<<(C + 31) / 32, 256, 0, (cudaStream_t)stream>>>(x, rows, C, ld, w, K, out, ld_out);
-  return check_launch("weighted_colsum_kernel");
-}
-
-extern "C" int obman_pointmlp_l1_bwd(const float* g, int B, int N, int C, int ld, float* gF, float* gG,
-                                     void* stream) {
-  OBMAN_REQUIRE(g && gF && B > 0 && N > 0 && C > 0 && ld >= C && B <= 65535, "obman_pointmlp_l1_bwd: bad arguments");
+extern "C" int obman_pointmlp_l1_bwd(const float* g, const float* grid, long long grid_bstride, int B, int N, int C,
+                                     int ld, float* gF, float* gW, float* dw, long long ld_dw, void* stream) {
+  OBMAN_REQUIRE(g && grid && gF && gW && dw && B > 0 && N > 0 && C > 0 && ld >= C && ld_dw >= 3 && B <= 65535,
+                "obman_pointmlp_l1_bwd: bad arguments");
+  OBMAN_REQUIRE(ld % 4 == 0 && ((uintptr_t)g & 15) == 0, "obman_pointmlp_l1_bwd: g must be 16-byte aligned, ld a multiple of 4");
   cudaStream_t st = (cudaStream_t)stream;
-  pointmlp_l1_bwd_f_kernel<<<dim3((C + 31) / 32, B), 256, 0, st>>>(g, N, C, ld, gF);
-  int rc = check_launch("pointmlp_l1_bwd_f_kernel");
-  if (rc || !gG) return rc;
-  const size_t total = (size_t)N * C;
-  pointmlp_l1_bwd_g_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, B, N, C, ld, gG);
-  return check_launch("pointmlp_l1_bwd_g_kernel");
+  pointmlp_l1_bwd_kernel<<<dim3((ld + 127) / 128, B), 256, 0, st>>>(g, grid, grid_bstride, N, C, ld, gF, gW);
+  int rc = check_launch("pointmlp_l1_bwd_kernel");
+  if (rc) return rc;
+  pointmlp_l1_bwd_finish_kernel<<<(3 * C + 255) / 256, 256, 0, st>>>(gW, B, C, dw, ld_dw);
+  return check_launch("pointmlp_l1_bwd_finish_kernel");
 }
 
 extern "C" int obman_stem_pack(const float* x, int B, int H, int W, float* out, void* stream) {

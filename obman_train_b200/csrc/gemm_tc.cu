@@ -51,149 +51,23 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// Epilogue shared by the GEMM kernels: wait for the accumulator, then TMEM -> registers -> global.
-// Called by the four epilogue warps (q = TMEM lane quadrant, r = q * 32 + lane = tile row); `smem` is the tile
-// buffer base (its first 16 KB are reused for staging, every operand read has retired by then).
-template <int BN, int MODE>
-__device__ __forceinline__ void gemm_epilogue(uint8_t* smem, uint32_t tmem_base, uint64_t* accum,
-                                              const GemmProgram& prog, const GemmEpilogue& epi, int m0, int n0,
-                                              int n_img0, int h0, int w0, int q, int lane, int r) {
-    // ---- epilogue ----
-    // TMEM -> registers (lane = tile row) -> XOR-swizzled shared-memory transpose -> each store / addend / mask
-    // instruction touches 4 rows x 128 contiguous bytes (the row-per-lane layout would touch 32 rows x 16 bytes).
-    // The global reads (residual addend, ReLU-mask source) of the first 32-column chunk are issued BEFORE the wait for
-    // the accumulator, so their latency hides behind the last MMAs.  (Fetching chunk c+1 row group by row group while
-    // chunk c is consumed was measured slower: the late rows' loads are exposed again and interleave with the stores.)
-    const int cc = lane & 7;     // 16-byte column chunk handled by this lane after the transpose
-    const int rsub = lane >> 3;  // row within each group of 4
-    long long ro[8];             // element offsets of the 8 rows this lane stores (row 4 i + rsub of the warp's 32), -1 = none
-    float4 add4[8], msk4[8];
-    bool ptr_ok = false;
-    if (MODE != 2) {
-      bool row_ok;
-      long long row_off;
-      if (MODE == 0 && prog.spatial) {
-        const int tw = r % prog.TW;
-        const int th = (r / prog.TW) % prog.TH;
-        const int tn = r / (prog.TW * prog.TH);
-        const int n = n_img0 + tn, h = h0 + th, w = w0 + tw;
-        row_ok = n < prog.n_img && h < prog.h_out && w < prog.w_out;
-        row_off = n * epi.sN + h * epi.sH + w * epi.sW;
-      } else {
-        row_ok = (m0 + r) < prog.M;
-        row_off = (long long)(m0 + r) * epi.ld;
-      }
-      const long long mine = row_ok ? row_off : -1;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ro[i] = __shfl_sync(0xffffffffu, mine, 4 * i + rsub);
-      ptr_ok = ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.addend) |
-                 reinterpret_cast<uintptr_t>(epi.mask_src)) & 15) == 0 && !epi.accumulate;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) epilogue_prefetch(epi, prog, ro[i], n0 + 4 * cc, ptr_ok, add4[i], msk4[i]);
-    }
-    mbar_wait(accum, 0);
-    tc_fence_after();
-    if (r == 0) trace_stamp(epi, 6);
-    if (MODE == 2) {
-      // D[m, n] with m = stacked (tap, c_in) index and n = output channel; dw is (c_out, taps*c_in) row-major, so
-      // element (m, n) lives at n*ld + m: the 32 lanes of a warp (consecutive m) make every column one coalesced access.
-      const bool row_ok = (m0 + r) < prog.M;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= prog.N) break;  // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = n0 + c0 + j;
-          if (col >= prog.N) break;
-          float* dst = epi.out + (long long)col * epi.ld + (m0 + r);
-          const float y = epi.alpha * __uint_as_float(v[j]);
-          if (epi.accumulate) atomicAdd(dst, y);
-          else *dst = y;
-        }
-      }
-    } else {
-    // all MMAs (and therefore all TMA loads and operand reads) have retired: stage 0 is free for staging
-    uint8_t* wbase = smem + q * 4096;                                   // 32 rows x 128 B per warp
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= prog.N) break;  // warp-uniform
-      const int col = n0 + c0 + 4 * cc;
-      const bool colvec = (col + 3 < prog.N) && ptr_ok;
-      // issue every global read of this chunk (residual, ReLU-mask source, bias) before touching the accumulator:
-      // they are independent, so their latencies overlap instead of forming 8 serial round trips (chunk 0 was
-      // fetched before the accumulator wait)
-      if (c0 > 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) epilogue_prefetch(epi, prog, ro[i], col, ptr_ok, add4[i], msk4[i]);
-      }
-      float bias4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (epi.bias) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) if (col + e < prog.N) bias4[e] = __ldg(epi.bias + col + e);
-      }
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      // Keep the mask words opaque until here.  Without this the compiler folds every mask load into predicate bits
-      // right behind the load (FSETP on the freshly loaded registers), which turns the 8 independent loads into 8
-      // serial memory round trips per chunk: +42 % on the 64-channel data-gradient kernels (scripts/ab_conv.py).
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        asm volatile("" : "+f"(msk4[i].x), "+f"(msk4[i].y), "+f"(msk4[i].z), "+f"(msk4[i].w));
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(wbase + lane * 128 + ((c ^ (lane & 7)) << 4)) =
-            make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = 4 * i + rsub;
-        const long long row_off = ro[i];
-        if (row_off >= 0 && col < prog.N) {
-          const float4 a = *reinterpret_cast<const float4*>(wbase + rr * 128 + ((cc ^ (rr & 7)) << 4));
-          float x[4] = {epi.alpha * a.x + bias4[0], epi.alpha * a.y + bias4[1], epi.alpha * a.z + bias4[2],
-                        epi.alpha * a.w + bias4[3]};
-          if (colvec && ((row_off & 3) == 0)) {
-            x[0] += add4[i].x; x[1] += add4[i].y; x[2] += add4[i].z; x[3] += add4[i].w;
-            if (epi.relu) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
-            }
-            x[0] = msk4[i].x > 0.f ? x[0] : 0.f; x[1] = msk4[i].y > 0.f ? x[1] : 0.f;
-            x[2] = msk4[i].z > 0.f ? x[2] : 0.f; x[3] = msk4[i].w > 0.f ? x[3] : 0.f;
-            *reinterpret_cast<float4*>(epi.out + row_off + col) = make_float4(x[0], x[1], x[2], x[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (col + e >= prog.N) break;
-              float y = x[e];
-              if (epi.addend) y += epi.addend[row_off + col + e];
-              if (epi.relu) y = fmaxf(y, 0.f);
-              if (epi.mask_src) y = epi.mask_src[row_off + col + e] > 0.f ? y : 0.f;
-              if (epi.accumulate) atomicAdd(epi.out + row_off + col + e, y);
-              else epi.out[row_off + col + e] = y;
-            }
-          }
-        }
-      }
-      __syncwarp();  // staging is overwritten by the next chunk
-    }
-    }  // MODE != 2
-}
-
 // CL > 1 (TS path only): thread-block cluster of CL CTAs along the M-tile axis.  They share the weight tile, so
 // each CTA fetches 1/CL of it and TMA-multicasts it to all of them: the kernels were L2->SM bandwidth bound
 // (~9 TB/s measured against ~42 B/clk/SM), the weight tile being 2/3 of the bytes of every K block.
-template <int BN, int PASSES, int MODE, int TS, int OCC, int CL>
+//
+// TAIL = 1 (TS == 2, plain matrices): N = 256 j + (1..4) columns, as in the point decoder (515 -> 257 -> 128: the "+3" / "+1"
+// of the concatenated grid coordinates survive the halvings).  A column tile of their own would repeat the whole
+// conversion of the A tile into tensor memory - which paces this kernel - for 1-3 useful columns; instead the
+// splitter thread of row r, which holds the 32 fp32 values of its row in registers anyway, accumulates those columns
+// with plain FMAs.  Their weights are unpacked per K block by the otherwise idle lanes of the producer warp into a
+// small shared-memory ring that travels with the pipeline stages.
+template <int BN, int PASSES, int MODE, int TS, int OCC, int CL, int TAIL>
 __global__ void __launch_bounds__(GEMM_THREADS, OCC)
 gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, const GemmEpilogue epi) {
   using Cfg = GemmCfg<BN, PASSES, TS, OCC>;
   static_assert(Cfg::STAGES >= 2, "pipeline needs at least two stages");
   static_assert(CL == 1 || (TS >= 1 && MODE == 0), "clusters are only used on the TS path");
+  static_assert(TAIL == 0 || (TS == 2 && MODE == 0 && CL == 1), "tail columns exist on the plain 3xBF16 path only");
   constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1);
   const uint32_t cl_rank = CL > 1 ? cluster_ctarank() : 0;
   constexpr int S = Cfg::STAGES;
@@ -206,6 +80,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   uint64_t* empty = bars + 2 * S;   // [S] MMAs reading the stage retired
   uint64_t* accum = bars + 3 * S;   // accumulator complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 1);
+  float* tailw = reinterpret_cast<float*>(smem + S * Cfg::STAGE_BYTES + 256);   // TAIL: [S][4 columns][32 k] fp32
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform by construction
   const int lane = threadIdx.x & 31;
@@ -276,15 +151,41 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   if (MODE == 1) valid_groups = min(BN / 32, prog.total_groups - n0 / 32);
   if (MODE == 2) valid_groups = min(BM / 32, prog.total_groups - m0 / 32);
 
+  const bool tail_on = TAIL && n0 == 0;   // CTA-uniform
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      tma_prefetch_desc(&maps.b);
-      tma_prefetch_desc(&maps.a[0]);
+    if (TAIL || lane == 0) {
+      if (lane == 0) {
+        tma_prefetch_desc(&maps.b);
+        tma_prefetch_desc(&maps.a[0]);
+      }
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+        float tw[4] = {0.f, 0.f, 0.f, 0.f};
+        if (TAIL && tail_on) {
+          // tail-column weights of this K block: lane = k, packed row = 32 bf16 hi then 32 bf16 lo per 128 bytes.
+          // Issued before the wait for the stage so that the loads overlap it.
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (e < prog.n_tail) {
+              const unsigned short* rowp =
+                  reinterpret_cast<const unsigned short*>(prog.tail_w + e * prog.tail_ldw + (long long)it * 128);
+              tw[e] = __uint_as_float((uint32_t)__ldg(rowp + lane) << 16) +
+                      __uint_as_float((uint32_t)__ldg(rowp + 32 + lane) << 16);
+            }
+          }
+        }
+        if (lane == 0) mbar_wait(&empty[s], ph ^ 1);
+        if (TAIL) {
+          __syncwarp();
+          if (tail_on) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) tailw[(s * 4 + e) * 32 + lane] = tw[e];
+          }
+          __syncwarp();   // lane 0's arrive on full[s] below publishes the whole warp's stores
+          if (lane != 0) continue;
+        }
         if (MODE == 2) {
           mbar_arrive_expect_tx(&full[s], 4096 * valid_groups + B_TILE_BYTES);
           int pb = pb_begin + it;
@@ -425,6 +326,7 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
     if (TS) {
       // A row r (32 fp32 along K, 8 swizzled 16-byte chunks) -> hi / lo -> tensor memory
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      float ext[4] = {0.f, 0.f, 0.f, 0.f};   // TAIL: row r of the tail columns
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
@@ -437,6 +339,15 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
             const float4 v = lds_v4(row + ((j ^ (r & 7)) << 4));
             split_bf16x2(v.x, v.y, hi[2 * j], lo[2 * j]);
             split_bf16x2(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+            if (TAIL && tail_on) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (e < prog.n_tail) {
+                  const float4 w = *reinterpret_cast<const float4*>(tailw + (s * 4 + e) * 32 + 4 * j);   // broadcast
+                  ext[e] = fmaf(v.w, w.w, fmaf(v.z, w.z, fmaf(v.y, w.y, fmaf(v.x, w.x, ext[e]))));
+                }
+              }
+            }
           }
           const uint32_t dst = lane_base + (uint32_t)(Cfg::ACC_COLS + Cfg::A_COLS * s);
           tmem_st_32x16(dst, hi);
@@ -444,6 +355,23 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
           tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&conv[s]);
+          if (TAIL && tail_on && it == n_iters - 1 && m0 + r < prog.M) {
+            // tail columns: same epilogue as the tiles (alpha, bias, addend, ReLU, mask), one row per thread
+            const long long row_off = (long long)(m0 + r) * epi.ld;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (e < prog.n_tail) {
+                const int col = prog.N + e;
+                float y = epi.alpha * ext[e];
+                if (epi.bias) y += __ldg(epi.bias + col);
+                if (epi.addend) y += epi.addend[row_off + col];
+                if (epi.relu) y = fmaxf(y, 0.f);
+                if (epi.mask_src) y = epi.mask_src[row_off + col] > 0.f ? y : 0.f;
+                if (epi.accumulate) atomicAdd(epi.out + row_off + col, y);
+                else epi.out[row_off + col] = y;
+              }
+            }
+          }
         } else {
         uint32_t hi[32], lo[32];
 #pragma unroll
@@ -500,16 +428,18 @@ gemm_tc_kernel(const __grid_constant__ GemmMaps maps, const GemmProgram prog, co
   if (threadIdx.x == 0) trace_stamp(epi, 7);
 }
 
-template <int BN, int PASSES, int MODE, int TS, int OCC, int CL = 1>
+template <int BN, int PASSES, int MODE, int TS, int OCC, int CL = 1, int TAIL = 0>
 static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const GemmEpilogue& epi, dim3 grid,
                        cudaStream_t st) {
   using Cfg = GemmCfg<BN, PASSES, TS, OCC>;
+  constexpr int SMEM = Cfg::SMEM_BYTES + (TAIL ? Cfg::STAGES * 512 : 0);
+  static_assert(SMEM <= 232448, "shared memory budget");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, MODE, TS, OCC, CL>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES, MODE, TS, OCC, CL, TAIL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
-      set_error("gemm_tc: cudaFuncSetAttribute(%d bytes) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+      set_error("gemm_tc: cudaFuncSetAttribute(%d bytes) failed: %s", SMEM, cudaGetErrorString(e));
       return OBMAN_ERR_CUDA;
     }
     attr = true;
@@ -520,7 +450,7 @@ static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const Gemm
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;
     cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
     cudaLaunchAttribute attrs[1];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
@@ -529,7 +459,7 @@ static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const Gemm
     attrs[0].val.clusterDim.z = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PASSES, MODE, TS, OCC, CL>, maps, prog, epi);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, PASSES, MODE, TS, OCC, CL, TAIL>, maps, prog, epi);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cluster launch failed: %s", cudaGetErrorString(e));
       (void)cudaGetLastError();
@@ -537,7 +467,7 @@ static int launch_gemm(const GemmMaps& maps, const GemmProgram& prog, const Gemm
     }
     return OBMAN_OK;
   }
-  gemm_tc_kernel<BN, PASSES, MODE, TS, OCC, CL><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, prog, epi);
+  gemm_tc_kernel<BN, PASSES, MODE, TS, OCC, CL, TAIL><<<grid, GEMM_THREADS, SMEM, st>>>(maps, prog, epi);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -1054,6 +984,9 @@ int try_conv64(const float* x, int n_img, int h_in, int w_in, int c_in, long lon
                const int* tap_wslot, float* out, int h_out, int w_out, long long o_sN, long long o_sH, long long o_sW,
                const float* bias, const float* addend, const float* mask_src, int relu, cudaStream_t st);   // conv64.cu
 
+int try_gemm_persist(const GemmMaps& maps, const GemmProgram& prog, const GemmEpilogue& epi, long long m_tiles,
+                     cudaStream_t st);   // gemm_persist.cu
+
 long long* g_trace = nullptr;       // obman_debug_trace (also read by conv64.cu)
 long long g_trace_cap = 0;
 
@@ -1168,6 +1101,17 @@ static bool stack64_enabled() {
   return v != 0;
 }
 
+// column-tile width of the TAIL variant (0 = off): OBMAN_GEMM_TAIL = 0 | 128 (default) | 256
+static int tail_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OBMAN_GEMM_TAIL");
+    v = e ? atoi(e) : 128;
+    if (v != 0 && v != 128 && v != 256) v = 128;
+  }
+  return v;
+}
+
 static bool ts_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -1199,8 +1143,15 @@ extern "C" int obman_gemm(const float* A, long long lda, const float* W, const f
   GemmMaps maps;
   memset(&maps, 0, sizeof(maps));
   const long long m_tiles = (M + BM - 1) / BM;
-  const int BN = pick_bn(N, m_tiles);
   const bool bf = passes == OBMAN_PREC_3XBF16;
+  // N = 128 j + (1..4) on a grid that fills the GPU: 128-wide tiles + tail columns on the CUDA cores (TAIL variant).
+  // OBMAN_GEMM_TAIL=256 takes 256-wide tiles where N = 256 j + (1..4): measured SLOWER on the decoder layers (K <= 544:
+  // one CTA per SM, the prologue and the 256-column epilogue are not hidden behind a second CTA's main loop).
+  const int tail_bn = tail_enabled();
+  const int n_tail = (bf && tail_bn && N > tail_bn && N % tail_bn >= 1 && N % tail_bn <= 4 && m_tiles >= num_sms() &&
+                      cluster_for(m_tiles) == 1) ? N % tail_bn : 0;
+  const int N_main = N - n_tail;
+  const int BN = n_tail ? tail_bn : pick_bn(N, m_tiles);
   int ts = bf ? 2 : ((W_lo != nullptr) && passes == 3 && ts_enabled());
   if (ts == 2 && BN == 64 && stack64_enabled() && cluster_for(m_tiles) == 1) ts = 3;
   OBMAN_REQUIRE(W_lo == nullptr || passes == 1 || ts == 1, "obman_gemm: pre-split weights need the TS path (OBMAN_GEMM_TS=0 set?)");
@@ -1231,13 +1182,30 @@ extern "C" int obman_gemm(const float* A, long long lda, const float* W, const f
   prog.num_taps = 1;
   prog.kblocks = (K + BK - 1) / BK;
   prog.M = M;
-  prog.N = N;
+  prog.N = N_main;
+  prog.n_tail = n_tail;
+  prog.tail_w = reinterpret_cast<const unsigned char*>(W) + (size_t)N_main * ldw * 4;
+  prog.tail_ldw = ldw * 4;
   GemmEpilogue epi;
   memset(&epi, 0, sizeof(epi));
   epi.out = out; epi.bias = bias; epi.addend = addend; epi.mask_src = mask_src;
   epi.alpha = alpha; epi.relu = relu; epi.accumulate = accumulate; epi.ld = ldo;
   epi.trace = g_trace; epi.trace_cap = g_trace_cap;
-  dim3 grid((unsigned)m_tiles, (unsigned)((N + BN - 1) / BN), 1);
+  dim3 grid((unsigned)m_tiles, (unsigned)((N_main + BN - 1) / BN), 1);
+  if (bf && BN == 128 && cluster_for(m_tiles) == 1) {
+    // many short tiles (the point decoder): persistent CTAs, epilogue overlapped with the next tile (gemm_persist.cu)
+    prog.n_tiles = (int)grid.y;
+    const int rc = try_gemm_persist(maps, prog, epi, m_tiles, (cudaStream_t)stream);
+    if (rc != 0) return rc < 0 ? rc : OBMAN_OK;
+  }
+  if (n_tail) {
+    if (grid.y > 1 && grid.x <= 65535) {
+      prog.raster_n = 1;
+      grid = dim3(grid.y, grid.x, 1);
+    }
+    if (BN == 256) return launch_gemm<256, 3, 0, 2, 1, 1, 1>(maps, prog, epi, grid, (cudaStream_t)stream);
+    return launch_gemm<128, 3, 0, 2, 2, 1, 1>(maps, prog, epi, grid, (cudaStream_t)stream);
+  }
   return dispatch_gemm<0>(BN, passes, ts, maps, prog, epi, grid, (cudaStream_t)stream);
 }
 

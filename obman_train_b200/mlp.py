@@ -248,16 +248,12 @@ class _PointDecoderFn(torch.autograd.Function):
         gw2, gb2, gg2, gbt2 = side_layer(l2, g2, h1, C2)
         g1 = _empty(M, h1.shape[1])
         dense.gemm(g2, l2.wft, out=g1, mask_src=h1, passes=pb, n=C1, k=C2, **l2.bw)
-        gFc = _empty(B, C1)
-        gG = None if per_sample else _empty(N, C1)
-        call("obman_pointmlp_l1_bwd", ptr(g1), B, N, C1, g1.shape[1], ptr(gFc), ptr(gG), st)
-        gF = pad_scale_mask(gFc, _r32(C1))
         # raw weight gradient of conv1 = [grid part (C1,3) | feature part (C1,F)], written into one (C1, 3+F) buffer
+        gFc = _empty(B, C1)
         dw1 = _empty(C1, 3 + Fdim)
-        if per_sample:
-            call("obman_weighted_colsum", ptr(g1), M, C1, g1.stride(0), ptr(grid), 3, ptr(dw1), dw1.stride(0), st)
-        else:
-            call("obman_weighted_colsum", ptr(gG), N, C1, C1, ptr(grid), 3, ptr(dw1), dw1.stride(0), st)
+        call("obman_pointmlp_l1_bwd", ptr(g1), ptr(grid), N * 3 if per_sample else 0, B, N, C1, g1.shape[1], ptr(gFc),
+             ptr(_empty(B, 3, C1)), ptr(dw1), dw1.stride(0), st)
+        gF = pad_scale_mask(gFc, _r32(C1))
         featp = feat if Fdim == _r32(Fdim) else pad_scale_mask(feat, _r32(Fdim))
         dw1[:, 3:] = dense.wgrad_matrix(gF, featp, passes=pw)[:C1, :Fdim]
         gw1, gb1, gg1, gbt1 = l1.finish(dw1, colsum(gF, C1))
@@ -400,14 +396,10 @@ class _PointDecoderTrainFn(torch.autograd.Function):
         dense.gemm(dz2, l2.wft, out=gy1, passes=pb, n=C1, k=C2, packed=True)
         dz1, gg1, gbt1 = bn1.backward(gy1, y1, z1)
         gFc = _empty(B, C1)
-        gG = None if per_sample else _empty(N, C1)
-        call("obman_pointmlp_l1_bwd", ptr(dz1), B, N, C1, dz1.shape[1], ptr(gFc), ptr(gG), st)
-        gF = pad_scale_mask(gFc, _r32(C1))
         dw1 = _empty(C1, 3 + Fdim)
-        if per_sample:
-            call("obman_weighted_colsum", ptr(dz1), M, C1, dz1.stride(0), ptr(grid), 3, ptr(dw1), dw1.stride(0), st)
-        else:
-            call("obman_weighted_colsum", ptr(gG), N, C1, C1, ptr(grid), 3, ptr(dw1), dw1.stride(0), st)
+        call("obman_pointmlp_l1_bwd", ptr(dz1), ptr(grid), N * 3 if per_sample else 0, B, N, C1, dz1.shape[1], ptr(gFc),
+             ptr(_empty(B, 3, C1)), ptr(dw1), dw1.stride(0), st)
+        gF = pad_scale_mask(gFc, _r32(C1))
         featp = feat if Fdim == _r32(Fdim) else pad_scale_mask(feat, _r32(Fdim))
         dw1[:, 3:] = dense.wgrad_matrix(gF, featp, passes=pw)[:C1, :Fdim]
         gb1 = colsum(gF, C1)

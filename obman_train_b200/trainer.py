@@ -9,6 +9,8 @@ Replaces the reference's single-process ``torch.nn.DataParallel`` wrap + per-ten
   (``obman_adam_step``) instead of ~130 per-tensor updates;
 * no ``.item()`` syncs inside the step: the loss stays on the device until the caller reads it.
 """
+import gc
+
 import torch
 import torch.distributed as dist
 
@@ -289,8 +291,20 @@ class FlatAdamTrainer(object):
         self._static_sample = sample
         self._graph = torch.cuda.CUDAGraph()
         steps_before = self.step_count
-        with torch.cuda.graph(self._graph):
-            loss, results, losses = self.step(sample, return_all=True)
+        # Destructors that run while a capture is in progress can invalidate it: cudaGraphExecDestroy of a dead trainer's
+        # graph is "not permitted when stream is capturing" in the default global mode, and the cyclic garbage collector
+        # may well decide to free one in the middle of the step (seen once in the test-suite, in the autograd thread).
+        # So: collect now, keep the collector off until the capture ends, and restrict the unsafe-call check to the
+        # capturing thread.
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
+                loss, results, losses = self.step(sample, return_all=True)
+        finally:
+            if gc_was_on:
+                gc.enable()
         # Static output tensors of the captured step, rewritten by every replay.  Detached views: holding the autograd
         # graph would keep its AccumulateGrad nodes (and their stream affinity) alive across steps.
         det = lambda d: {k: (v.detach() if torch.is_tensor(v) else v) for k, v in d.items()}  # noqa: E731

@@ -252,6 +252,25 @@ CASES.update({
     "dgrad3x3_s1_64_64_64_b3_persistent": lambda: case_dgrad(20, 64, 64, 64, 3, 1, 2),
     "dgrad3x3_s2_64_64_128_b3": lambda: case_dgrad(6, 64, 64, 128, 3, 2, 2),
 })
+# TAIL variant of gemm_tc_kernel: N = 256 j + (1..4) on >= 148 row tiles (the decoder's 515 -> 257 -> 128 layers and their
+# data gradients); the last case stays below the row-tile threshold and takes the ordinary column tiles
+CASES.update({
+    "gemm_tail_19000x257x515_b3_epi": lambda: case_gemm(19000, 257, 515, 2, True),
+    "gemm_tail_19000x515x257_b3_epi": lambda: case_gemm(19000, 515, 257, 2, True),
+    "gemm_tail_19000x257x128_b3": lambda: case_gemm(19000, 257, 128, 2),
+    "gemm_tail_19001x260x96_b3_epi": lambda: case_gemm(19001, 260, 96, 2, True),
+    "gemm_tail_19000x514x40_b3": lambda: case_gemm(19000, 514, 40, 2),
+    "gemm_notail_3000x257x515_b3_epi": lambda: case_gemm(3000, 257, 515, 2, True),
+})
+# persistent kernel (gemm_persist.cu): >= 4 x 148 tiles of 128 columns, K <= 768; with and without tail columns, ragged rows
+CASES.update({
+    "gemm_persist_40001x257x515_b3_epi": lambda: case_gemm(40001, 257, 515, 2, True),
+    "gemm_persist_40000x515x257_b3_epi": lambda: case_gemm(40000, 515, 257, 2, True),
+    "gemm_persist_40000x257x128_b3": lambda: case_gemm(40000, 257, 128, 2),
+    "gemm_persist_80000x128x257_b3_epi": lambda: case_gemm(80000, 128, 257, 2, True),
+    "gemm_persist_77777x100x40_b3_epi": lambda: case_gemm(77777, 100, 40, 2, True),
+    "gemm_persist_40000x384x768_b3": lambda: case_gemm(40000, 384, 768, 2),
+})
 CASES["rounding_mode_p1"] = case_rounding_mode
 CASES["stemlike_wgrad_4x4_128_32_64_p3"] = lambda: case_wgrad(2, 64, 32, 64, 3, 1, 3)
 CASES["wgrad3x3_s1_32_128_128_p3"] = lambda: case_wgrad(3, 32, 128, 128, 3, 1, 3)

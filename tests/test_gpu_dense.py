@@ -94,22 +94,26 @@ def test_maxpool_and_stem_pack_vs_torch(B, H, C):
 
 @pytest.mark.parametrize("env", [{"OBMAN_GEMM_STACK64": "1", "OBMAN_CONV64": "0"}, {"OBMAN_WGRAD_STACK64": "1"},
                                  {"OBMAN_CONV64_GEN": "1"}, {"OBMAN_CONV64_GEN": "1", "OBMAN_CONV64_CFG": "18"},
-                                 {"OBMAN_CONV64": "0"}])
+                                 {"OBMAN_CONV64": "0"}, {"OBMAN_GEMM_PERSIST": "2"}, {"OBMAN_GEMM_TAIL": "256"},
+                                 {"OBMAN_GEMM_TAIL": "0", "OBMAN_GEMM_PERSIST": "0"}])
 def test_alternative_kernel_variants_in_a_subprocess(env):
     """Kernel variants that are selected by environment switches read once per process (the stacked-N variants of the
-    generic kernels, the first generation of the persistent 64-channel kernel, the generic kernel on 64-channel layers)
-    ship in the library: each runs its 64-channel cases here, in a process of its own, against the fp64 references."""
+    generic kernels, the first generation of the persistent 64-channel kernel, the generic kernel on 64-channel layers;
+    the persistent plain-matrix kernel forced onto every eligible shape, the 256-wide tail variant, no tail columns at
+    all) ship in the library: each runs its cases here, in a process of its own, against the fp64 references."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = (
-        "import sys; sys.path.insert(0, %r)\n"
+        "import os, sys; sys.path.insert(0, %r)\n"
         "import importlib.util\n"
         "spec = importlib.util.spec_from_file_location('probe_dense', %r)\n"
         "m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)\n"
         "names = ['conv3x3_s1_16_64_64_b3_epi', 'conv3x3_s1_50_64_64_b3_epi_ragged', 'dgrad3x3_s1_16_64_64_b3',\n"
         "         'dgrad3x3_s2_32_64_128_b3', 'wgrad3x3_s1_16_64_64_b3', 'stemlike_wgrad_4x4_128_32_64_b3', 'gemm_64x33x256_b3']\n"
+        "if 'OBMAN_GEMM_PERSIST' in os.environ or 'OBMAN_GEMM_TAIL' in os.environ:   # plain-matrix variants (decoder shapes)\n"
+        "    names = [n for n in m.CASES if n.startswith(('gemm_persist_', 'gemm_tail_', 'gemm_notail_'))]\n"
         "for n in names:\n"
         "    r = m.CASES[n]()\n"
         "    assert not r['nan'] and r['rel'] < 5e-5, (n, r)\n"

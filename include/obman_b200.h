@@ -58,9 +58,11 @@ int obman_chamfer_bwd(const float* preds, const float* gts, const int* idx1, con
 /* ---- Contact loss -------------------------------------------------------------------------------
  * batch_mesh_contains_points (mano_train/networks/branches/contactutils.py:62-159): hits (B,P) int32 =
  * number of triangles of the per-sample mesh (obj_verts (B,N,3), faces (F,3) int32 shared by the batch)
- * crossed by the fixed-direction ray from points (B,P,3); exterior <=> hits even. */
+ * crossed by the fixed-direction ray from points (B,P,3); exterior <=> hits even.
+ * tri_scratch (nullable): 32 * B * ceil(F/2) floats, 16-byte aligned; when given, the per-triangle records are built
+ * once per sample there and streamed by the search kernel (faster); NULL = staged per CTA in shared memory. */
 int obman_raycast_hits(const float* points, const float* obj_verts, const int* faces, int B, int P,
-                       int N, int F, int* hits, void* stream);
+                       int N, int F, int* hits, float* tri_scratch, void* stream);
 /* compute_contact_loss value/mask stage (contactloss.py:174-307).  modes: 0 dist_sq, 1 dist,
  * 2 dist_tanh; zones_mode: 0 all, 1 tips (zone_ids = tip ids, zone_ptr = {0,5}), 2 zones (CSR table).
  * Outputs: attr_mask/rep_mask (B,P) u8, close (B,P,3), anchor (B,P), partial (B,6) workspace,

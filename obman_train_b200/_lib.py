@@ -68,7 +68,7 @@ def load():
 launch_count = 0  # kernel-launching C calls issued
 kernel_count = 0  # kernels those calls launched (bench.py reads this for its gpu_launches claim)
 KERNELS_PER_CALL = {"obman_chamfer_fwd": 2, "obman_contact_fwd": 2, "obman_mano_fwd": 3, "obman_mano_bwd": 3,
-                    "obman_pointmlp_l1_bwd": 2, "obman_laplacian_fwd": 2, "obman_edge_loss_fwd": 2, "obman_contact_iou": 2, "obman_bn_stats": 2, "obman_bn_bwd": 3}
+                    "obman_pointmlp_l1_bwd": 2, "obman_raycast_hits": 2, "obman_laplacian_fwd": 2, "obman_edge_loss_fwd": 2, "obman_contact_iou": 2, "obman_bn_stats": 2, "obman_bn_bwd": 3}
 
 
 def call(name, *args):

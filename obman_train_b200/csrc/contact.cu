@@ -5,6 +5,8 @@
 //   compute_contact_loss         mano_train/networks/branches/contactloss.py:149-308   (values, masks)
 //   masked_mean_loss             mano_train/networks/branches/contactloss.py:50-57     (batch-global means)
 // The hand->object nearest-vertex search (contactloss.py:164-166) is the shared kernel in nn_pairs.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace obman {
@@ -78,6 +80,235 @@ raycast_kernel(const float* __restrict__ pts, const float* __restrict__ obj,
     }
   }
   if (p < P && count) atomicAdd(hits + (size_t)b * P + p, count);
+}
+
+// Packed-math variant: two triangles per instruction with the sm_100 packed fp32 forms (FADD2 / FMUL2 / FFMA2), as in
+// nn_pairs.cu's nn_packed_kernel - the scalar kernel is bound by instruction issue (~30 instructions per ray / triangle
+// test).  Per pair of triangles the staged record is 8 float4 = {a, b} interleaved per component:
+//   v0.xyz, invdet | pvec.xyz | e1.xyz | -e1.xyz | e2.xyz
+// A triangle parallel to the ray is staged with invdet = 0 (u = 0 fails "u > 0"), an odd triangle out likewise, so the
+// inner loop has no flag test; "u < 1" is implied by v > 0 and u + v < 1 (rounding is monotonic) and "u + v < 1" is
+// evaluated as 1 - (u + v) > 0 (exactly equivalent), which turns four of the comparisons into one three-way minimum.
+__device__ __forceinline__ unsigned long long rc_pk(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void rc_upk(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long rc_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long rc_sub(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long rc_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long rc_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// PT = points per thread (p, p + blockDim.x, ...): the eight broadcast LDS.128 of a triangle pair - the shared-memory
+// pipe, not instruction issue, bounds this kernel once the arithmetic is packed - are amortised over PT points.
+constexpr int RC_PACKED_THREADS = 448;
+template <int PT>
+__global__ void __launch_bounds__(RC_PACKED_THREADS)
+raycast_packed_kernel(const float* __restrict__ pts, const float* __restrict__ obj,
+                      const int* __restrict__ faces, int P, int N, int F, int f_per_split,
+                      int* __restrict__ hits) {
+  __shared__ float4 sp[RC_CHUNK / 2][8];   // 32 KB
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * (blockDim.x * PT) + threadIdx.x;
+  const int f_begin = blockIdx.z * f_per_split;
+  const int f_end = min(F, f_begin + f_per_split);
+  const float* __restrict__ ob = obj + (size_t)b * N * 3;
+  unsigned long long px[PT], py[PT], pz[PT];
+  int count[PT];
+#pragma unroll
+  for (int k = 0; k < PT; ++k) {
+    const int p = p0 + k * blockDim.x;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    if (p < P) {
+      const float* q = pts + ((size_t)b * P + p) * 3;
+      fx = q[0]; fy = q[1]; fz = q[2];
+    }
+    px[k] = rc_pk(fx, fx); py[k] = rc_pk(fy, fy); pz[k] = rc_pk(fz, fz);
+    count[k] = 0;
+  }
+  const unsigned long long dirx = rc_pk(RC_DX, RC_DX), diry = rc_pk(RC_DY, RC_DY), dirz = rc_pk(RC_DZ, RC_DZ);
+  const unsigned long long one = rc_pk(1.f, 1.f);
+  for (int f0 = f_begin; f0 < f_end; f0 += RC_CHUNK) {
+    const int n = min(RC_CHUNK, f_end - f0);
+    const int n2 = (n + 1) & ~1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      float rec[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) rec[k] = 0.f;   // the odd one out: invdet = 0 never hits
+      if (i < n) {
+        const int* fc = faces + (size_t)(f0 + i) * 3;
+        const float* a = ob + 3 * fc[0];
+        const float* bb = ob + 3 * fc[1];
+        const float* c = ob + 3 * fc[2];
+        const float v0x = a[0], v0y = a[1], v0z = a[2];
+        const float e1x = bb[0] - v0x, e1y = bb[1] - v0y, e1z = bb[2] - v0z;
+        const float e2x = c[0] - v0x, e2y = c[1] - v0y, e2z = c[2] - v0z;
+        // pvec = dir x e2
+        const float pvx = RC_DY * e2z - RC_DZ * e2y;
+        const float pvy = RC_DZ * e2x - RC_DX * e2z;
+        const float pvz = RC_DX * e2y - RC_DY * e2x;
+        const float det = e1x * pvx + e1y * pvy + e1z * pvz;
+        const float invdet = fabsf(det) < RC_TOL ? 0.f : 1.0f / (det + RC_DET_EPS);
+        rec[0] = v0x; rec[1] = v0y; rec[2] = v0z; rec[3] = invdet;
+        rec[4] = pvx; rec[5] = pvy; rec[6] = pvz;
+        rec[7] = e1x; rec[8] = e1y; rec[9] = e1z;
+        rec[10] = -e1x; rec[11] = -e1y; rec[12] = -e1z;
+        rec[13] = e2x; rec[14] = e2y; rec[15] = e2z;
+      }
+      float* dst = reinterpret_cast<float*>(sp[i >> 1]) + (i & 1);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) dst[2 * k] = rec[k];
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < n2 / 2; ++j) {
+      const float4 L0 = sp[j][0], L1 = sp[j][1], L2 = sp[j][2], L3 = sp[j][3];
+      const float4 L4 = sp[j][4], L5 = sp[j][5], L6 = sp[j][6], L7 = sp[j][7];
+      const unsigned long long v0x = rc_pk(L0.x, L0.y), v0y = rc_pk(L0.z, L0.w), v0z = rc_pk(L1.x, L1.y);
+      const unsigned long long inv = rc_pk(L1.z, L1.w);
+      const unsigned long long Dx = rc_pk(L2.x, L2.y), Dy = rc_pk(L2.z, L2.w), Dz = rc_pk(L3.x, L3.y);
+      const unsigned long long e1x = rc_pk(L3.z, L3.w), e1y = rc_pk(L4.x, L4.y), e1z = rc_pk(L4.z, L4.w);
+      const unsigned long long m1x = rc_pk(L5.x, L5.y), m1y = rc_pk(L5.z, L5.w), m1z = rc_pk(L6.x, L6.y);
+      const unsigned long long e2x = rc_pk(L6.z, L6.w), e2y = rc_pk(L7.x, L7.y), e2z = rc_pk(L7.z, L7.w);
+#pragma unroll
+      for (int k = 0; k < PT; ++k) {
+        const unsigned long long tx = rc_sub(px[k], v0x), ty = rc_sub(py[k], v0y), tz = rc_sub(pz[k], v0z);
+        const unsigned long long u = rc_mul(rc_fma(tz, Dz, rc_fma(ty, Dy, rc_mul(tx, Dx))), inv);
+        // q = t x e1
+        const unsigned long long qx = rc_fma(tz, m1y, rc_mul(ty, e1z));
+        const unsigned long long qy = rc_fma(tx, m1z, rc_mul(tz, e1x));
+        const unsigned long long qz = rc_fma(ty, m1x, rc_mul(tx, e1y));
+        const unsigned long long v = rc_mul(rc_fma(dirz, qz, rc_fma(diry, qy, rc_mul(dirx, qx))), inv);
+        const unsigned long long t = rc_mul(rc_fma(e2z, qz, rc_fma(e2y, qy, rc_mul(e2x, qx))), inv);
+        const unsigned long long w = rc_sub(one, rc_add(u, v));
+        float ua, ub, va, vb, wa, wb, ta, tb;
+        rc_upk(u, ua, ub); rc_upk(v, va, vb); rc_upk(w, wa, wb); rc_upk(t, ta, tb);
+        count[k] += (fminf(fminf(ua, va), wa) > 0.f) & (ta >= RC_TOL);
+        count[k] += (fminf(fminf(ub, vb), wb) > 0.f) & (tb >= RC_TOL);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PT; ++k) {
+    const int p = p0 + k * blockDim.x;
+    if (p < P && count[k]) atomicAdd(hits + (size_t)b * P + p, count[k]);
+  }
+}
+
+// Streamed variant: the triangle-pair records are built ONCE per sample by raycast_prep_kernel into a scratch buffer
+// ((B, ceil(F/2), 8) float4, 84 MB at B = 256 / 5120 faces: L2 resident), the search kernel reads them with uniform
+// (broadcast) global loads - no shared memory, no barriers, any number of warps per CTA.  Measured on the staged kernel
+// above (ncu, profiles/ncu_raycast_r2.txt): a quarter of the warp samples sat at the barriers around the per-chunk
+// record set-up (13 warps per CTA on 4 schedulers, 2 CTAs per SM), issue slots 50 % busy.
+__global__ void __launch_bounds__(256)
+raycast_prep_kernel(const float* __restrict__ obj, const int* __restrict__ faces, int N, int F, int F2,
+                    float* __restrict__ rec) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * F2) return;
+  const float* __restrict__ ob = obj + (size_t)b * N * 3;
+  float r[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) r[k] = 0.f;   // the odd one out: invdet = 0 never hits
+  if (i < F) {
+    const int* fc = faces + (size_t)i * 3;
+    const float* a = ob + 3 * fc[0];
+    const float* bb = ob + 3 * fc[1];
+    const float* c = ob + 3 * fc[2];
+    const float v0x = a[0], v0y = a[1], v0z = a[2];
+    const float e1x = bb[0] - v0x, e1y = bb[1] - v0y, e1z = bb[2] - v0z;
+    const float e2x = c[0] - v0x, e2y = c[1] - v0y, e2z = c[2] - v0z;
+    const float pvx = RC_DY * e2z - RC_DZ * e2y;
+    const float pvy = RC_DZ * e2x - RC_DX * e2z;
+    const float pvz = RC_DX * e2y - RC_DY * e2x;
+    const float det = e1x * pvx + e1y * pvy + e1z * pvz;
+    const float invdet = fabsf(det) < RC_TOL ? 0.f : 1.0f / (det + RC_DET_EPS);
+    r[0] = v0x; r[1] = v0y; r[2] = v0z; r[3] = invdet;
+    r[4] = pvx; r[5] = pvy; r[6] = pvz;
+    r[7] = e1x; r[8] = e1y; r[9] = e1z;
+    r[10] = -e1x; r[11] = -e1y; r[12] = -e1z;
+    r[13] = e2x; r[14] = e2y; r[15] = e2z;
+  }
+  float* dst = rec + ((size_t)b * F2 + (i >> 1)) * 32 + (i & 1);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) dst[2 * k] = r[k];
+}
+
+template <int PT>
+__global__ void __launch_bounds__(256)
+raycast_stream_kernel(const float* __restrict__ pts, const float4* __restrict__ rec, int P, int F2, int pairs_per_split,
+                      int* __restrict__ hits) {
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * (blockDim.x * PT) + threadIdx.x;
+  const int j_begin = blockIdx.z * pairs_per_split;
+  const int j_end = min(F2, j_begin + pairs_per_split);
+  unsigned long long px[PT], py[PT], pz[PT];
+  int count[PT];
+#pragma unroll
+  for (int k = 0; k < PT; ++k) {
+    const int p = p0 + k * blockDim.x;
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    if (p < P) {
+      const float* q = pts + ((size_t)b * P + p) * 3;
+      fx = q[0]; fy = q[1]; fz = q[2];
+    }
+    px[k] = rc_pk(fx, fx); py[k] = rc_pk(fy, fy); pz[k] = rc_pk(fz, fz);
+    count[k] = 0;
+  }
+  const unsigned long long dirx = rc_pk(RC_DX, RC_DX), diry = rc_pk(RC_DY, RC_DY), dirz = rc_pk(RC_DZ, RC_DZ);
+  const unsigned long long one = rc_pk(1.f, 1.f);
+  const float4* __restrict__ r = rec + ((size_t)b * F2 + j_begin) * 8;
+#pragma unroll 2
+  for (int j = j_begin; j < j_end; ++j, r += 8) {
+    const float4 L0 = __ldg(r), L1 = __ldg(r + 1), L2 = __ldg(r + 2), L3 = __ldg(r + 3);
+    const float4 L4 = __ldg(r + 4), L5 = __ldg(r + 5), L6 = __ldg(r + 6), L7 = __ldg(r + 7);
+    const unsigned long long v0x = rc_pk(L0.x, L0.y), v0y = rc_pk(L0.z, L0.w), v0z = rc_pk(L1.x, L1.y);
+    const unsigned long long inv = rc_pk(L1.z, L1.w);
+    const unsigned long long Dx = rc_pk(L2.x, L2.y), Dy = rc_pk(L2.z, L2.w), Dz = rc_pk(L3.x, L3.y);
+    const unsigned long long e1x = rc_pk(L3.z, L3.w), e1y = rc_pk(L4.x, L4.y), e1z = rc_pk(L4.z, L4.w);
+    const unsigned long long m1x = rc_pk(L5.x, L5.y), m1y = rc_pk(L5.z, L5.w), m1z = rc_pk(L6.x, L6.y);
+    const unsigned long long e2x = rc_pk(L6.z, L6.w), e2y = rc_pk(L7.x, L7.y), e2z = rc_pk(L7.z, L7.w);
+#pragma unroll
+    for (int k = 0; k < PT; ++k) {
+      const unsigned long long tx = rc_sub(px[k], v0x), ty = rc_sub(py[k], v0y), tz = rc_sub(pz[k], v0z);
+      const unsigned long long u = rc_mul(rc_fma(tz, Dz, rc_fma(ty, Dy, rc_mul(tx, Dx))), inv);
+      const unsigned long long qx = rc_fma(tz, m1y, rc_mul(ty, e1z));
+      const unsigned long long qy = rc_fma(tx, m1z, rc_mul(tz, e1x));
+      const unsigned long long qz = rc_fma(ty, m1x, rc_mul(tx, e1y));
+      const unsigned long long v = rc_mul(rc_fma(dirz, qz, rc_fma(diry, qy, rc_mul(dirx, qx))), inv);
+      const unsigned long long t = rc_mul(rc_fma(e2z, qz, rc_fma(e2y, qy, rc_mul(e2x, qx))), inv);
+      const unsigned long long w = rc_sub(one, rc_add(u, v));
+      float ua, ub, va, vb, wa, wb, ta, tb;
+      rc_upk(u, ua, ub); rc_upk(v, va, vb); rc_upk(w, wa, wb); rc_upk(t, ta, tb);
+      count[k] += (fminf(fminf(ua, va), wa) > 0.f) & (ta >= RC_TOL);
+      count[k] += (fminf(fminf(ub, vb), wb) > 0.f) & (tb >= RC_TOL);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PT; ++k) {
+    const int p = p0 + k * blockDim.x;
+    if (p < P && count[k]) atomicAdd(hits + (size_t)b * P + p, count[k]);
+  }
 }
 
 // ---- per-vertex values, masks, per-sample partial sums ------------------------------------------
@@ -314,11 +545,39 @@ contact_iou_finalize_kernel(const float* __restrict__ iou, int B, const IouThres
 using namespace obman;
 
 extern "C" int obman_raycast_hits(const float* points, const float* obj_verts, const int* faces,
-                                  int B, int P, int N, int F, int* hits, void* stream) {
+                                  int B, int P, int N, int F, int* hits, float* tri_scratch, void* stream) {
   OBMAN_REQUIRE(B > 0 && P > 0 && N > 0 && F > 0 && B <= 65535, "obman_raycast_hits: bad sizes");
   OBMAN_REQUIRE(points && obj_verts && faces && hits, "obman_raycast_hits: null argument");
+  OBMAN_REQUIRE(((uintptr_t)tri_scratch & 15) == 0, "obman_raycast_hits: tri_scratch must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(hits, 0, sizeof(int) * (size_t)B * P, st);
+  static int stream_on = -1;
+  if (stream_on < 0) {
+    const char* e = getenv("OBMAN_RAYCAST_STREAM");   // 0: stage the triangle records per CTA even when scratch is given
+    stream_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (tri_scratch && stream_on) {
+    const int F2 = (F + 1) / 2;
+    raycast_prep_kernel<<<dim3((2 * F2 + 255) / 256, B), 256, 0, st>>>(obj_verts, faces, N, F, F2, tri_scratch);
+    int rc = check_launch("raycast_prep_kernel");
+    if (rc) return rc;
+    // two points per lane; warps per CTA (<= 8) chosen for the fewest idle lanes, pairs split until the grid is
+    // several waves deep (short CTAs: no tail)
+    const int w2 = (P + 63) / 64;
+    int t2 = (w2 + 7) / 8, thr2 = 256, best = 1 << 30;
+    for (int t = t2; t <= w2; ++t) {
+      const int w = (w2 + t - 1) / t;
+      if (w * t - w2 < best || (w * t - w2 == best && w > thr2 / 32)) { best = w * t - w2; t2 = t; thr2 = w * 32; }
+      if (best == 0) break;
+    }
+    int sp = 1;
+    while (sp < 16 && (long long)t2 * B * sp * (thr2 / 32) < 8LL * 32 * num_sms() && F2 / (sp + 1) >= 128) ++sp;
+    const int per2 = (F2 + sp - 1) / sp;
+    sp = (F2 + per2 - 1) / per2;
+    raycast_stream_kernel<2><<<dim3(t2, B, sp), thr2, 0, st>>>(points, reinterpret_cast<const float4*>(tri_scratch), P,
+                                                              F2, per2, hits);
+    return check_launch("raycast_stream_kernel");
+  }
   // point tiles: the block size (whole warps, <= RC_THREADS) that leaves the fewest idle lanes.  778 hand vertices =
   // 25 warps: 4 tiles of 256 threads would idle 24 % of the lanes, 5 tiles of 160 threads idle 3 %.
   const int warps = (P + 31) / 32;
@@ -336,6 +595,33 @@ extern "C" int obman_raycast_hits(const float* points, const float* obj_verts, c
   while (splits < chunks && (long long)ptiles * B * splits < 2LL * num_sms()) ++splits;
   int per = ((chunks + splits - 1) / splits) * RC_CHUNK;
   splits = (F + per - 1) / per;
+  static int packed = -1;
+  if (packed < 0) {
+    const char* e = getenv("OBMAN_RAYCAST_PACKED");   // 0: the scalar kernel
+    packed = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (packed) {
+    // PT points per thread; tiles of whole warps (<= RC_PACKED_THREADS) that leave the fewest idle lanes
+    static int pt = -1;
+    if (pt < 0) {
+      const char* e = getenv("OBMAN_RAYCAST_PT");
+      pt = (e && atoi(e) == 4) ? 4 : 2;
+    }
+    const int w2 = (P + 32 * pt - 1) / (32 * pt);        // warps when every lane owns PT points
+    const int maxw = RC_PACKED_THREADS / 32;
+    int t2 = (w2 + maxw - 1) / maxw, thr2 = RC_PACKED_THREADS, best = 1 << 30;
+    for (int t = t2; t <= t2 + 3 && t <= w2; ++t) {
+      const int w = (w2 + t - 1) / t;
+      if (w * t - w2 < best) { best = w * t - w2; t2 = t; thr2 = w * 32; }
+    }
+    int sp2 = 1;
+    while (sp2 < chunks && (long long)t2 * B * sp2 < 2LL * num_sms()) ++sp2;
+    const int per2 = ((chunks + sp2 - 1) / sp2) * RC_CHUNK;
+    sp2 = (F + per2 - 1) / per2;
+    if (pt == 4) raycast_packed_kernel<4><<<dim3(t2, B, sp2), thr2, 0, st>>>(points, obj_verts, faces, P, N, F, per2, hits);
+    else raycast_packed_kernel<2><<<dim3(t2, B, sp2), thr2, 0, st>>>(points, obj_verts, faces, P, N, F, per2, hits);
+    return check_launch("raycast_packed_kernel");
+  }
   raycast_kernel<<<dim3(ptiles, B, splits), threads, 0, st>>>(points, obj_verts, faces, P, N, F,
                                                                 per, hits);
   return check_launch("raycast_kernel");

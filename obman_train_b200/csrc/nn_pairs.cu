@@ -11,6 +11,8 @@
 //
 // Algorithmic traffic per launch: 12*B*(N+M) bytes read, 8*B*(N+M) bytes written (min + idx);
 // work: 2*B*N*M pair evaluations when both directions are requested.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace obman {
@@ -99,6 +101,137 @@ nn_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int M
     if (j < nq) {
       omin[j] = (nan_seen[k] || s_nan) ? __int_as_float(0x7fc00000) : best[k];
       oidx[j] = bi[k];
+    }
+  }
+}
+
+// ---- packed-math variant ----------------------------------------------------------------------------------------
+// Same search, same arithmetic per pair ((q - p) per coordinate, fma chain z, y, x: bit-identical distances), but two
+// candidates per instruction with the sm_100 packed fp32 forms (sub / mul / fma .f32x2 -> FADD2 / FMUL2 / FFMA2): the
+// scalar kernel is bound by instruction ISSUE (6 FMA-pipe + ~1.3 other instructions per pair at 57-61 % of the issue
+// peak), the packed forms halve the FMA-pipe instruction count.  Candidates sit in shared memory as structure of arrays
+// in groups of four ({x0..x3}, {y0..y3}, {z0..z3}: three broadcast LDS.128 per four candidates instead of four).
+__device__ __forceinline__ unsigned long long pk2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+template <int Q>
+__global__ void __launch_bounds__(NN_THREADS)
+nn_packed_kernel(const float* __restrict__ x, const float* __restrict__ y, int N, int M,
+                 float* __restrict__ minx, int* __restrict__ idxx,
+                 float* __restrict__ miny, int* __restrict__ idxy, int dirs) {
+  const int dir = (dirs == 3) ? (int)blockIdx.z : (dirs == 2 ? 1 : 0);
+  const int nq = dir == 0 ? N : M;
+  const int nc = dir == 0 ? M : N;
+  const int q0 = blockIdx.x * (NN_THREADS * Q);
+  if (q0 >= nq) return;
+  const int b = blockIdx.y;
+  const float* __restrict__ qp = (dir == 0 ? x : y) + (size_t)b * nq * 3;
+  const float* __restrict__ cp = (dir == 0 ? y : x) + (size_t)b * nc * 3;
+  float* __restrict__ omin = (dir == 0 ? minx : miny) + (size_t)b * nq;
+  int* __restrict__ oidx = (dir == 0 ? idxx : idxy) + (size_t)b * nq;
+
+  __shared__ float4 sc[3][NN_CHUNK / 4];   // [coordinate][group of four candidates]
+  __shared__ int s_nan;                    // see nn_kernel
+  if (threadIdx.x == 0) s_nan = 0;
+
+  unsigned long long qx[Q], qy[Q], qz[Q];  // the query coordinate in both halves
+  float best[Q];
+  int bi[Q];
+  bool nan_seen[Q];
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    int j = q0 + k * NN_THREADS + threadIdx.x;
+    bool ok = j < nq;
+    const float fx = ok ? __ldg(qp + 3 * j + 0) : 0.f;
+    const float fy = ok ? __ldg(qp + 3 * j + 1) : 0.f;
+    const float fz = ok ? __ldg(qp + 3 * j + 2) : 0.f;
+    qx[k] = pk2(fx, fx); qy[k] = pk2(fy, fy); qz[k] = pk2(fz, fz);
+    best[k] = 3.0e38f;
+    bi[k] = 0;
+    nan_seen[k] = (fx != fx) | (fy != fy) | (fz != fz);
+  }
+
+  for (int c0 = 0; c0 < nc; c0 += NN_CHUNK) {
+    const int n = min(NN_CHUNK, nc - c0);
+    const int n4 = (n + 3) & ~3;
+    __syncthreads();
+    const float* __restrict__ src = cp + (size_t)c0 * 3;
+    for (int e = threadIdx.x; e < 3 * n; e += NN_THREADS) {
+      float v = __ldg(src + e);
+      int p = e / 3;
+      reinterpret_cast<float*>(sc[e - 3 * p])[p] = v;
+      if (v != v) s_nan = 1;
+    }
+    for (int p = n + threadIdx.x; p < n4; p += NN_THREADS) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) reinterpret_cast<float*>(sc[c])[p] = 1.0e18f;   // never the minimum
+    }
+    __syncthreads();
+
+#pragma unroll 2
+    for (int i = 0; i < n4 / 4; ++i) {
+      const float4 X = sc[0][i], Y = sc[1][i], Z = sc[2][i];
+      const unsigned long long x01 = pk2(X.x, X.y), x23 = pk2(X.z, X.w);
+      const unsigned long long y01 = pk2(Y.x, Y.y), y23 = pk2(Y.z, Y.w);
+      const unsigned long long z01 = pk2(Z.x, Z.y), z23 = pk2(Z.z, Z.w);
+#pragma unroll
+      for (int k = 0; k < Q; ++k) {
+        const unsigned long long ax01 = sub2(qx[k], x01), ay01 = sub2(qy[k], y01), az01 = sub2(qz[k], z01);
+        const unsigned long long ax23 = sub2(qx[k], x23), ay23 = sub2(qy[k], y23), az23 = sub2(qz[k], z23);
+        const unsigned long long d01 = fma2(az01, az01, fma2(ay01, ay01, mul2(ax01, ax01)));
+        const unsigned long long d23 = fma2(az23, az23, fma2(ay23, ay23, mul2(ax23, ax23)));
+        float d0, d1, d2, d3;
+        upk2(d01, d0, d1);
+        upk2(d23, d2, d3);
+        const float m = fminf(fminf(d0, d1), fminf(d2, d3));
+        // only the GROUP of the running minimum is tracked here (one compare + two selects); which of its four
+        // candidates it was is resolved once, after the search
+        const bool better = m < best[k];
+        best[k] = better ? m : best[k];
+        bi[k] = better ? c0 + 4 * i : bi[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < Q; ++k) {
+    int j = q0 + k * NN_THREADS + threadIdx.x;
+    if (j < nq) {
+      // first candidate of the winning group whose distance (same operations, hence the same bits) is the minimum:
+      // ties keep the lowest candidate index, as a strict "<" over all candidates in order would
+      float fx, fy, fz, unused;
+      upk2(qx[k], fx, unused); upk2(qy[k], fy, unused); upk2(qz[k], fz, unused);
+      int idx = bi[k];
+#pragma unroll
+      for (int e = 3; e >= 0; --e) {
+        const int c = bi[k] + e;
+        if (c < nc) {
+          const float ax = fx - __ldg(cp + 3 * c), ay = fy - __ldg(cp + 3 * c + 1), az = fz - __ldg(cp + 3 * c + 2);
+          if (fmaf(az, az, fmaf(ay, ay, ax * ax)) == best[k]) idx = c;
+        }
+      }
+      omin[j] = (nan_seen[k] || s_nan) ? __int_as_float(0x7fc00000) : best[k];
+      oidx[j] = idx;
     }
   }
 }
@@ -289,6 +422,20 @@ int launch_nn(const float* x, const float* y, int B, int N, int M, float* minx, 
   if (nq_max <= 1024 || (long long)B * nq_max < 128LL * 4 * 2 * num_sms()) Q = 2;
   if (nq_max <= 320) Q = 1;
   dim3 grid((nq_max + NN_THREADS * Q - 1) / (NN_THREADS * Q), B, ndir);
+  static int packed = -1;
+  if (packed < 0) {
+    const char* e = getenv("OBMAN_NN_PACKED");   // 0: the scalar kernel
+    packed = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (packed) {
+    if (Q == 4)
+      nn_packed_kernel<4><<<grid, NN_THREADS, 0, st>>>(x, y, N, M, minx, idxx, miny, idxy, dirs);
+    else if (Q == 2)
+      nn_packed_kernel<2><<<grid, NN_THREADS, 0, st>>>(x, y, N, M, minx, idxx, miny, idxy, dirs);
+    else
+      nn_packed_kernel<1><<<grid, NN_THREADS, 0, st>>>(x, y, N, M, minx, idxx, miny, idxy, dirs);
+    return check_launch("nn_packed_kernel");
+  }
   if (Q == 4)
     nn_kernel<4><<<grid, NN_THREADS, 0, st>>>(x, y, N, M, minx, idxx, miny, idxy, dirs);
   else if (Q == 2)

@@ -105,7 +105,8 @@ def mesh_exterior(points, obj_verts, faces_i32):
     N = obj_verts.shape[1]
     F = faces_i32.shape[0]
     hits = torch.empty((B, P), device=points.device, dtype=torch.int32)
-    call("obman_raycast_hits", ptr(points), ptr(obj_verts), ptr(faces_i32), B, P, N, F, ptr(hits),
+    scratch = torch.empty((B, (F + 1) // 2, 32), device=points.device, dtype=torch.float32)
+    call("obman_raycast_hits", ptr(points), ptr(obj_verts), ptr(faces_i32), B, P, N, F, ptr(hits), ptr(scratch),
          stream_ptr())
     return (hits & 1) == 0, hits
 
@@ -123,8 +124,9 @@ class _ContactFn(torch.autograd.Function):
         idx21 = torch.empty((B, P), device=dev, dtype=torch.int32)
         call("obman_nn_fwd", ptr(hand), ptr(obj), B, P, N, ptr(mins21), ptr(idx21), None, None, 1, st)
         hits = torch.empty((B, P), device=dev, dtype=torch.int32)
-        call("obman_raycast_hits", ptr(hand), ptr(obj), ptr(faces_i32), B, P, N, faces_i32.shape[0],
-             ptr(hits), st)
+        n_faces = faces_i32.shape[0]
+        scratch = torch.empty((B, (n_faces + 1) // 2, 32), device=dev, dtype=torch.float32)
+        call("obman_raycast_hits", ptr(hand), ptr(obj), ptr(faces_i32), B, P, N, n_faces, ptr(hits), ptr(scratch), st)
         attr = torch.empty((B, P), device=dev, dtype=torch.uint8)
         rep = torch.empty((B, P), device=dev, dtype=torch.uint8)
         close = torch.empty((B, P, 3), device=dev)

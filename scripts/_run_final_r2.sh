@@ -1,5 +1,5 @@
-# Evidence run of the round: smoke, GPU tests, headline bench (+ per-launch table), reference arm, ncu launch list with
-# DRAM traffic of one configs[2] step, --set full capture of representative tensor-core kernels.
+# Evidence run of the round: smoke, GPU tests, headline bench (+ per-launch table), reference arm, CUDA-core kernel timings,
+# ncu launch list with DRAM traffic of one configs[2] step, --set full capture of representative tensor-core kernels.
 mkdir -p gpurun_out
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/gpu_tests_final.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/gpu_tests_final.log
@@ -20,9 +20,12 @@ for k in ('workload', 'sweep_2048x10000'):
 r = json.loads(open('gpurun_out/bench_ref_final.json').read().strip().splitlines()[-1])
 print('  reference arm', r['value'], r['steps'], r['warmup'], r['cpu_baseline'])
 PY
-timeout 700 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 16000 --csv \
+timeout 100 python scripts/time_nn.py 2>&1 | grep "^nn" > gpurun_out/cuda_core_kernels_final.txt
+timeout 100 python scripts/time_raycast.py 2>&1 | grep "^raycast" >> gpurun_out/cuda_core_kernels_final.txt
+cat gpurun_out/cuda_core_kernels_final.txt
+timeout 420 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1400 --csv \
    --log-file gpurun_out/launches.csv python bench.py --config 3 --steps 1 --warmup 1 --no-graph --quick > gpurun_out/ncu_bench.log 2>&1; echo "ncu list rc=$?"
 wc -l gpurun_out/launches.csv
-PROF_B=256 PROF_PASSES=2 PROF_WG_PASSES=2 PROF_REPS=1 timeout 500 ncu --set full --clock-control none --import-source on \
+PROF_B=256 PROF_PASSES=2 PROF_WG_PASSES=2 PROF_REPS=1 timeout 400 ncu --set full --clock-control none --import-source on \
    -k regex:'gemm_tc_kernel|wgrad_bf16_kernel|conv64_' -c 9 -o gpurun_out/prof_r2 -f python scripts/prof_kernels.py > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out/*.ncu-rep

@@ -70,7 +70,7 @@ def launch_list(tag):
         x[2] += v.get("dram__bytes_read.sum", 0)
         x[3] += v.get("dram__bytes_write.sum", 0)
     tot = sum(x[1] for x in agg.values())
-    tc = [x for n, x in agg.items() if "gemm_tc_kernel" in n or "wgrad_bf16_kernel" in n or "conv64_" in n]
+    tc = [x for n, x in agg.items() if "gemm_tc_kernel" in n or "wgrad_bf16_kernel" in n or "conv64_" in n or "gemm_persist" in n]
     n_tc, us_tc, by = sum(x[0] for x in tc), sum(x[1] for x in tc), sum(x[2] + x[3] for x in tc)
     with open(os.path.join(PROF, "launches_%s_bench_step_summary.txt" % tag), "w") as f:
         f.write("# per-kernel totals of ONE training step (B=256, configs[2], bf16x3, eager launches, ncu serialises all streams) from "
@@ -79,7 +79,7 @@ def launch_list(tag):
         f.write("%-66s %5s %10s %6s %10s %10s\n" % ("kernel", "n", "us", "share", "dram rd MB", "dram wr MB"))
         for n, x in sorted(agg.items(), key=lambda q: -q[1][1]):
             f.write("%-66s %5d %10.1f %5.1f%% %10.1f %10.1f\n" % (n, x[0], x[1], 100 * x[1] / tot, x[2] / 1e6, x[3] / 1e6))
-        f.write("\n# tensor-core kernels (gemm_tc_kernel + wgrad_bf16_kernel + conv64_*): %d launches, %.1f us = %.1f%% of the step, DRAM "
+        f.write("\n# tensor-core kernels (gemm_tc_kernel + gemm_persist_kernel + wgrad_bf16_kernel + conv64_*): %d launches, %.1f us = %.1f%% of the step, DRAM "
                 "traffic %.1f MB per step = %.2f MB per launch\n" % (n_tc, us_tc, 100 * us_tc / tot, by / 1e6, by / 1e6 / n_tc))
     sys.path.insert(0, ROOT)
     import bench

@@ -107,17 +107,22 @@ class _Unit(object):
                         x_geom=stem_view(x) if self.stem else None)
         return out
 
-    def dgrad(self, g, h_in, w_in, addend=None, mask_src=None, passes=3):
+    def dgrad(self, g, h_in, w_in, addend=None, mask_src=None, passes=3, phase00_only=False, addend_phase00=False):
         """g (B,Ho,Wo,O) -> gx (B,h_in,w_in,I) = conv^T(g) [+ addend] [masked by mask_src > 0].
         A stride-2 convolution is four launches that write the four interleaved output phases; each is a small
         GEMM (a quarter of the pixels, 1-4 taps) that cannot fill 148 SMs on its own, so two of them are issued on
-        the CHAIN auxiliary stream (disjoint outputs, same inputs)."""
+        the CHAIN auxiliary stream (disjoint outputs, same inputs).
+
+        A 1x1 stride-2 convolution (the downsample branch) reaches output phase (0, 0) only.  ``phase00_only``: the
+        caller promises to read nothing but that phase, so the other three quarters of ``gx`` stay uninitialised
+        instead of being zero-filled; ``addend_phase00`` is the consuming side: ``addend`` holds data in phase (0, 0)
+        only and is treated as zero elsewhere (three of the four phase launches then skip the addend read)."""
         B = g.shape[0]
         s, k = self.stride, self.k
         # a 1x1 stride-2 convolution reaches one of the four output phases only: one contiguous memset instead of
         # three strided fills
         sparse = s > 1 and k == 1 and addend is None
-        gx = torch.zeros((B, h_in, w_in, self.I), device="cuda", dtype=torch.float32) if sparse \
+        gx = torch.zeros((B, h_in, w_in, self.I), device="cuda", dtype=torch.float32) if sparse and not phase00_only \
             else _empty(B, h_in, w_in, self.I)
         two_lanes = s > 1 and k > 1 and streams.enabled()
         if two_lanes:
@@ -134,9 +139,10 @@ class _Unit(object):
                         view.copy_(src if mask_src is None else src * (mask_src[:, ph::s, pw::s] > 0))
                     continue  # (without addend: gx was allocated zero-filled, see above)
                 lane = streams.on_aux(streams.CHAIN) if (two_lanes and ph == 1) else _NullCtx()
+                add = None if (addend_phase00 and s > 1 and (ph, pw) != (0, 0)) else addend
                 with lane:
                     dense.conv_nhwc(g, self.wft, self.I, (dh, dw, None, slot), 1, gx, h_in // s, w_in // s,
-                                    out_strides=strides, out_offset=off, addend=addend, mask_src=mask_src,
+                                    out_strides=strides, out_offset=off, addend=add, mask_src=mask_src,
                                     passes=passes, w_slots=k * k, w_lo=self.wft_lo)
         if two_lanes:
             streams.join(streams.CHAIN)
@@ -317,7 +323,7 @@ class _EncoderFn(torch.autograd.Function):
                 keep.append(g2)
                 streams.fork(streams.CHAIN)
                 with streams.on_aux(streams.CHAIN):
-                    gres = ud.dgrad(g2, h, w_, passes=pb)
+                    gres = ud.dgrad(g2, h, w_, passes=pb, phase00_only=True)
             else:
                 gres = g2
             g1 = u2.dgrad(g2, ho, wo, mask_src=a, passes=pb)
@@ -327,7 +333,7 @@ class _EncoderFn(torch.autograd.Function):
             if ud is not None:
                 streams.join(streams.CHAIN)
             keep.append(gres)
-            g2 = u1.dgrad(g1, h, w_, addend=gres, mask_src=x, passes=pb)
+            g2 = u1.dgrad(g1, h, w_, addend=gres, mask_src=x, passes=pb, addend_phase00=ud is not None)
             if bidx == 4 and _grad_sink is not None:
                 # layer4 and layer3 are done on the WGRAD stream: their flat-buffer range can go on the wire now
                 first = blocks[4][0]                      # layer3.0.conv1

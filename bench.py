@@ -247,8 +247,8 @@ def chamfer_report(peaks, wl):
     """Second half of BASELINE.json's metric ("Chamfer kernel HBM GB/s vs peak"): the fused nearest-neighbour
     kernel at the workload's own shapes and at a large sweep point, on algorithmic bytes (20 B per point: 12 read,
     8 written), plus the backward kernel (the one genuinely HBM-bound piece: 16 B read per point + 12 B written per
-    predicted point).  The fused forward does 200-3300 flop per algorithmic byte, so its bound is the FP32 issue rate
-    (reported as well); the full sweep is profiles/chamfer_sweep_*.json (scripts/bench_chamfer.py)."""
+    predicted point).  The fused forward does 200-3300 flop per algorithmic byte, so its bound is the FP32 pipe (128 lanes
+    per SM and clock; reported as well, next to the issue-slot utilisation); the full sweep is profiles/chamfer_sweep_*.json (scripts/bench_chamfer.py)."""
     from obman_train_b200 import functional as Fb
     hbm = peaks.get("hbm_gbs", 6650.0)
     issue_peak = 148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6
@@ -274,7 +274,10 @@ def chamfer_report(peaks, wl):
         gbs = 20.0 * b * (n + m) / ms / 1e6
         out[tag] = {"B": b, "N": n, "M": m, "ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm,
                     "pairs_per_s": 2.0 * b * n * m / ms * 1e3,
-                    "frac_of_fp32_issue_peak": 2.0 * b * n * m * 7.3 / (ms * 1e-3) / issue_peak}
+                    # per pair: 3 subtractions, 1 multiply, 2 fused multiply-adds = 6 fp32 lane operations (issued two
+                    # at a time as FADD2 / FMUL2 / FFMA2 by nn_packed_kernel) and ~4.75 issue slots in all
+                    "frac_of_fp32_pipe_peak": 2.0 * b * n * m * 6.0 / (ms * 1e-3) / issue_peak,
+                    "frac_of_issue_peak": 2.0 * b * n * m * 4.75 / (ms * 1e-3) / issue_peak}
         # backward: gradient of mean_b(loss_1 + loss_2) w.r.t. the predicted cloud
         xr = x.clone().requires_grad_(True)
         l1, l2 = Fb.chamfer(xr, y)

@@ -232,3 +232,33 @@ def test_nearest_neighbours_propagate_nan_like_torch_min():
     assert torch.isfinite(minx[0]).all() and torch.isfinite(miny[0]).all() and torch.isfinite(minx[2]).all()
     l1, l2 = Fb.chamfer(x, y)
     assert torch.isnan(l1[1]) and torch.isnan(l2[1]) and torch.isfinite(l1[0]) and torch.isfinite(l2[2])
+
+
+def test_packed_and_scalar_search_kernels_agree_bit_for_bit(tmp_path):
+    """The packed fp32x2 nearest-neighbour / ray-triangle kernels (default), their scalar forms and the staged / streamed
+    ray variants evaluate the same operations per pair: distances, arg-mins (ties -> lowest index), NaN propagation and
+    hit counts must be IDENTICAL.  The switches are read once per process, so each variant runs in its own."""
+    import os
+    import subprocess
+    import sys
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "scripts", "dump_search_kernels.py")
+    variants = {"default": {},
+                "scalar": {"OBMAN_NN_PACKED": "0", "OBMAN_RAYCAST_PACKED": "0"},
+                "staged": {"OBMAN_RAYCAST_STREAM": "0"},
+                "staged4": {"OBMAN_RAYCAST_STREAM": "0", "OBMAN_RAYCAST_PT": "4"}}
+    dumps = {}
+    for name, env in variants.items():
+        full_env = dict(os.environ)
+        full_env.update(env)
+        path = str(tmp_path / (name + ".npz"))
+        out = subprocess.run([sys.executable, script, path], env=full_env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and "dumped" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
+        dumps[name] = dict(np.load(path))
+    ref = dumps["scalar"]
+    assert np.isnan(ref["small_minx"][1, 5]) and np.isnan(ref["small_minx"][2]).all() and not np.isnan(ref["small_minx"][0]).any()
+    assert (ref["chamfer_minx"][0, :50] == 0).all()
+    for name, d in dumps.items():
+        for key, val in ref.items():
+            assert np.array_equal(val, d[key], equal_nan=True), (name, key)

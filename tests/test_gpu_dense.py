@@ -27,7 +27,7 @@ def test_dense_case(name):
     assert res["rel"] < tol, res
 
 
-def test_linear_and_point_decoder_autograd_vs_torch():
+def test_linear_autograd_vs_torch():
     import torch
     import torch.nn.functional as F
     from obman_train_b200 import mlp
@@ -122,3 +122,55 @@ def test_alternative_kernel_variants_in_a_subprocess(env):
     full_env.update(env)
     out = subprocess.run([sys.executable, "-c", code], env=full_env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "variants ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("per_sample", [False, True])
+def test_point_decoder_eval_mode_vs_fp64_oracle(per_sample):
+    """PointGenCon in eval mode (the benchmarked configuration) against the fp64 oracle, with the grid shared by the batch
+    (mesh mode, atlasbranch.py:110-150) and per sample (random-points mode, atlasbranch.py:78-108): vertices, every
+    parameter gradient - the grid columns of conv1.weight come out of the fused first-layer backward kernel - and the
+    feature gradient."""
+    import torch
+    from oracle import nets
+    from obman_train_b200.networks.branches.atlasutils import PointGenCon
+    B, N = 5, 300
+    torch.manual_seed(11)
+    dec = PointGenCon(bottleneck_size=515, out_factor=200)
+    g = torch.Generator().manual_seed(12)
+    for bn in (dec.bn1, dec.bn2, dec.bn3):
+        bn.weight.data = 0.5 + torch.rand(bn.weight.shape, generator=g)
+        bn.bias.data = torch.randn(bn.bias.shape, generator=g) * 0.1
+        bn.running_mean.data = torch.randn(bn.running_mean.shape, generator=g) * 0.1
+        bn.running_var.data = 0.5 + torch.rand(bn.running_var.shape, generator=g)
+    dec.eval()
+    grid = torch.randn((B, N, 3) if per_sample else (N, 3), generator=g)
+    grid = grid / grid.norm(dim=-1, keepdim=True)
+    feat = torch.randn(B, 512, generator=g)
+    wts = torch.randn(B, N, 3, generator=g)
+    state = {"d." + k: v.detach().double().clone() for k, v in dec.state_dict().items()}
+    for k, v in state.items():
+        if v.is_floating_point() and "running_" not in k:
+            v.requires_grad_(True)
+    f64 = feat.double().requires_grad_(True)
+    g64 = grid.double() if per_sample else grid.double().unsqueeze(0).expand(B, -1, -1)
+    x = torch.cat([g64.transpose(2, 1), f64.unsqueeze(2).expand(-1, -1, N)], 1)
+    ref = nets.point_decoder(state, x, "d", False, 200).transpose(2, 1)
+    (ref * wts.double()).sum().backward()
+    dec = dec.cuda()
+    fc = feat.cuda().requires_grad_(True)
+    out = dec.decode(fc, grid.cuda())
+    (out * wts.cuda()).sum().backward()
+    rel = ((out.detach().cpu().double() - ref.detach()).abs().max() / ref.abs().max()).item()
+    assert rel < 1e-4, rel
+    worst = []
+    for name, p in dec.named_parameters():
+        gref = state["d." + name].grad.reshape(p.shape)
+        worst.append((((p.grad.cpu().double() - gref).norm() / (gref.norm() + 1e-30)).item(), name))
+    w1 = dec.conv1.weight.grad.cpu().double().reshape(515, 515)
+    r1 = state["d.conv1.weight"].grad.reshape(515, 515)
+    worst.append((((w1[:, :3] - r1[:, :3]).norm() / r1[:, :3].norm()).item(), "conv1.weight[:, grid columns]"))
+    worst.append((((fc.grad.cpu().double() - f64.grad).norm() / f64.grad.norm()).item(), "features"))
+    worst.sort(reverse=True)
+    print("decoder (eval-mode BN, per_sample=%s) output rel err %.2e; worst gradients: %s" % (
+        per_sample, rel, ["%s %.2e" % (n, r) for r, n in worst[:4]]))
+    assert worst[0][0] < 1e-3, worst[:4]

@@ -173,4 +173,7 @@ def test_point_decoder_eval_mode_vs_fp64_oracle(per_sample):
     worst.sort(reverse=True)
     print("decoder (eval-mode BN, per_sample=%s) output rel err %.2e; worst gradients: %s" % (
         per_sample, rel, ["%s %.2e" % (n, r) for r, n in worst[:4]]))
-    assert worst[0][0] < 1e-3, worst[:4]
+    # Bound: a random-init decoder has ~1e-5 of its 0.8 M first-layer pre-activations within the 3xBF16 rounding error of
+    # zero; every such ReLU flip against the fp64 oracle changes one gradient element by its full magnitude (measured
+    # 3.8e-3 in norm on the layer-1 parameters, 2e-5 on the output).  A wrong kernel would be off by O(1).
+    assert worst[0][0] < 1e-2, worst[:4]

@@ -202,3 +202,41 @@ def test_bench_traffic_record_goes_stale_with_the_kernel_sources(tmp_path, monke
     tr, src = bench.traffic_record("bf16x3")
     assert tr is None and "stale" in src
     assert bench.traffic_record("tf32") == (None, None) or bench.traffic_record("tf32")[0] is None
+
+
+def test_ray_triangle_predicate_folding_is_exact_in_fp32():
+    """contact.cu's packed ray / triangle kernels test  min(u, v, 1 - (u + v)) > 0  instead of the reference's
+    (u > 0) & (u < 1) & (v > 0) & (u + v < 1)  (contactutils.py:117-127).  In IEEE fp32 the two are the same predicate for
+    all finite u, v: 1 - s > 0 <=> s < 1 exactly (a difference of two floats is zero only if they are equal and has the
+    right sign), and u < 1 follows from v > 0 and fl(u + v) < 1 because rounding is monotonic.  Checked here on random
+    values, on values within a few ulps of the boundaries and on the boundaries themselves."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    one = np.float32(1.0)
+    parts = [rng.uniform(-0.5, 1.5, 400000).astype(np.float32)]
+    edge = np.array([0.0, 1.0, 0.5, 1e-30, -1e-30, 1e-7, 1.0 - 2.0 ** -24, 1.0 + 2.0 ** -23], dtype=np.float32)
+    for base in edge:   # the value itself and its 8 neighbours on either side
+        parts.append(np.array([base], np.float32))
+        lo, hi = parts[-1].copy(), parts[-1].copy()
+        for _ in range(8):
+            lo = np.nextafter(lo, np.float32(-np.inf))
+            hi = np.nextafter(hi, np.float32(np.inf))
+            parts.append(lo.copy())
+            parts.append(hi.copy())
+    vals = np.concatenate(parts).astype(np.float32)
+    special = vals[-(len(vals) - 400000):]
+    u = np.concatenate([vals[:200000], np.repeat(special, len(special)), rng.choice(special, 50000)])
+    v = np.concatenate([vals[200000:400000], np.tile(special, len(special)), rng.uniform(-0.5, 1.5, 50000).astype(np.float32)])
+    # also pairs that sum to (almost) exactly one
+    u2 = rng.uniform(0, 1, 100000).astype(np.float32)
+    v2 = (one - u2).astype(np.float32)
+    for k in range(3):
+        u = np.concatenate([u, u2])
+        v = np.concatenate([v, np.nextafter(v2, np.float32(np.inf)) if k == 1 else (np.nextafter(v2, np.float32(-np.inf)) if k == 2 else v2)])
+    s = (u + v).astype(np.float32)
+    reference = (u > 0) & (u < 1) & (v > 0) & (s < 1)
+    w = (one - s).astype(np.float32)
+    folded = np.minimum(np.minimum(u, v), w) > 0
+    assert u.dtype == np.float32 and w.dtype == np.float32
+    assert np.array_equal(reference, folded), int((reference != folded).sum())
+    assert reference.any() and (~reference).any()
